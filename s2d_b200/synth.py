@@ -1,0 +1,250 @@
+"""Seeded synthetic videos for the keymask-discovery hot path.
+
+A *scene* is what the reference's per-video loop consumes once the upstream producers
+(CutS3D masks, CoTracker) have run:
+
+  labels  u8  [T, H, W]      per-frame label maps, 0 = background, ids are per-frame
+                             ranks exactly as load_masks() builds them
+                             (keymask_ident/cotracker_matching.py:54-71)
+  tracks  f32 [Nm, T, P, 2]  CoTracker pred_tracks (x, y) of the P points sampled inside mask q,
+                             one row block per (frame, mask) query in global-id order
+                             (cotracker_matching.py:289-306)
+  vis     u8  [Nm, T, P]     CoTracker pred_visibility flags of the same points
+                             (cotracker_occlusions.py:355-359)
+
+The host generator (numpy) is used by tests, golden generation and the CPU baseline; the
+device generator (torch, plumbing only - it is outside every timed region) builds the large
+BASELINE.json configurations directly in HBM.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class Scene:
+    labels: np.ndarray            # u8 [T,H,W]
+    tracks: np.ndarray            # f32 [Nm,T,P,2]
+    vis: np.ndarray               # u8 [Nm,T,P]
+    query_frame: np.ndarray       # i32 [Nm]
+    query_label: np.ndarray       # i32 [Nm]
+    object_of_query: np.ndarray   # i32 [Nm] (generator bookkeeping, not an input of the path)
+    colors: np.ndarray = field(default=None)  # u8 [K,3] palette used when written as colour PNGs
+
+    @property
+    def shape(self):
+        T, H, W = self.labels.shape
+        return T, H, W, self.tracks.shape[0], self.tracks.shape[2]
+
+
+def enumerate_queries(labels: np.ndarray):
+    """(frame, label) pairs in global-id order: per frame the sorted unique labels minus the
+    smallest one (cotracker_matching.py:294 - the [1:] drops the first unique value even when
+    it is not background)."""
+    qf, ql = [], []
+    for t in range(labels.shape[0]):
+        ids = np.unique(labels[t])[1:]
+        for o in ids:
+            qf.append(t)
+            ql.append(int(o))
+    return np.asarray(qf, np.int32), np.asarray(ql, np.int32)
+
+
+def _paint(T, H, W, objs, rng, occluded_obj, occl_span, full_cover_frames):
+    """Paint object index maps [T,H,W] (int16, -1 background) with later objects on top."""
+    yy, xx = np.mgrid[0:H, 0:W]
+    omap = np.full((T, H, W), -1, np.int16)
+    for t in range(T):
+        if t in full_cover_frames:
+            # no background pixel in this frame: vertical stripes of the objects
+            k = len(objs)
+            omap[t] = (xx * k // W).astype(np.int16)
+            continue
+        for k, o in enumerate(objs):
+            if k == occluded_obj and occl_span[0] <= t < occl_span[1]:
+                continue
+            cx = o["cx"] + o["vx"] * t
+            cy = o["cy"] + o["vy"] * t
+            if o["ellipse"]:
+                m = ((xx - cx) / o["rx"]) ** 2 + ((yy - cy) / o["ry"]) ** 2 <= 1.0
+            else:
+                m = (np.abs(xx - cx) <= o["rx"]) & (np.abs(yy - cy) <= o["ry"])
+            omap[t][m] = k
+    return omap
+
+
+def make_scene(seed: int, T: int, H: int, W: int, M: int, P: int, *, occlude: bool = True,
+               full_cover_frames=(), specials: bool = False, noise: float = 0.7,
+               dup_rate: float = 0.0) -> Scene:
+    """M moving rectangles/ellipses; object 0 is absent for the middle third of the video so
+    that at least two visibility clusters appear. `specials` injects NaN/inf, half-integer and
+    out-of-range coordinates; `dup_rate` forces exact duplicate points."""
+    rng = np.random.default_rng(seed)
+    objs = []
+    for k in range(M):
+        rx = rng.uniform(0.05, 0.12) * W
+        ry = rng.uniform(0.06, 0.14) * H
+        objs.append(dict(cx=rng.uniform(rx, W - rx), cy=rng.uniform(ry, H - ry), rx=rx, ry=ry,
+                         vx=rng.uniform(-0.006, 0.006) * W, vy=rng.uniform(-0.006, 0.006) * H,
+                         ellipse=bool(k % 2)))
+    occl_span = (T // 3, (2 * T) // 3) if occlude else (0, 0)
+    omap = _paint(T, H, W, objs, rng, 0 if occlude else -1, occl_span, set(full_cover_frames))
+
+    # per-frame rank labels (what load_masks produces from the colour PNGs)
+    labels = np.zeros((T, H, W), np.uint8)
+    present = []
+    for t in range(T):
+        ks = np.unique(omap[t])
+        ks = ks[ks >= 0]
+        present.append(ks)
+        lut = np.zeros(M + 1, np.uint8)
+        lut[ks + 1] = np.arange(1, len(ks) + 1, dtype=np.uint8)
+        labels[t] = lut[omap[t].astype(np.int32) + 1]
+    area = np.zeros((T, M), np.int64)
+    for t in range(T):
+        for k in present[t]:
+            area[t, k] = int((omap[t] == k).sum())
+
+    qf, ql = enumerate_queries(labels)
+    Nm = len(qf)
+    tracks = np.empty((Nm, T, P, 2), np.float32)
+    vis = np.empty((Nm, T, P), np.uint8)
+    obj_of_q = np.empty(Nm, np.int32)
+    dts = np.arange(T, dtype=np.float64)
+    for q in range(Nm):
+        t, lab = int(qf[q]), int(ql[q])
+        ys, xs = np.nonzero(labels[t] == lab)
+        k = int(omap[t][ys[0], xs[0]])
+        obj_of_q[q] = k
+        sel = rng.integers(0, len(ys), size=P)
+        if dup_rate > 0:
+            ndup = int(P * dup_rate)
+            sel[P - ndup:] = sel[:ndup]
+        jit = rng.uniform(-0.4, 0.4, size=(P, 2)) if dup_rate == 0 else np.zeros((P, 2))
+        px = xs[sel] + jit[:, 0]
+        py = ys[sel] + jit[:, 1]
+        o = objs[k]
+        dx = o["vx"] * (dts - t)
+        dy = o["vy"] * (dts - t)
+        nz = rng.normal(0.0, noise, size=(T, P, 2)) if noise > 0 else np.zeros((T, P, 2))
+        nz[t] = 0.0
+        tracks[q, :, :, 0] = (px[None, :] + dx[:, None] + nz[..., 0]).astype(np.float32)
+        tracks[q, :, :, 1] = (py[None, :] + dy[:, None] + nz[..., 1]).astype(np.float32)
+        pvis = np.where(area[:, k] > 0, 0.95, 0.05)
+        vis[q] = (rng.random((T, P)) < pvis[:, None]).astype(np.uint8)
+    if specials and Nm > 0:
+        # NaN/inf -> INT64_MIN -> dropped; x.5 -> round-half-even; W-0.5 -> W -> dropped
+        # (cotracker_matching.py:472-479)
+        n = max(1, P // 16)
+        for q in range(Nm):
+            tt = rng.integers(0, T, size=n)
+            pp = rng.integers(0, P, size=n)
+            vals = rng.choice(np.asarray([np.nan, np.inf, -np.inf, W - 0.5, -0.5, 0.5, 1.5, 2.5,
+                                          -0.49, 1e20, -3e9, H - 0.5], np.float32), size=n)
+            cc = rng.integers(0, 2, size=n)
+            tracks[q, tt, pp, cc] = vals
+    palette = np.zeros((M, 3), np.uint8)
+    for k in range(M):  # strictly increasing lexicographically -> rank order == object order
+        palette[k] = (10 + 2 * k, (37 * k + 11) % 256, (91 * k + 5) % 256)
+    return Scene(labels, tracks, vis, qf, ql, obj_of_q, palette)
+
+
+def scene_object_map(scene: Scene) -> np.ndarray:
+    """Recover per-pixel palette indices [T,H,W] (-1 background) for writing colour PNGs."""
+    T, H, W = scene.labels.shape
+    omap = np.full((T, H, W), -1, np.int16)
+    for q in range(len(scene.query_frame)):
+        t, lab = int(scene.query_frame[q]), int(scene.query_label[q])
+        omap[t][scene.labels[t] == lab] = scene.object_of_query[q]
+    # the dropped (smallest) label of frames without background is not a query: recover it
+    for t in range(T):
+        ids = np.unique(scene.labels[t])
+        if ids[0] != 0:
+            # stripes frame: object index == label-1 by construction
+            omap[t][scene.labels[t] == ids[0]] = int(ids[0]) - 1
+    return omap
+
+
+# --------------------------------------------------------------------------------------
+# Device-side generator for the BASELINE.json-sized configurations (torch = plumbing only)
+# --------------------------------------------------------------------------------------
+
+def make_scene_device(seed: int, T: int, H: int, W: int, M: int, P: int, device, *,
+                      noise: float = 0.7, occlude: bool = True):
+    """Same scene family as make_scene, built directly in HBM with torch ops.
+
+    Returns dict(labels u8 [T,H,W], tracks f32 [Nm,T,P,2], vis u8 [Nm,T,P],
+    query_frame i32 [Nm], query_label i32 [Nm]). Background is always present, every object
+    keeps a visible pixel (objects are painted small enough and re-checked on the host for
+    the tiny per-frame presence table only)."""
+    import torch
+
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    u = lambda lo, hi, n: torch.rand(n, generator=g, dtype=torch.float64) * (hi - lo) + lo
+    rx = u(0.05, 0.12, M) * W
+    ry = u(0.06, 0.14, M) * H
+    cx = rx + torch.rand(M, generator=g, dtype=torch.float64) * (W - 2 * rx)
+    cy = ry + torch.rand(M, generator=g, dtype=torch.float64) * (H - 2 * ry)
+    vx = u(-0.006, 0.006, M) * W
+    vy = u(-0.006, 0.006, M) * H
+    occl = (T // 3, (2 * T) // 3) if occlude else (0, 0)
+
+    yy = torch.arange(H, device=device, dtype=torch.float32)[:, None]
+    xx = torch.arange(W, device=device, dtype=torch.float32)[None, :]
+    omap = torch.full((T, H, W), -1, dtype=torch.int16, device=device)
+    for t in range(T):
+        for k in range(M):
+            if k == 0 and occl[0] <= t < occl[1]:
+                continue
+            ccx = float(cx[k] + vx[k] * t)
+            ccy = float(cy[k] + vy[k] * t)
+            if k % 2:
+                m = ((xx - ccx) / float(rx[k])) ** 2 + ((yy - ccy) / float(ry[k])) ** 2 <= 1.0
+            else:
+                m = ((xx - ccx).abs() <= float(rx[k])) & ((yy - ccy).abs() <= float(ry[k]))
+            omap[t][m] = k
+    # presence [T,M] and rank labels
+    onehot_cnt = torch.zeros((T, M + 1), dtype=torch.int64, device=device)
+    onehot_cnt.scatter_add_(1, (omap.reshape(T, -1).long() + 1),
+                            torch.ones((T, H * W), dtype=torch.int64, device=device))
+    area = onehot_cnt[:, 1:]                                   # [T,M]
+    pres = area > 0
+    rank = torch.cumsum(pres.long(), dim=1) * pres.long()      # 1-based rank among present
+    lut = torch.cat([torch.zeros((T, 1), dtype=torch.long, device=device), rank], dim=1)
+    labels = torch.gather(lut, 1, omap.reshape(T, -1).long() + 1).reshape(T, H, W).to(torch.uint8)
+
+    pres_h = pres.cpu()
+    rank_h = rank.cpu()
+    qf, ql, qk = [], [], []
+    for t in range(T):
+        for k in range(M):
+            if pres_h[t, k]:
+                qf.append(t); ql.append(int(rank_h[t, k])); qk.append(k)
+    Nm = len(qf)
+    qf_t = torch.tensor(qf, dtype=torch.int32, device=device)
+    ql_t = torch.tensor(ql, dtype=torch.int32, device=device)
+    qk_t = torch.tensor(qk, dtype=torch.long, device=device)
+
+    dg = torch.Generator(device=device)
+    dg.manual_seed(seed * 7919 + 13)
+    tracks = torch.empty((Nm, T, P, 2), dtype=torch.float32, device=device)
+    vis = torch.empty((Nm, T, P), dtype=torch.uint8, device=device)
+    vx_d = vx.to(device=device, dtype=torch.float32)
+    vy_d = vy.to(device=device, dtype=torch.float32)
+    dts = torch.arange(T, device=device, dtype=torch.float32)
+    pvis_obj = torch.where(pres, 0.95, 0.05).to(torch.float32)  # [T,M]
+    for q in range(Nm):
+        t, lab, k = qf[q], ql[q], qk[q]
+        idx = torch.nonzero(labels[t].reshape(-1) == lab).squeeze(1)
+        sel = idx[torch.randint(0, idx.numel(), (P,), generator=dg, device=device)]
+        px = (sel % W).float() + (torch.rand(P, generator=dg, device=device) - 0.5) * 0.8
+        py = (sel // W).float() + (torch.rand(P, generator=dg, device=device) - 0.5) * 0.8
+        nz = torch.randn((T, P, 2), generator=dg, device=device) * noise
+        nz[t] = 0
+        tracks[q, :, :, 0] = px[None, :] + (vx_d[k] * (dts - t))[:, None] + nz[..., 0]
+        tracks[q, :, :, 1] = py[None, :] + (vy_d[k] * (dts - t))[:, None] + nz[..., 1]
+        vis[q] = (torch.rand((T, P), generator=dg, device=device) < pvis_obj[:, k][:, None]).to(torch.uint8)
+    return dict(labels=labels, tracks=tracks, vis=vis, query_frame=qf_t, query_label=ql_t)

@@ -1,0 +1,55 @@
+"""The CPU restatement (oracle/keymask_oracle.py) against fixtures produced by the unmodified
+reference (oracle/make_golden.py). Runs without a GPU and without /root/reference."""
+import numpy as np
+import pytest
+
+from oracle import keymask_oracle as ko
+from oracle.compare import check_against_golden
+
+
+def test_oracle_matches_reference_golden(golden_case):
+    name, g, labels, tracks, vis = golden_case
+    res = ko.discover(labels, tracks, vis, g["visibility_threshold"], g["matching_threshold"])
+    check_against_golden(res, g)
+
+
+def test_candidate_files_match(golden_case):
+    name, g, labels, tracks, vis = golden_case
+    res = ko.discover(labels, tracks, vis, g["visibility_threshold"], g["matching_threshold"])
+    files = sorted(f"{folder}/cluster{idx}_frame{f}_mask{m}.png"
+                   for folder, idx, cands in ko.lexsorted_cluster_folders(res["clusters"]) for f, m in cands)
+    assert files == g["candidate_files"]
+    if g["status"] == 1:
+        gf = sorted(f"cluster_{gr['cluster_id']}/group_{lab}/frame{f}_mask{m}.png"
+                    for gr in res["groupings"] for lab, fms in gr["overall_mask_ids_per_label"].items()
+                    for f, m in fms)
+        assert gf == g["group_files"]
+
+
+def test_tracker_requests_match(golden_case):
+    """grid size heuristic and backward_tracking flag of the stage-D tracker request
+    (cotracker_matching.py:1064-1073)."""
+    name, g, labels, tracks, vis = golden_case
+    if g["status"] != 1:
+        pytest.skip("video fails in the reference")
+    res = ko.discover(labels, tracks, vis, g["visibility_threshold"], g["matching_threshold"])
+    nm = len(res["query_frame"])
+    stage_d = g["tracker_calls"][nm:]
+    got = [[q["frame_id"], q["mask_id"], q["grid_size"], bool(q["backward_tracking"])] for q in res["queries"]]
+    assert got == [[c[0], c[1], c[2], bool(c[3])] for c in stage_d]
+
+
+@pytest.mark.parametrize("eps,ms", [(0.2, 5), (0.1, 5), (0.1, 3), (0.05, 5)])
+def test_dbscan_restatement_vs_sklearn(eps, ms):
+    from sklearn.cluster import DBSCAN
+    rng = np.random.default_rng(7)
+    for it in range(60):
+        n = int(rng.integers(1, 60))
+        d = int(rng.integers(1, 70))
+        base = rng.random((int(rng.integers(1, 5)), d)) < 0.5
+        X = base[rng.integers(0, len(base), n)] ^ (rng.random((n, d)) < rng.choice([0.0, 0.03, 0.1]))
+        if it % 3 == 0:
+            X[rng.integers(0, n, max(1, n // 4))] = False
+        for arr in (X, X.astype(np.float32)):
+            ref = DBSCAN(eps=eps, min_samples=ms, metric="hamming").fit(arr).labels_
+            assert np.array_equal(ref, ko.dbscan_hamming(arr, eps, ms)), (it, n, d)
