@@ -1,0 +1,180 @@
+/* s2d_b200 - C ABI of the B200-native keymask-discovery hot path.
+ *
+ * Drop-in boundary for the arithmetic underneath the reference's per-video loop
+ * (leonsick/s2d keymask_ident/main_keymask_ident.py:81-139). The reference has no FFI of its own
+ * (it is pure Python); each entry point below names the reference code it replaces. A Python
+ * maintainer binds these with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; s2d_last_error() gives the message
+ *     (thread-local). No exceptions cross the boundary, nothing is allocated inside: all
+ *     buffers are caller-owned DEVICE pointers unless the name says `host`.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs.
+ *   - work is batched over videos: `descs` is a DEVICE array of `nvideos` s2d_video_desc that
+ *     places each video inside the batch-wide buffers (layout below). Videos may differ in every
+ *     dimension.
+ *
+ * Inputs are referenced per video by absolute device pointers in the descriptor (the producer's
+ * own buffers: nothing is concatenated or copied). Workspace and outputs are batch-wide buffers;
+ * the descriptor holds each video's element offset into them:
+ *   per-(row,frame) arrays  [Nm][T]   cnt i32, V f32, uniq i32                @ vt_off
+ *   hits     i32  [Nm][T][L]                                                  @ hits_off
+ *   xbits / winbits / majbits / rsbits / rebits   u32 [Nm][TW]                @ xbits_off
+ *   mbits    u32  [Nm][NW]            match matrix rows (bit g = target gid)  @ mbits_off
+ *   per-row arrays [row0 + q]         qframe, qlabel, labels1, rowinfo (int4), one2x, glabel ...
+ *   per-frame arrays [frame0 + t]     area i32 [256], gid_of i32 [256], frameinfo (int4)
+ *   per-video arrays [v]              vidinfo i32 [S2D_VIDINFO_WORDS]
+ *   per-(video,cluster) arrays        [v][S2D_MAX_CLUSTERS] clusterinfo i32 [S2D_CLINFO_WORDS]
+ */
+#ifndef S2D_B200_H
+#define S2D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2D_MAX_LABELS 256      /* label ids are u8 */
+#define S2D_MAX_CLUSTERS 16     /* visibility clusters carried into stage D (>=11 fails the video) */
+#define S2D_VIDINFO_WORDS 8
+#define S2D_CLINFO_WORDS 16
+
+typedef struct s2d_video_desc {
+    int32_t T, H, W, P;
+    int32_t Nm;          /* rows = (frame,label) queries of this video                      */
+    int32_t L;           /* histogram bins kept per (q,t): max label + 1, <= 256            */
+    int32_t TW;          /* words per frame-bit row  = ceil(T / 32)                         */
+    int32_t NW;          /* words per match-bit row  = ceil(Nm / 32)                        */
+    int64_t row0;        /* first row in batch-wide per-row arrays                          */
+    int64_t frame0;      /* first frame in batch-wide per-frame arrays                      */
+    const uint8_t* labels;  /* device, u8  [T][H][W]      label maps, 0 = background          */
+    const float*   tracks;  /* device, f32 [Nm][T][P][2]  CoTracker pred_tracks (x, y)        */
+    const uint8_t* vis;     /* device, u8  [Nm][T][P]     CoTracker pred_visibility bytes     */
+    const int32_t* npts;    /* device, i32 [Nm] valid points per query (<= P) or NULL = all P  */
+    int64_t vt_off;      /* elements of [Nm][T] arrays                                       */
+    int64_t hits_off;    /* int32 elements                                                   */
+    int64_t xbits_off;   /* u32 words of [Nm][TW] arrays                                     */
+    int64_t mbits_off;   /* u32 words of [Nm][NW] arrays                                     */
+} s2d_video_desc;
+
+/* rowinfo int4: x = visibility cluster id (-1 noise), y = candidate run index (-1 = not a
+ * candidate), z = v0, w = v1 (merged window of the cluster, cotracker_matching.py:1033-1038) */
+/* frameinfo int4: x = number of objects (present labels minus the smallest), y = first gid of
+ * the frame, z = smallest present label (dropped, cotracker_matching.py:294), w = #present   */
+/* vidinfo: [0] nclusters (DBSCAN #1), [1] status after stage B (1 ok, -1 fail),
+ *          [2] max matched gid (cotracker_matching.py:770-773), [3] final status (1 / -1),
+ *          [4] number of candidate queries, [5] number of rows (check)                     */
+/* clusterinfo: [0] size, [1] #candidates, [2] v0, [3] v1, [4] #runs, [5] row_min, [6] row_max,
+ *          [7] col_min, [8] col_max, [9] kmax, [10] min_samples, [11] factor,
+ *          [12] matched rows (coverage numerator), [13] one2x sum over queries, [14] #queries */
+
+const char* s2d_last_error(void);
+int s2d_version(void);
+int s2d_desc_size(void);            /* sizeof(s2d_video_desc), for binding self-checks */
+int s2d_device_sm_count(int device);
+
+/* All `max_*` / `total_*` arguments are host-side bounds over the batch (grid sizing and memset
+ * extents): max_T = max frames, max_npix = max H*W, max_rows_x_T = max Nm*T, total_rows = sum Nm,
+ * total_frames = sum T, total_vt = sum Nm*T ... */
+
+/* K0. Per-frame label histogram + object enumeration + global ids.
+ * Replaces torch.unique(label[t])[1:] (cotracker_occlusions.py:337-338, cotracker_matching.py:
+ * 294-295, 682-683) and contruct_frameid_maskid_lookup (cotracker_matching.py:289-306).
+ * Outputs area[frame][256], gid_of[frame][256] (-1 = not an object), frameinfo[frame] (int4),
+ * qframe/qlabel[row]; vidinfo[5] receives the enumerated row count (must equal desc.Nm). */
+int s2d_label_stats(const s2d_video_desc* descs, int nvideos, int max_T, int64_t max_npix,
+                    int64_t total_frames, int32_t* area, int32_t* gid_of,
+                    int32_t* frameinfo, int32_t* qframe, int32_t* qlabel, int32_t* vidinfo,
+                    void* stream);
+
+/* K3a. Visibility reduce: cnt[q,t] = #nonzero flags, V = float32(cnt) / float32(P) (IEEE
+ * division), replaces torch.mean(pred_visibility.float(), dim=2) (cotracker_occlusions.py:359). */
+int s2d_vis_reduce(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_T,
+                   int32_t* cnt, float* V, void* stream);
+
+/* K3 binarise: xbits[row] bit t = V[row,t] > thr (float32 compare,
+ * identify_visibility_windows.py:114,119). */
+int s2d_binarize(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_TW, const float* V,
+                 float visibility_threshold, uint32_t* xbits, void* stream);
+
+/* K3b. Hamming DBSCAN #1 over the rows of xbits, eps 0.2 / min_samples 5 in the reference
+ * (identify_visibility_windows.py:114; sklearn.cluster.DBSCAN(metric="hamming")).
+ * work: int32 scratch of s2d_dbscan_work_ints(total_rows, nvideos) elements, 8-byte aligned.
+ * labels1[row] = cluster id or -1; vidinfo[0] = number of clusters. */
+int s2d_dbscan_work_ints(int64_t total_rows, int nproblems, int64_t* out);
+int s2d_dbscan_visibility(const s2d_video_desc* descs, int nvideos, int max_Nm, int max_TW,
+                          int64_t total_rows, const uint32_t* xbits, double eps, int min_samples,
+                          int32_t* work, int32_t* labels1, int32_t* vidinfo, void* stream);
+
+/* K3c. Majority vote, run-length windows, highly-visible rows, candidates
+ * (identify_visibility_windows.py:134-203; get_visible_ranges :65-88;
+ * get_highly_visible_rows :90-105). Per cluster c (slot c of the video's [Nm][TW] arrays):
+ * majbits, rsbits (run starts), rebits (run ends); clrow[row0+c] int4 = (size, #runs, v0, v1).
+ * Per row: winbits (bit r = winner of run r), rowinfo. Per video: vidinfo[1..4], clusterinfo
+ * for the first S2D_MAX_CLUSTERS clusters. ccount: int32 scratch [Nm][T] @ vt_off. T <= 1024. */
+int s2d_windows(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_TW, int max_TW,
+                int64_t total_rows, int64_t total_vt, const uint32_t* xbits,
+                const int32_t* labels1, const int32_t* qframe, float winner_fraction,
+                int32_t* ccount, int32_t* clrow, uint32_t* majbits, uint32_t* rsbits,
+                uint32_t* rebits, uint32_t* winbits, int32_t* rowinfo, int32_t* vidinfo,
+                int32_t* clusterinfo, void* stream);
+
+/* K2. Point-in-mask voting for every candidate query q and every frame t of its window:
+ *   uniq[q,t]      = # distinct in-bounds pixels of round-half-even(tracks[q,t])
+ *   hits[q,t,lab]  = # of those pixels whose label is lab
+ * Replaces pred_tracks_to_binary_masks + compute_point_mask_intersection for all masks of the
+ * frame (cotracker_matching.py:453-503, 640-662, 665-692). Rows whose rowinfo.y < 0, frames
+ * outside [v0,v1] and videos whose vidinfo[1] < 0 are skipped (hits/uniq left untouched).
+ * rowinfo == NULL votes every (q,t); vidinfo == NULL ignores the stage-B status.
+ * vec4_ok != 0 promises P even and 16-byte aligned tracks for every video (128-bit loads).
+ * H, W <= 65535; P <= 32768. */
+int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_T, int max_P,
+                    int vec4_ok, const int32_t* rowinfo, const int32_t* vidinfo, int32_t* hits,
+                    int32_t* uniq, void* stream);
+
+/* K4a. Scores and selection per candidate query: iou = hits/uniq (double), match bit when
+ * iou > matching_threshold (cotracker_matching.py:710), one-to-many flag when >= one2x_frames
+ * frames hold more than one mask with iou > one2x_iou (cotracker_matching.py:1082-1111).
+ * mbits is cleared inside. Maintains vidinfo[2] (max matched gid, matching.py:770-773). */
+int s2d_select(const s2d_video_desc* descs, int nvideos, int max_Nm, int64_t total_mbits_words,
+               const int32_t* hits, const int32_t* uniq, const int32_t* gid_of,
+               const int32_t* rowinfo, double matching_threshold, double one2x_iou,
+               int one2x_frames, uint32_t* mbits, int32_t* one2x, int32_t* nmatch,
+               int32_t* vidinfo, void* stream);
+
+/* K4b. Temporal-correspondence grouping: per visibility cluster crop the match matrix to its
+ * bounding box, Hamming DBSCAN #2 with the reference's eps/min_samples table, zero rows -> -1,
+ * factor, coverage and one2x sums (cotracker_matching.py:764-840, 843-921).
+ * work: int32 scratch of s2d_group_work_ints(total_rows, nvideos) elements, 8-byte aligned.
+ * glabel[row] = group label or -1; grp_n / grp_one2x: int32 [16*total_rows], slot
+ * 16*row0 + c*Nm + label = rows / one2x sum of that group; vidinfo[3] = final status. */
+int s2d_group_work_ints(int64_t total_rows, int nvideos, int64_t* out);
+int s2d_group(const s2d_video_desc* descs, int nvideos, int max_Nm, int max_NW, int64_t total_rows,
+              const uint32_t* mbits, const int32_t* rowinfo, const int32_t* one2x, int32_t* work,
+              int32_t* glabel, int32_t* grp_n, int32_t* grp_one2x, int32_t* vidinfo,
+              int32_t* clusterinfo, void* stream);
+
+/* Generic Hamming DBSCAN on one bit matrix (device), N rows of `stride` words, D columns
+ * (padding bits must be zero). work: s2d_dbscan_work_ints(N, 1) int32, 8-byte aligned. */
+int s2d_hamming_dbscan(const uint32_t* bits, int N, int stride, int D, double eps,
+                       int min_samples, int32_t* work, int32_t* labels, void* stream);
+
+/* K1. Dense mask-overlap contraction (cotracker_matching.py:653-657 for point-raster x mask;
+ * model_training/mask2former_video/engine/train_loop.py:378-388 for mask x mask):
+ *   I[a,b] = sum_px (A[a,px] != 0) * (B[b,px] != 0),  areaA[a], areaB[b]
+ * _bits: operands bit-packed ([N][ceil(npix/32)] u32), AND + popc on CUDA cores.
+ * _i8  : operands u8 0/1 ([N][npix]), tcgen05.mma kind::i8, int32 accumulators in TMEM. */
+int s2d_pack_bits(const uint8_t* planes, int N, int64_t npix, uint32_t* bits, void* stream);
+int s2d_overlap_bits(const uint32_t* Abits, int Na, const uint32_t* Bbits, int Nb, int64_t nwords,
+                     int32_t* I, int32_t* areaA, int32_t* areaB, void* stream);
+
+/* Rasterise tracks of one query into a u8 plane per frame (pred_tracks_to_binary_masks,
+ * return_mask=False, cotracker_matching.py:453-503) - the dense A operand of K1. */
+int s2d_rasterise_tracks(const float* tracks, int T, int P, int H, int W, uint8_t* planes,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2D_B200_H */

@@ -1,0 +1,261 @@
+// Batched Hamming DBSCAN: XOR + popc neighbour tests on bit rows, lock-free union-find over the
+// core-core graph (root = lowest core index of the component, which is exactly the order in
+// which sklearn's sequential expansion numbers clusters), border rows take the minimum label
+// among their core neighbours.
+#include "dbscan.cuh"
+
+#include <limits.h>
+
+namespace s2d {
+
+constexpr int DB_THREADS = 256;
+constexpr int DB_ROWS_I = 32;     // rows i per CTA: 8 warps x 4 rows
+constexpr int DB_NWC = 64;        // word chunk staged in shared memory
+
+__device__ __forceinline__ int uf_find(int32_t* parent, int i) {
+    while (true) {
+        int p = parent[i];
+        if (p == i) return i;
+        int gp = parent[p];
+        if (gp != p) parent[i] = gp;   // path halving (benign race)
+        i = p;
+    }
+}
+
+// hook the larger root under the smaller one: the root of a component is its minimum index
+__device__ __forceinline__ void uf_unite(int32_t* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        if (atomicCAS(&parent[a], a, b) == a) return;
+    }
+}
+
+template <int MODE>   // 0: neighbour counts -> core   1: unions   2: border -> min core root
+__global__ void __launch_bounds__(DB_THREADS) db_pass_kernel(const DbProblem* __restrict__ problems) {
+    const DbProblem p = problems[blockIdx.y];
+    const int N = p.N;
+    const int i0 = blockIdx.x * DB_ROWS_I;
+    if (i0 >= N) return;
+
+    __shared__ uint32_t xi[DB_ROWS_I][DB_NWC];
+    __shared__ uint32_t xjT[DB_NWC][33];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int irow[4];
+    bool icore[4];
+    int acc[4];   // MODE0: neighbour count; MODE2: min root
+    bool mine = false;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        irow[r] = i0 + warp * 4 + r;
+        icore[r] = false;
+        acc[r] = (MODE == 2) ? INT_MAX : 0;
+        if (MODE != 0 && irow[r] < N) icore[r] = p.core[irow[r]] != 0;
+        if (irow[r] < N) mine |= (MODE == 1) ? icore[r] : (MODE == 2 ? !icore[r] : true);
+    }
+    if (!__syncthreads_or(mine)) return;   // CTA-uniform: nothing to do for these 32 rows
+
+    const int jend = (MODE == 1) ? min(N, i0 + DB_ROWS_I) : N;   // unions only need j < i
+    const bool single_chunk = p.nw <= DB_NWC;
+    for (int j0 = 0; j0 < jend; j0 += 32) {
+        int dist[4] = {0, 0, 0, 0};
+        for (int c0 = 0; c0 < p.nw; c0 += DB_NWC) {
+            const int cw = min(DB_NWC, p.nw - c0);
+            __syncthreads();
+            if (!(single_chunk && j0 > 0)) {
+                for (int idx = tid; idx < DB_ROWS_I * cw; idx += DB_THREADS) {
+                    const int r = idx / cw, w = idx - r * cw, row = i0 + r;
+                    uint32_t v = 0;
+                    if (row < N && (!p.valid || p.valid[row])) v = p.bits[(int64_t)row * p.stride + p.w0 + c0 + w];
+                    xi[r][w] = v;
+                }
+            }
+            for (int idx = tid; idx < 32 * cw; idx += DB_THREADS) {
+                const int r = idx / cw, w = idx - r * cw, row = j0 + r;
+                uint32_t v = 0;
+                if (row < N && (!p.valid || p.valid[row])) v = p.bits[(int64_t)row * p.stride + p.w0 + c0 + w];
+                xjT[w][r] = v;
+            }
+            __syncthreads();
+            for (int w = 0; w < cw; ++w) {
+                const uint32_t xj = xjT[w][lane];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) dist[r] += __popc(xi[warp * 4 + r][w] ^ xj);
+            }
+        }
+        const int j = j0 + lane;
+        const bool jv = j < N;
+        bool jcore = false;
+        if (MODE != 0 && jv) jcore = p.core[j] != 0;
+        int jroot = INT_MAX;
+        if (MODE == 2 && jcore) jroot = uf_find(p.parent, j);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const bool nb = jv && irow[r] < N && dist[r] <= p.kmax;
+            if (MODE == 0) {
+                acc[r] += __popc(__ballot_sync(0xffffffffu, nb));
+            } else if (MODE == 1) {
+                if (nb && icore[r] && jcore && j < irow[r]) uf_unite(p.parent, irow[r], j);
+            } else {
+                const int cand = (nb && !icore[r] && jcore) ? jroot : INT_MAX;
+                acc[r] = min(acc[r], __reduce_min_sync(0xffffffffu, cand));
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (irow[r] >= N) continue;
+            if (MODE == 0) {
+                p.core[irow[r]] = acc[r] >= p.min_samples;
+                p.parent[irow[r]] = irow[r];
+            } else if (MODE == 2) {
+                if (!icore[r]) p.aux[irow[r]] = acc[r];
+            }
+        }
+    }
+}
+
+// cluster numbering by ascending root index + final labels; one CTA per problem
+__global__ void __launch_bounds__(1024) db_label_kernel(const DbProblem* __restrict__ problems) {
+    const DbProblem p = problems[blockIdx.x];
+    const int N = p.N, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __shared__ int wsum[32];
+    __shared__ int running;
+    if (tid == 0) running = 0;
+    for (int i = tid; i < N; i += 1024)
+        if (p.core[i]) p.aux[i] = uf_find(p.parent, i);
+    __syncthreads();
+    for (int base = 0; base < N; base += 1024) {
+        const int i = base + tid;
+        const bool flag = i < N && p.core[i] && p.aux[i] == i;
+        const uint32_t b = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) wsum[warp] = __popc(b);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int s = wsum[w];
+            if (w < warp) before += s;
+            total += s;
+        }
+        const int pos = running + before + __popc(b & ((1u << lane) - 1u));
+        if (flag) p.parent[i] = pos;     // parent[] of a root now holds its cluster id
+        __syncthreads();
+        if (tid == 0) running += total;
+        __syncthreads();
+    }
+    for (int i = tid; i < N; i += 1024) {
+        const int a = p.aux[i];
+        int lab = -1;
+        if (p.core[i] || a != INT_MAX) lab = p.parent[a];
+        p.labels[i] = lab;
+    }
+    if (tid == 0 && p.nclusters) *p.nclusters = running;
+}
+
+int launch_dbscan(const DbProblem* problems, int nproblems, int max_N, int max_nw, cudaStream_t st) {
+    (void)max_nw;
+    if (nproblems <= 0 || max_N <= 0) return 0;
+    dim3 grid((max_N + DB_ROWS_I - 1) / DB_ROWS_I, nproblems);
+    db_pass_kernel<0><<<grid, DB_THREADS, 0, st>>>(problems);
+    S2D_CHECK_LAUNCH("db_pass_kernel<0>");
+    db_pass_kernel<1><<<grid, DB_THREADS, 0, st>>>(problems);
+    S2D_CHECK_LAUNCH("db_pass_kernel<1>");
+    db_pass_kernel<2><<<grid, DB_THREADS, 0, st>>>(problems);
+    S2D_CHECK_LAUNCH("db_pass_kernel<2>");
+    db_label_kernel<<<nproblems, 1024, 0, st>>>(problems);
+    S2D_CHECK_LAUNCH("db_label_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void db1_setup_kernel(const s2d_video_desc* __restrict__ descs, int nvideos,
+                                 const uint32_t* __restrict__ xbits, double eps, int min_samples,
+                                 int32_t* __restrict__ work, int32_t* __restrict__ labels1,
+                                 int32_t* __restrict__ vidinfo, DbProblem* __restrict__ problems) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvideos) return;
+    const s2d_video_desc d = descs[v];
+    DbProblem p;
+    p.bits = xbits + d.xbits_off;
+    p.valid = nullptr;
+    p.core = work + 3 * d.row0;
+    p.parent = p.core + d.Nm;
+    p.aux = p.parent + d.Nm;
+    p.labels = labels1 + d.row0;
+    p.nclusters = vidinfo + (int64_t)v * S2D_VIDINFO_WORDS + 0;
+    p.stride = d.TW;
+    p.w0 = 0;
+    p.nw = d.TW;
+    p.N = d.Nm;
+    p.kmax = hamming_kmax(d.T, eps);
+    p.min_samples = min_samples;
+    problems[v] = p;
+}
+
+__global__ void db_single_setup_kernel(const uint32_t* bits, int N, int stride, int D, double eps,
+                                       int min_samples, int32_t* work, int32_t* labels,
+                                       DbProblem* problems) {
+    DbProblem p;
+    p.bits = bits;
+    p.valid = nullptr;
+    p.core = work;
+    p.parent = work + N;
+    p.aux = work + 2 * N;
+    p.labels = labels;
+    p.nclusters = nullptr;
+    p.stride = stride;
+    p.w0 = 0;
+    p.nw = (D + 31) / 32;
+    p.N = N;
+    p.kmax = hamming_kmax(D, eps);
+    p.min_samples = min_samples;
+    problems[0] = p;
+}
+
+}  // namespace s2d
+
+using namespace s2d;
+
+static_assert(sizeof(DbProblem) % 8 == 0, "DbProblem must keep 8-byte alignment in the work buffer");
+
+extern "C" int s2d_dbscan_work_ints(int64_t total_rows, int nproblems, int64_t* out) {
+    if (!out) return -1;
+    *out = 3 * total_rows + 2 + (int64_t)nproblems * (int64_t)(sizeof(DbProblem) / 4);
+    return 0;
+}
+
+extern "C" int s2d_dbscan_visibility(const s2d_video_desc* descs, int nvideos, int max_Nm, int max_TW,
+                                     int64_t total_rows, const uint32_t* xbits, double eps,
+                                     int min_samples, int32_t* work, int32_t* labels1,
+                                     int32_t* vidinfo, void* stream) {
+    S2D_CHECK_ARG(descs && xbits && work && labels1 && vidinfo, "s2d_dbscan_visibility: null pointer");
+    S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_Nm > 0, "s2d_dbscan_visibility: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    // problem descriptors live behind the 3*total_rows ints of union-find scratch (8-byte aligned)
+    int64_t off = 3 * total_rows;
+    off += off & 1;
+    DbProblem* problems = reinterpret_cast<DbProblem*>(work + off);
+    S2D_CHECK_ARG((((uintptr_t)problems) & 7) == 0, "s2d_dbscan_visibility: work must be 8-byte aligned");
+    db1_setup_kernel<<<(nvideos + 127) / 128, 128, 0, st>>>(descs, nvideos, xbits, eps, min_samples, work,
+                                                            labels1, vidinfo, problems);
+    S2D_CHECK_LAUNCH("db1_setup_kernel");
+    return launch_dbscan(problems, nvideos, max_Nm, max_TW, st);
+}
+
+extern "C" int s2d_hamming_dbscan(const uint32_t* bits, int N, int stride, int D, double eps,
+                                  int min_samples, int32_t* work, int32_t* labels, void* stream) {
+    S2D_CHECK_ARG(bits && work && labels, "s2d_hamming_dbscan: null pointer");
+    S2D_CHECK_ARG(N > 0 && D > 0 && stride >= (D + 31) / 32, "s2d_hamming_dbscan: bad sizes N=%d D=%d stride=%d", N, D, stride);
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t off = 3 * (int64_t)N;
+    off += off & 1;
+    DbProblem* problems = reinterpret_cast<DbProblem*>(work + off);
+    S2D_CHECK_ARG((((uintptr_t)problems) & 7) == 0, "s2d_hamming_dbscan: work must be 8-byte aligned");
+    db_single_setup_kernel<<<1, 1, 0, st>>>(bits, N, stride, D, eps, min_samples, work, labels, problems);
+    S2D_CHECK_LAUNCH("db_single_setup_kernel");
+    return launch_dbscan(problems, 1, N, (D + 31) / 32, st);
+}

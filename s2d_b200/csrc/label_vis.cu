@@ -1,0 +1,226 @@
+// K0 label statistics / object enumeration and K3a visibility reduce + binarise.
+// HBM-bound streaming kernels: 128-bit loads, run-length aggregation into warp-private
+// shared-memory histograms, one global atomic per (CTA, label).
+#include "common.cuh"
+
+namespace s2d {
+
+// ------------------------------------------------------------------------------------------
+// K0a: area[frame][256] += histogram of a chunk of the frame's label bytes.
+// ------------------------------------------------------------------------------------------
+constexpr int LH_THREADS = 256;
+constexpr int LH_BYTES_PER_CTA = 64 * 1024;
+
+__device__ __forceinline__ void hist_flush(int* wh, int cur, int cnt) {
+    if (cnt) atomicAdd(&wh[cur], cnt);
+}
+
+__global__ void __launch_bounds__(LH_THREADS)
+label_hist_kernel(const s2d_video_desc* __restrict__ descs, int32_t* __restrict__ area) {
+    const s2d_video_desc d = descs[blockIdx.z];
+    const int t = blockIdx.y;
+    if (t >= d.T) return;
+    const int64_t npix = (int64_t)d.H * d.W;
+    const int64_t beg = (int64_t)blockIdx.x * LH_BYTES_PER_CTA;
+    if (beg >= npix) return;
+    const int64_t end = min(npix, beg + (int64_t)LH_BYTES_PER_CTA);
+
+    __shared__ int wh[LH_THREADS / 32][S2D_MAX_LABELS];
+    for (int i = threadIdx.x; i < (LH_THREADS / 32) * S2D_MAX_LABELS; i += LH_THREADS) (&wh[0][0])[i] = 0;
+    __syncthreads();
+    int* mywh = wh[threadIdx.x >> 5];
+
+    const uint8_t* base = d.labels + (int64_t)t * npix;
+    int cur = 0, cnt = 0;
+    // head: bytes until 16-byte alignment (thread 0 of the CTA handles them; at most 15)
+    const uintptr_t addr0 = (uintptr_t)(base + beg);
+    int64_t head = min((int64_t)((16 - (addr0 & 15)) & 15), end - beg);
+    const int64_t vbeg = beg + head;
+    const int64_t nvec = (end - vbeg) / 16;
+    if (threadIdx.x == 0) {
+        for (int64_t i = beg; i < vbeg; ++i) {
+            int v = base[i];
+            if (v != cur) { hist_flush(mywh, cur, cnt); cur = v; cnt = 0; }
+            ++cnt;
+        }
+        for (int64_t i = vbeg + nvec * 16; i < end; ++i) {
+            int v = base[i];
+            if (v != cur) { hist_flush(mywh, cur, cnt); cur = v; cnt = 0; }
+            ++cnt;
+        }
+    }
+    const int4* vp = reinterpret_cast<const int4*>(base + vbeg);
+    for (int64_t i = threadIdx.x; i < nvec; i += LH_THREADS) {
+        int4 w = ld_stream(vp + i);
+        const uint32_t splat = (uint32_t)cur * 0x01010101u;
+        if (((uint32_t)w.x == splat) & ((uint32_t)w.y == splat) & ((uint32_t)w.z == splat) & ((uint32_t)w.w == splat)) {
+            cnt += 16;
+            continue;
+        }
+        uint32_t ws[4] = {(uint32_t)w.x, (uint32_t)w.y, (uint32_t)w.z, (uint32_t)w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                int v = (ws[k] >> (8 * b)) & 255;
+                if (v != cur) { hist_flush(mywh, cur, cnt); cur = v; cnt = 0; }
+                ++cnt;
+            }
+        }
+    }
+    hist_flush(mywh, cur, cnt);
+    __syncthreads();
+    int32_t* out = area + (d.frame0 + t) * S2D_MAX_LABELS;
+    for (int l = threadIdx.x; l < S2D_MAX_LABELS; l += LH_THREADS) {
+        int s = 0;
+#pragma unroll
+        for (int w = 0; w < LH_THREADS / 32; ++w) s += wh[w][l];
+        if (s) atomicAdd(&out[l], s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K0b: object enumeration. One CTA (256 threads = one per label) per video, frames in order.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(S2D_MAX_LABELS)
+frame_tables_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __restrict__ area,
+                    int32_t* __restrict__ gid_of, int32_t* __restrict__ frameinfo,
+                    int32_t* __restrict__ qframe, int32_t* __restrict__ qlabel,
+                    int32_t* __restrict__ vidinfo) {
+    const s2d_video_desc d = descs[blockIdx.x];
+    __shared__ uint32_t pres[8];
+    const int l = threadIdx.x, w = l >> 5, lane = l & 31;
+    int gid_base = 0;
+    for (int t = 0; t < d.T; ++t) {
+        const int64_t f = d.frame0 + t;
+        const bool p = area[f * S2D_MAX_LABELS + l] > 0;
+        const uint32_t b = __ballot_sync(0xffffffffu, p);
+        if (lane == 0) pres[w] = b;
+        __syncthreads();
+        int below = 0, total = 0, minlab = -1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t m = pres[k];
+            total += __popc(m);
+            if (k < w) below += __popc(m);
+            if (minlab < 0 && m) minlab = k * 32 + __ffs(m) - 1;
+        }
+        below += __popc(b & ((1u << lane) - 1u));
+        int gid = -1;
+        if (p && l != minlab) {
+            gid = gid_base + below - 1;
+            if (gid < d.Nm) {
+                qframe[d.row0 + gid] = t;
+                qlabel[d.row0 + gid] = l;
+            }
+        }
+        gid_of[f * S2D_MAX_LABELS + l] = gid;
+        const int nobj = total > 0 ? total - 1 : 0;
+        if (l == 0) reinterpret_cast<int4*>(frameinfo)[f] = make_int4(nobj, gid_base, minlab, total);
+        gid_base += nobj;
+        __syncthreads();
+    }
+    if (l == 0) vidinfo[blockIdx.x * S2D_VIDINFO_WORDS + 5] = gid_base;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3a: visibility reduce. One warp per (row, frame): popcount of nonzero flag bytes.
+// ------------------------------------------------------------------------------------------
+constexpr int VR_WARPS = 8;
+
+__global__ void __launch_bounds__(VR_WARPS * 32)
+vis_reduce_kernel(const s2d_video_desc* __restrict__ descs, int32_t* __restrict__ cnt_out,
+                  float* __restrict__ V) {
+    const s2d_video_desc d = descs[blockIdx.y];
+    const int64_t rt = (int64_t)blockIdx.x * VR_WARPS + (threadIdx.x >> 5);
+    if (rt >= (int64_t)d.Nm * d.T) return;
+    const int lane = threadIdx.x & 31;
+    const int q = (int)(rt / d.T);
+    const int n = d.npts ? min(max(d.npts[q], 0), d.P) : d.P;
+    const uint8_t* row = d.vis + rt * d.P;
+    int c = 0;
+    if (n == d.P && (d.P & 15) == 0 && (((uintptr_t)row) & 15) == 0) {
+        const int4* vp = reinterpret_cast<const int4*>(row);
+        const int nv = d.P >> 4;
+        int i = lane;
+        // two independent 128-bit loads in flight per lane
+        for (; i + 32 < nv; i += 64) {
+            int4 a = ld_stream(vp + i), b = ld_stream(vp + i + 32);
+            c += __popc(__vsetne4((uint32_t)a.x, 0u)) + __popc(__vsetne4((uint32_t)a.y, 0u)) +
+                 __popc(__vsetne4((uint32_t)a.z, 0u)) + __popc(__vsetne4((uint32_t)a.w, 0u));
+            c += __popc(__vsetne4((uint32_t)b.x, 0u)) + __popc(__vsetne4((uint32_t)b.y, 0u)) +
+                 __popc(__vsetne4((uint32_t)b.z, 0u)) + __popc(__vsetne4((uint32_t)b.w, 0u));
+        }
+        for (; i < nv; i += 32) {
+            int4 a = ld_stream(vp + i);
+            c += __popc(__vsetne4((uint32_t)a.x, 0u)) + __popc(__vsetne4((uint32_t)a.y, 0u)) +
+                 __popc(__vsetne4((uint32_t)a.z, 0u)) + __popc(__vsetne4((uint32_t)a.w, 0u));
+        }
+    } else {
+        for (int i = lane; i < n; i += 32) c += row[i] != 0;
+    }
+    c = warp_sum(c);
+    if (lane == 0) {
+        cnt_out[d.vt_off + rt] = c;
+        // torch.mean(bool.float()) on CPU == float32(cnt) / float32(P), IEEE division; 0/0 = NaN
+        V[d.vt_off + rt] = __fdiv_rn((float)c, (float)n);
+    }
+}
+
+// K3 binarise: one thread per (row, word of 32 frames).
+__global__ void binarize_kernel(const s2d_video_desc* __restrict__ descs, const float* __restrict__ V,
+                                float thr, uint32_t* __restrict__ xbits) {
+    const s2d_video_desc d = descs[blockIdx.y];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)d.Nm * d.TW) return;
+    const int q = (int)(i / d.TW), w = (int)(i % d.TW);
+    const float* v = V + d.vt_off + (int64_t)q * d.T;
+    uint32_t m = 0;
+    for (int b = 0; b < 32; ++b) {
+        const int t = w * 32 + b;
+        if (t < d.T && v[t] > thr) m |= 1u << b;   // NaN compares false
+    }
+    xbits[d.xbits_off + i] = m;
+}
+
+}  // namespace s2d
+
+using namespace s2d;
+
+extern "C" int s2d_label_stats(const s2d_video_desc* descs, int nvideos, int max_T, int64_t max_npix,
+                               int64_t total_frames, int32_t* area,
+                               int32_t* gid_of, int32_t* frameinfo, int32_t* qframe, int32_t* qlabel,
+                               int32_t* vidinfo, void* stream) {
+    S2D_CHECK_ARG(descs && area && gid_of && frameinfo && qframe && qlabel && vidinfo,
+                  "s2d_label_stats: null pointer");
+    S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_T > 0 && max_T <= 65535 && max_npix > 0,
+                  "s2d_label_stats: bad sizes nvideos=%d max_T=%d", nvideos, max_T);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(area, 0, (size_t)total_frames * S2D_MAX_LABELS * sizeof(int32_t), st);
+    dim3 grid((unsigned)((max_npix + LH_BYTES_PER_CTA - 1) / LH_BYTES_PER_CTA), max_T, nvideos);
+    label_hist_kernel<<<grid, LH_THREADS, 0, st>>>(descs, area);
+    S2D_CHECK_LAUNCH("label_hist_kernel");
+    frame_tables_kernel<<<nvideos, S2D_MAX_LABELS, 0, st>>>(descs, area, gid_of, frameinfo, qframe, qlabel, vidinfo);
+    S2D_CHECK_LAUNCH("frame_tables_kernel");
+    return 0;
+}
+
+extern "C" int s2d_vis_reduce(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_T,
+                              int32_t* cnt, float* V, void* stream) {
+    S2D_CHECK_ARG(descs && cnt && V, "s2d_vis_reduce: null pointer");
+    S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_rows_x_T > 0, "s2d_vis_reduce: bad sizes");
+    dim3 grid((unsigned)((max_rows_x_T + VR_WARPS - 1) / VR_WARPS), nvideos);
+    vis_reduce_kernel<<<grid, VR_WARPS * 32, 0, (cudaStream_t)stream>>>(descs, cnt, V);
+    S2D_CHECK_LAUNCH("vis_reduce_kernel");
+    return 0;
+}
+
+extern "C" int s2d_binarize(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_TW,
+                            const float* V, float visibility_threshold, uint32_t* xbits, void* stream) {
+    S2D_CHECK_ARG(descs && V && xbits, "s2d_binarize: null pointer");
+    S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_rows_x_TW > 0, "s2d_binarize: bad sizes");
+    dim3 grid((unsigned)((max_rows_x_TW + 255) / 256), nvideos);
+    binarize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs, V, visibility_threshold, xbits);
+    S2D_CHECK_LAUNCH("binarize_kernel");
+    return 0;
+}

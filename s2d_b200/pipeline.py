@@ -1,0 +1,322 @@
+"""Batched, device-resident keymask discovery: the arithmetic of the reference's per-video loop
+(keymask_ident/main_keymask_ident.py:91-128, stages A-D) as one sequence of CUDA launches over a
+whole batch of videos, with no host round trip between the stages.
+
+torch is used for device memory and streams only; every number is produced by the kernels in
+s2d_b200/csrc through the C ABI (include/s2d_b200.h). `decode()` turns the raw device results
+into the same python structures the reference builds (stage-B json schema, matches_data,
+groupings, one2x, coverage) - it only unpacks bit masks and index tables.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (S2D_CLINFO_WORDS, S2D_MAX_CLUSTERS, S2D_MAX_LABELS, S2D_VIDINFO_WORDS, VideoDesc)
+
+
+@dataclass
+class VideoInput:
+    """Device tensors of one video (see s2d_b200.synth for the layout)."""
+    labels: torch.Tensor                    # u8  [T,H,W]
+    tracks: torch.Tensor                    # f32 [Nm,T,P,2]
+    vis: torch.Tensor                       # u8/bool [Nm,T,P]
+    npts: Optional[torch.Tensor] = None     # i32 [Nm]
+    max_label: Optional[int] = None         # upper bound of the label ids (default 255)
+    name: str = ""
+
+
+@dataclass
+class Params:
+    """Constants the reference hard-codes with its defaults."""
+    visibility_threshold: float = 0.3       # --visibility-threshold
+    matching_threshold: float = 0.5         # --matching-threshold
+    dbscan1_eps: float = 0.2                # identify_visibility_windows.py:114
+    dbscan1_min_samples: int = 5
+    winner_fraction: float = 0.3            # identify_visibility_windows.py:166
+    one2x_iou: float = 0.25                 # cotracker_matching.py:1085
+    one2x_frames: int = 5                   # cotracker_matching.py:1111
+
+
+def _i32(n, device, fill=None):
+    t = torch.empty(int(n), dtype=torch.int32, device=device)
+    if fill is not None:
+        t.fill_(fill)
+    return t
+
+
+class Batch:
+    """Descriptor table + workspace for a list of videos. Allocation happens here, once; `run`
+    only enqueues kernels, so a Batch can be re-run (benchmarks) without touching the allocator."""
+
+    def __init__(self, videos: List[VideoInput], device=None, keep_votes: bool = True):
+        assert len(videos) > 0
+        self.videos = videos
+        self.device = device or videos[0].labels.device
+        dev = self.device
+        nv = len(videos)
+        descs = (VideoDesc * nv)()
+        row0 = frame0 = vt = hits = xw = mw = 0
+        self.max_T = self.max_Nm = self.max_TW = self.max_NW = self.max_P = 0
+        self.max_npix = self.max_rows_x_T = self.max_rows_x_TW = 0
+        self.vec4 = 1
+        self._keep = []
+        for i, v in enumerate(videos):
+            T, H, W = v.labels.shape
+            Nm, T2, P, two = v.tracks.shape
+            assert two == 2 and T2 == T and tuple(v.vis.shape) == (Nm, T, P), "inconsistent video tensors"
+            assert v.labels.dtype == torch.uint8 and v.tracks.dtype == torch.float32
+            assert v.vis.dtype in (torch.uint8, torch.bool)
+            assert v.labels.is_contiguous() and v.tracks.is_contiguous() and v.vis.is_contiguous()
+            assert H <= 65535 and W <= 65535 and P <= 32768 and T <= 1024
+            L = min(S2D_MAX_LABELS, (v.max_label if v.max_label is not None else 255) + 1)
+            d = descs[i]
+            d.T, d.H, d.W, d.P, d.Nm, d.L = T, H, W, P, Nm, L
+            d.TW, d.NW = (T + 31) // 32, (Nm + 31) // 32
+            d.row0, d.frame0 = row0, frame0
+            d.labels, d.tracks, d.vis = v.labels.data_ptr(), v.tracks.data_ptr(), v.vis.data_ptr()
+            d.npts = v.npts.data_ptr() if v.npts is not None else None
+            d.vt_off, d.hits_off, d.xbits_off, d.mbits_off = vt, hits, xw, mw
+            if P % 2 or v.tracks.data_ptr() % 16:
+                self.vec4 = 0
+            row0 += Nm; frame0 += T; vt += Nm * T; hits += Nm * T * L
+            xw += Nm * d.TW; mw += Nm * d.NW
+            self.max_T = max(self.max_T, T); self.max_Nm = max(self.max_Nm, Nm)
+            self.max_TW = max(self.max_TW, d.TW); self.max_NW = max(self.max_NW, d.NW)
+            self.max_P = max(self.max_P, P); self.max_npix = max(self.max_npix, H * W)
+            self.max_rows_x_T = max(self.max_rows_x_T, Nm * T)
+            self.max_rows_x_TW = max(self.max_rows_x_TW, Nm * d.TW)
+        self.nv = nv
+        self.host_descs = descs
+        self.total_rows, self.total_frames, self.total_vt = row0, frame0, vt
+        self.total_hits, self.total_xw, self.total_mw = hits, xw, mw
+        raw = np.frombuffer(bytes(descs), dtype=np.uint8)
+        self.descs = torch.from_numpy(raw.copy()).to(dev)
+
+        # workspace / outputs
+        self.area = _i32(frame0 * S2D_MAX_LABELS, dev)
+        self.gid_of = _i32(frame0 * S2D_MAX_LABELS, dev)
+        self.frameinfo = _i32(frame0 * 4, dev)
+        self.qframe = _i32(row0, dev, 0)
+        self.qlabel = _i32(row0, dev, 0)
+        self.vidinfo = _i32(nv * S2D_VIDINFO_WORDS, dev, 0)
+        self.cnt = _i32(vt, dev)
+        self.V = torch.empty(vt, dtype=torch.float32, device=dev)
+        self.xbits = _i32(xw, dev)
+        self.labels1 = _i32(row0, dev)
+        n = C.c_int64()
+        _lib.call("s2d_dbscan_work_ints", row0, nv, C.byref(n))
+        self.dbwork = _i32(n.value + 2, dev)
+        self.ccount = _i32(vt, dev)
+        self.clrow = _i32(row0 * 4, dev)
+        self.majbits = _i32(xw, dev)
+        self.rsbits = _i32(xw, dev)
+        self.rebits = _i32(xw, dev)
+        self.winbits = _i32(xw, dev)
+        self.rowinfo = _i32(row0 * 4, dev)
+        self.clusterinfo = _i32(nv * S2D_MAX_CLUSTERS * S2D_CLINFO_WORDS, dev, 0)
+        self.hits = _i32(hits, dev)
+        self.uniq = _i32(vt, dev)
+        self.mbits = _i32(mw, dev)
+        self.one2x = _i32(row0, dev)
+        self.nmatch = _i32(row0, dev)
+        _lib.call("s2d_group_work_ints", row0, nv, C.byref(n))
+        self.grpwork = _i32(n.value + 2, dev)
+        self.glabel = _i32(row0, dev)
+        self.grp_n = _i32(16 * row0, dev)
+        self.grp_one2x = _i32(16 * row0, dev)
+        self.kernel_launches_per_run = 0
+
+    # ------------------------------------------------------------------ enqueue
+    def run(self, params: Params = Params(), stream=None, stages: str = "ABD"):
+        """Enqueue the whole path on `stream` (default: torch's current stream). Returns the
+        number of kernel launches enqueued."""
+        st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        p = lambda t: t.data_ptr()
+        d, nv = p(self.descs), self.nv
+        launches = 0
+        if "A" in stages:
+            _lib.call("s2d_label_stats", d, nv, self.max_T, self.max_npix, self.total_frames, p(self.area),
+                      p(self.gid_of), p(self.frameinfo), p(self.qframe), p(self.qlabel), p(self.vidinfo), st)
+            _lib.call("s2d_vis_reduce", d, nv, self.max_rows_x_T, p(self.cnt), p(self.V), st)
+            launches += 3
+        if "B" in stages:
+            _lib.call("s2d_binarize", d, nv, self.max_rows_x_TW, p(self.V),
+                      float(np.float32(params.visibility_threshold)), p(self.xbits), st)
+            _lib.call("s2d_dbscan_visibility", d, nv, self.max_Nm, self.max_TW, self.total_rows, p(self.xbits),
+                      params.dbscan1_eps, params.dbscan1_min_samples, p(self.dbwork), p(self.labels1),
+                      p(self.vidinfo), st)
+            _lib.call("s2d_windows", d, nv, self.max_rows_x_TW, self.max_TW, self.total_rows, self.total_vt,
+                      p(self.xbits), p(self.labels1), p(self.qframe), float(np.float32(params.winner_fraction)),
+                      p(self.ccount), p(self.clrow), p(self.majbits), p(self.rsbits), p(self.rebits),
+                      p(self.winbits), p(self.rowinfo), p(self.vidinfo), p(self.clusterinfo), st)
+            launches += 1 + 5 + 2
+        if "D" in stages:
+            _lib.call("s2d_point_votes", d, nv, self.max_rows_x_T, self.max_P, self.vec4, p(self.rowinfo),
+                      p(self.vidinfo), p(self.hits), p(self.uniq), st)
+            _lib.call("s2d_select", d, nv, self.max_Nm, self.total_mw, p(self.hits), p(self.uniq), p(self.gid_of),
+                      p(self.rowinfo), params.matching_threshold, params.one2x_iou, params.one2x_frames,
+                      p(self.mbits), p(self.one2x), p(self.nmatch), p(self.vidinfo), st)
+            _lib.call("s2d_group", d, nv, self.max_Nm, self.max_NW, self.total_rows, p(self.mbits), p(self.rowinfo),
+                      p(self.one2x), p(self.grpwork), p(self.glabel), p(self.grp_n), p(self.grp_one2x),
+                      p(self.vidinfo), p(self.clusterinfo), st)
+            launches += 1 + 1 + 1 + 7
+        self.kernel_launches_per_run = launches
+        return launches
+
+    def votes_all(self, stream=None):
+        """K2 over every (query, frame) of every video, ignoring candidates/status (tests, bench)."""
+        st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        _lib.call("s2d_point_votes", self.descs.data_ptr(), self.nv, self.max_rows_x_T, self.max_P, self.vec4,
+                  None, None, self.hits.data_ptr(), self.uniq.data_ptr(), st)
+
+    # ------------------------------------------------------------------ results
+    def fetch_summary(self):
+        """The small device->host read of a step's result: status, cluster table, per-row
+        (cluster, candidate, window), group labels, one2x flags."""
+        out = dict(vidinfo=self.vidinfo.cpu().numpy().reshape(self.nv, S2D_VIDINFO_WORDS),
+                   clusterinfo=self.clusterinfo.cpu().numpy().reshape(self.nv, S2D_MAX_CLUSTERS, S2D_CLINFO_WORDS),
+                   rowinfo=self.rowinfo.cpu().numpy().reshape(-1, 4),
+                   glabel=self.glabel.cpu().numpy(), one2x=self.one2x.cpu().numpy())
+        return out
+
+    def decode(self, want_comps: bool = True):
+        """Full results in the reference's python structures, one dict per video (same schema as
+        oracle.keymask_oracle.discover)."""
+        h = {k: getattr(self, k).cpu().numpy() for k in
+             ("qframe", "qlabel", "vidinfo", "V", "labels1", "clrow", "rsbits", "rebits", "winbits", "rowinfo",
+              "clusterinfo", "one2x", "nmatch", "mbits", "glabel", "grp_n", "grp_one2x", "area", "gid_of")}
+        if want_comps:
+            h["hits"] = self.hits.cpu().numpy()
+            h["uniq"] = self.uniq.cpu().numpy()
+        vidinfo = h["vidinfo"].reshape(self.nv, S2D_VIDINFO_WORDS)
+        clinfo = h["clusterinfo"].reshape(self.nv, S2D_MAX_CLUSTERS, S2D_CLINFO_WORDS)
+        rowinfo = h["rowinfo"].reshape(-1, 4)
+        clrow = h["clrow"].reshape(-1, 4)
+        area = h["area"].reshape(-1, S2D_MAX_LABELS)
+        gid_of = h["gid_of"].reshape(-1, S2D_MAX_LABELS)
+        results = []
+        for vi in range(self.nv):
+            d = self.host_descs[vi]
+            T, Nm, TW, NW, L = d.T, d.Nm, d.TW, d.NW, d.L
+            r0, f0 = d.row0, d.frame0
+            if int(vidinfo[vi, 5]) != Nm:
+                raise _lib.S2DError(f"video {vi}: tracks hold {Nm} queries but the label maps enumerate "
+                                    f"{int(vidinfo[vi, 5])} objects")
+            qf = h["qframe"][r0:r0 + Nm].astype(np.int64)
+            ql = h["qlabel"][r0:r0 + Nm].astype(np.int64)
+            res = {"query_frame": qf, "query_label": ql}
+            res["V"] = h["V"][d.vt_off:d.vt_off + Nm * T].reshape(Nm, T)
+            lab1 = h["labels1"][r0:r0 + Nm].astype(np.int64)
+            res["labels1"] = lab1
+            ri = rowinfo[r0:r0 + Nm]
+            bits = lambda name: h[name][d.xbits_off:d.xbits_off + Nm * TW].reshape(Nm, TW).view(np.uint32)
+            rs, re, wb = bits("rsbits"), bits("rebits"), bits("winbits")
+            k = int(vidinfo[vi, 0])
+            clusters = []
+            for c in range(k):
+                starts = _setbits(rs[c], T)
+                ends = _setbits(re[c], T)
+                rows = np.nonzero(lab1 == c)[0]
+                all_cands, all_vis = [], []
+                for r, (s, e) in enumerate(zip(starts, ends)):
+                    cands = []
+                    for g in rows:
+                        if (wb[g, r >> 5] >> (r & 31)) & 1:
+                            all_vis.append({"frame_id": int(qf[g]), "mask_id": int(ql[g])})
+                            if ri[g, 1] == r:
+                                cands.append({"start_frame": s, "end_frame": e, "frame_id": int(qf[g]),
+                                              "mask_id": int(ql[g])})
+                    all_cands.append({"range": [s, e], "candidates": cands})
+                clusters.append({"cluster_id": c, "cluster_size": int(clrow[r0 + c, 0]),
+                                 "ranges": [[s, e] for s, e in zip(starts, ends)],
+                                 "all_candidates": all_cands, "all_visible_masks": all_vis})
+            res["clusters"] = clusters
+            status = int(vidinfo[vi, 3])
+            res["status"] = status
+            res["stage_b_status"] = int(vidinfo[vi, 1])
+            res["queries"] = []
+            res["groupings"] = None
+            if status == 1:
+                mb = h["mbits"][d.mbits_off:d.mbits_off + Nm * NW].reshape(Nm, NW).view(np.uint32)
+                if want_comps:
+                    hits = h["hits"][d.hits_off:d.hits_off + Nm * T * L].reshape(Nm, T, L)
+                    uniq = h["uniq"][d.vt_off:d.vt_off + Nm * T].reshape(Nm, T)
+                queries = []
+                for c in range(k):
+                    rows = np.nonzero((ri[:, 0] == c) & (ri[:, 1] >= 0))[0]
+                    # processing order: files sorted lexicographically by name, then stable by frame
+                    names = sorted((f"cluster{c}_frame{int(qf[g])}_mask{int(ql[g])}.png", int(g)) for g in rows)
+                    order = sorted(names, key=lambda ng: int(qf[ng[1]]))
+                    for _, g in order:
+                        v0, v1 = int(ri[g, 2]), int(ri[g, 3])
+                        a = int(area[f0 + int(qf[g]), int(ql[g])])
+                        q = {"cluster_id": c, "frame_id": int(qf[g]), "mask_id": int(ql[g]), "overall_mask_id": g,
+                             "one2x": int(h["one2x"][r0 + g]), "matches": _setbits(mb[g], Nm),
+                             "v_range": (v0, v1), "grid_size": max(min(a // 800, 50), 25),
+                             "backward_tracking": int(qf[g]) > v0}
+                        if want_comps:
+                            comps = []
+                            for t in range(v0, v1 + 1):
+                                gids = gid_of[f0 + t]
+                                for o in np.nonzero(gids >= 0)[0]:
+                                    I, U = int(hits[g, t, o]), int(uniq[g, t])
+                                    comps.append((t, int(o), int(gids[o]), I, U, 0.0 if U == 0 else I / U))
+                            q["comps"] = comps
+                        queries.append(q)
+                res["queries"] = queries
+                groupings, cov = [], []
+                tot_m = tot_n = 0
+                one2x_video = {}
+                for c in range(k):
+                    ci = clinfo[vi, c]
+                    rows = np.nonzero(ri[:, 0] == c)[0]
+                    gl = h["glabel"][r0:r0 + Nm]
+                    groups = {}
+                    for g in rows:
+                        if gl[g] >= 0:
+                            groups.setdefault(int(gl[g]), []).append((int(qf[g]), int(ql[g])))
+                    groupings.append({"cluster_id": c, "visibility_to_temporal_factor": int(ci[11]),
+                                      "overall_mask_ids_per_label": groups})
+                    cov.append(int(ci[12]) / int(ci[1]) if ci[1] else 0)
+                    tot_m += int(ci[12]); tot_n += int(ci[1])
+                    od = {"avg_one2x_cluster": int(ci[13]) / int(ci[14]) if ci[14] else float("nan")}
+                    base = 16 * r0 + c * Nm
+                    for lab in groups:
+                        n_, s_ = int(h["grp_n"][base + lab]), int(h["grp_one2x"][base + lab])
+                        avg = s_ / n_ if n_ else 0
+                        od[f"group_{lab}"] = {"avg_one2x": avg, "one2x_counts": n_, "noisy": bool(avg > 0.5)}
+                    one2x_video[f"cluster_{c}"] = od
+                res["groupings"] = groupings
+                res["cluster_coverages"] = cov
+                res["video_coverage"] = tot_m / tot_n if tot_n else 0
+                res["one2x"] = one2x_video
+            results.append(res)
+        return results
+
+
+def _setbits(words: np.ndarray, limit: int):
+    out = []
+    for w, m in enumerate(words.tolist()):
+        m &= 0xFFFFFFFF
+        while m:
+            b = (m & -m).bit_length() - 1
+            m &= m - 1
+            i = w * 32 + b
+            if i < limit:
+                out.append(i)
+    return out
+
+
+def discover_keymasks(videos: List[VideoInput], params: Params = Params(), want_comps: bool = True):
+    """Public in-memory entry point: run stages A-D for a batch of videos on their device and
+    return one result dict per video."""
+    b = Batch(videos)
+    b.run(params)
+    torch.cuda.synchronize(b.device)
+    return b.decode(want_comps=want_comps)

@@ -1,0 +1,212 @@
+"""CUDA path vs reference goldens and vs the CPU oracle, through the C ABI (needs a B200)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import keymask_oracle as ko
+from oracle.compare import check_against_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _video(labels, tracks, vis, **kw):
+    from s2d_b200.pipeline import VideoInput
+    d = _dev()
+    return VideoInput(torch.from_numpy(np.ascontiguousarray(labels)).to(d),
+                      torch.from_numpy(np.ascontiguousarray(tracks)).to(d),
+                      torch.from_numpy(np.ascontiguousarray(vis)).to(d), **kw)
+
+
+def test_pipeline_matches_reference_golden(golden_case):
+    from s2d_b200.pipeline import Params, discover_keymasks
+    name, g, labels, tracks, vis = golden_case
+    res = discover_keymasks([_video(labels, tracks, vis)],
+                            Params(g["visibility_threshold"], g["matching_threshold"]))[0]
+    check_against_golden(res, g)
+
+
+def test_batched_heterogeneous_videos_match_goldens():
+    """all golden cases in ONE batch (different T/H/W/P/Nm per video)."""
+    from tests.conftest import GOLDEN_CASES, load_golden
+    from s2d_b200.pipeline import Params, discover_keymasks
+    cases = [load_golden(n) for n in GOLDEN_CASES]
+    groups = {}
+    for n, c in zip(GOLDEN_CASES, cases):
+        groups.setdefault((c[0]["visibility_threshold"], c[0]["matching_threshold"]), []).append((n, c))
+    for (vt, mt), items in groups.items():
+        res = discover_keymasks([_video(c[1], c[2], c[3]) for _, c in items], Params(vt, mt))
+        for (n, c), r in zip(items, res):
+            check_against_golden(r, c[0])
+
+
+def test_point_votes_all_pairs_vs_oracle(golden_case):
+    from s2d_b200.pipeline import Batch
+    name, g, labels, tracks, vis = golden_case
+    b = Batch([_video(labels, tracks, vis)])
+    b.hits.fill_(-7); b.uniq.fill_(-7)
+    b.votes_all()
+    torch.cuda.synchronize()
+    Nm, T, P, _ = tracks.shape
+    L = b.host_descs[0].L
+    hits = b.hits.cpu().numpy().reshape(Nm, T, L)
+    uniq = b.uniq.cpu().numpy().reshape(Nm, T)
+    for q in range(Nm):
+        h, u = ko.point_votes(tracks[q], labels, 0, T - 1, nbins=L)
+        assert np.array_equal(u, uniq[q]), (name, q)
+        assert np.array_equal(h, hits[q]), (name, q)
+
+
+@pytest.mark.parametrize("P,H,W", [(1000, 480, 854), (4096, 720, 1280), (777, 33, 1900), (8192, 1080, 1920), (20000, 64, 64)])
+def test_point_votes_shapes_and_bands(P, H, W):
+    """odd P (no 128-bit path), P above the register tile, bounding boxes that need several
+    bitmap bands (points spread over the whole 1080p frame), heavy duplication (P >> H*W)."""
+    from s2d_b200.pipeline import Batch
+    rng = np.random.default_rng(P + H)
+    T, Nm = 3, 4
+    labels = rng.integers(0, 7, size=(T, H, W)).astype(np.uint8)
+    labels[:, : H // 2] = 3
+    tracks = np.empty((Nm, T, P, 2), np.float32)
+    tracks[..., 0] = rng.uniform(-20, W + 20, size=(Nm, T, P))
+    tracks[..., 1] = rng.uniform(-20, H + 20, size=(Nm, T, P))
+    tracks[0, 0, : P // 2] = tracks[0, 0, P // 2: P // 2 + P // 2][: P // 2]   # duplicates
+    tracks[1, 1, ::5, 0] = np.nan
+    tracks[2, 2, ::7, 1] = np.inf
+    tracks[3, :, :, :] = np.round(tracks[3]) + 0.5                            # all half-integers
+    vis = rng.integers(0, 2, size=(Nm, T, P)).astype(np.uint8)
+    b = Batch([_video(labels, tracks, vis, max_label=6)])
+    b.votes_all()
+    torch.cuda.synchronize()
+    hits = b.hits.cpu().numpy().reshape(Nm, T, 7)
+    uniq = b.uniq.cpu().numpy().reshape(Nm, T)
+    for q in range(Nm):
+        h, u = ko.point_votes(tracks[q], labels, 0, T - 1, nbins=7)
+        assert np.array_equal(u, uniq[q]) and np.array_equal(h, hits[q]), (q, u, uniq[q])
+    # stage A on the same batch: visibility mean is float32(cnt)/float32(P)
+    from s2d_b200 import _lib
+    _lib.call("s2d_vis_reduce", b.descs.data_ptr(), 1, b.max_rows_x_T, b.cnt.data_ptr(), b.V.data_ptr(),
+              torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(b.V.cpu().numpy().reshape(Nm, T), ko.visibility_mean(vis))
+
+
+def test_ragged_npts():
+    from s2d_b200.pipeline import Batch
+    rng = np.random.default_rng(5)
+    T, Nm, P, H, W = 4, 6, 512, 90, 120
+    labels = rng.integers(0, 4, size=(T, H, W)).astype(np.uint8)
+    tracks = rng.uniform(0, 100, size=(Nm, T, P, 2)).astype(np.float32)
+    vis = rng.integers(0, 2, size=(Nm, T, P)).astype(np.uint8)
+    npts = np.asarray([512, 1, 0, 33, 400, 511], np.int32)
+    v = _video(labels, tracks, vis, max_label=3)
+    v.npts = torch.from_numpy(npts).to(_dev())
+    b = Batch([v])
+    b.votes_all()
+    from s2d_b200 import _lib
+    _lib.call("s2d_vis_reduce", b.descs.data_ptr(), 1, b.max_rows_x_T, b.cnt.data_ptr(), b.V.data_ptr(),
+              torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    hits = b.hits.cpu().numpy().reshape(Nm, T, 4)
+    uniq = b.uniq.cpu().numpy().reshape(Nm, T)
+    V = b.V.cpu().numpy().reshape(Nm, T)
+    for q in range(Nm):
+        n = int(npts[q])
+        h, u = ko.point_votes(tracks[q][:, :n], labels, 0, T - 1, nbins=4)
+        assert np.array_equal(u, uniq[q]) and np.array_equal(h, hits[q]), q
+        assert np.array_equal(V[q], ko.visibility_mean(vis[q][:, :n]), equal_nan=True), q
+
+
+@pytest.mark.parametrize("eps,ms", [(0.2, 5), (0.1, 5), (0.1, 3), (0.05, 5)])
+def test_hamming_dbscan_vs_oracle(eps, ms):
+    import ctypes as C
+    from s2d_b200 import _lib
+    rng = np.random.default_rng(11)
+    dev = _dev()
+    for it in range(25):
+        n = int(rng.integers(1, 400))
+        d = int(rng.integers(1, 200))
+        if it == 0:
+            n, d = 3000, 2100          # several word chunks and many row tiles
+        base = rng.random((int(rng.integers(1, 6)), d)) < 0.5
+        X = base[rng.integers(0, len(base), n)] ^ (rng.random((n, d)) < rng.choice([0.0, 0.02, 0.08]))
+        if it % 3 == 0:
+            X[rng.integers(0, n, max(1, n // 4))] = False
+        stride = (d + 31) // 32
+        pad = np.zeros((n, stride * 32), bool)
+        pad[:, :d] = X
+        words = np.packbits(pad.reshape(n, stride, 32), axis=-1, bitorder="little").view(np.uint32).reshape(n, stride)
+        bits = torch.from_numpy(words.view(np.int32).copy()).to(dev)
+        nw = C.c_int64()
+        _lib.call("s2d_dbscan_work_ints", n, 1, C.byref(nw))
+        work = torch.empty(nw.value + 2, dtype=torch.int32, device=dev)
+        out = torch.empty(n, dtype=torch.int32, device=dev)
+        _lib.call("s2d_hamming_dbscan", bits.data_ptr(), n, stride, d, eps, ms, work.data_ptr(), out.data_ptr(),
+                  torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), ko.dbscan_hamming(X, eps, ms)), (it, n, d)
+
+
+def test_overlap_bits_vs_oracle():
+    from s2d_b200 import _lib
+    rng = np.random.default_rng(3)
+    dev = _dev()
+    st = torch.cuda.current_stream().cuda_stream
+    for (Na, Nb, H, W) in [(5, 7, 30, 50), (70, 20, 96, 128), (33, 65, 100, 333)]:
+        A = (rng.random((Na, H, W)) < 0.05).astype(np.uint8) * 255
+        Bm = (rng.random((Nb, H, W)) < 0.4).astype(np.uint8)
+        npix = H * W
+        nw = (npix + 31) // 32
+        dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(Bm).to(dev)
+        bA = torch.empty(Na * nw, dtype=torch.int32, device=dev)
+        bB = torch.empty(Nb * nw, dtype=torch.int32, device=dev)
+        _lib.call("s2d_pack_bits", dA.data_ptr(), Na, npix, bA.data_ptr(), st)
+        _lib.call("s2d_pack_bits", dB.data_ptr(), Nb, npix, bB.data_ptr(), st)
+        I = torch.empty(Na * Nb, dtype=torch.int32, device=dev)
+        aA = torch.empty(Na, dtype=torch.int32, device=dev)
+        aB = torch.empty(Nb, dtype=torch.int32, device=dev)
+        _lib.call("s2d_overlap_bits", bA.data_ptr(), Na, bB.data_ptr(), Nb, nw, I.data_ptr(), aA.data_ptr(),
+                  aB.data_ptr(), st)
+        torch.cuda.synchronize()
+        rI, rA, rB = ko.overlap_counts(A, Bm)
+        assert np.array_equal(I.cpu().numpy().reshape(Na, Nb), rI)
+        assert np.array_equal(aA.cpu().numpy(), rA) and np.array_equal(aB.cpu().numpy(), rB)
+
+
+def test_dense_overlap_equals_sparse_votes(golden_case):
+    """K1 on rasterised tracks x one-hot masks == K2's hits."""
+    from s2d_b200 import _lib
+    from s2d_b200.pipeline import Batch
+    name, g, labels, tracks, vis = golden_case
+    dev = _dev()
+    st = torch.cuda.current_stream().cuda_stream
+    T, H, W = labels.shape
+    Nm, _, P, _ = tracks.shape
+    b = Batch([_video(labels, tracks, vis)])
+    b.votes_all()
+    L = b.host_descs[0].L
+    hits = b.hits.cpu().numpy().reshape(Nm, T, L)
+    npix, nw = H * W, (H * W + 31) // 32
+    nq = min(Nm, 6)
+    planes = torch.empty((T, H, W), dtype=torch.uint8, device=dev)
+    for q in range(nq):
+        tq = torch.from_numpy(np.ascontiguousarray(tracks[q])).to(dev)
+        _lib.call("s2d_rasterise_tracks", tq.data_ptr(), T, P, H, W, planes.data_ptr(), st)
+        torch.cuda.synchronize()
+        ref_planes = np.stack([ko.rasterise_tracks(tracks[q][t], H, W) for t in range(T)])
+        assert np.array_equal(planes.cpu().numpy(), ref_planes)
+        for t in range(0, T, max(1, T // 3)):
+            labs = np.unique(labels[t])
+            onehot = np.stack([(labels[t] == l) for l in labs]).astype(np.uint8)
+            dB = torch.from_numpy(onehot).to(dev)
+            bA = torch.empty(nw, dtype=torch.int32, device=dev)
+            bB = torch.empty(len(labs) * nw, dtype=torch.int32, device=dev)
+            _lib.call("s2d_pack_bits", planes[t].data_ptr(), 1, npix, bA.data_ptr(), st)
+            _lib.call("s2d_pack_bits", dB.data_ptr(), len(labs), npix, bB.data_ptr(), st)
+            I = torch.empty(len(labs), dtype=torch.int32, device=dev)
+            _lib.call("s2d_overlap_bits", bA.data_ptr(), 1, bB.data_ptr(), len(labs), nw, I.data_ptr(), None, None, st)
+            torch.cuda.synchronize()
+            assert np.array_equal(I.cpu().numpy(), hits[q, t, labs]), (name, q, t)

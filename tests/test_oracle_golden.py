@@ -53,3 +53,27 @@ def test_dbscan_restatement_vs_sklearn(eps, ms):
         for arr in (X, X.astype(np.float32)):
             ref = DBSCAN(eps=eps, min_samples=ms, metric="hamming").fit(arr).labels_
             assert np.array_equal(ref, ko.dbscan_hamming(arr, eps, ms)), (it, n, d)
+
+
+def test_dense_port_matches_reference_pairs(golden_case):
+    """the dense torch-CPU port used as bench.py's CPU baseline reproduces the reference's
+    per-pair (intersection, union, iou) and match lists."""
+    import torch
+    from oracle import dense_port
+    name, g, labels, tracks, vis = golden_case
+    if g["status"] != 1:
+        pytest.skip("video fails in the reference")
+    T, H, W = labels.shape
+    lab = torch.from_numpy(labels.astype(np.int64))[..., None]
+    qs = g["queries"][:: max(1, len(g["queries"]) // 4)]
+    for q in qs:
+        row = q["overall_mask_id"]
+        m, comps, o2 = dense_port.match_query_dense(lab, torch.from_numpy(tracks[row]), q["v_range"][0],
+                                                    q["v_range"][1], H, W, g["matching_threshold"])
+        assert [[c[0], c[1], c[2], c[3]] for c in comps] == [[c[0], c[1], c[3], c[4]] for c in q["comps"]]
+        assert o2 == q["one2x"]
+        gid = {(c[0], c[1]): c[2] for c in q["comps"]}
+        assert [gid[fm] for fm in m] == q["matches"]
+    V = dense_port.visibility_rows(torch.from_numpy(vis.astype(bool))).numpy()
+    ref = np.asarray([r["visibility"] for r in g["visibility_rows"]], np.float32)
+    assert np.array_equal(V, ref)
