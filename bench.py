@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Keymask-discovery throughput (frames/s) on B200 - BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|target] [--impl reference]
+
+A step = one pass of the whole hot path (stages A-D: label stats, visibility reduce, DBSCAN #1,
+windows, point votes, selection, grouping) over one batch of synthetic videos per GPU. The
+default workload is BASELINE.json configs[1]: 64 videos x 36 frames 720p, 20 masks/frame,
+4096 tracks per query (one such batch per GPU: videos are independent, so N GPUs run N batches
+- weak scaling, no collective on the data path). One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (videos per GPU, T, H, W, masks/frame, tracks/query, description)
+    "c2": (64, 36, 720, 1280, 20, 4096, "YouTubeVIS-2021-shaped batch: 64 videos x 36 frames 720p, 20 masks/frame, 4k tracks"),
+    "c1": (1, 24, 480, 854, 10, 1000, "single synthetic 24-frame 480x854 video, 10 masks/frame, 1k tracks"),
+    "target": (64, 36, 480, 854, 20, 4096, "480p videos, 20 masks/frame, 4k tracks (north_star target shape)"),
+    "tiny": (4, 12, 120, 160, 6, 256, "tiny self-test shape"),
+}
+METRIC = "keymask_discovery_frames_per_sec"
+UNIT = "frames/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_videos(workload, device, seed0):
+    import torch
+    from s2d_b200.pipeline import VideoInput
+    from s2d_b200.synth import make_scene_device
+    nvid, T, H, W, M, P, _ = WORKLOADS[workload]
+    vids = []
+    for i in range(nvid):
+        sc = make_scene_device(seed0 + i, T, H, W, M, P, device)
+        vids.append(VideoInput(sc["labels"], sc["tracks"], sc["vis"], max_label=M, name=f"v{i}"))
+    torch.cuda.synchronize(device)
+    return vids
+
+
+def cpu_sample(vid, nq, threads=None):
+    """Dense torch-CPU port of the reference (oracle/dense_port.py) on `nq` queries of one video over
+    the whole video as window; returns (frames/s extrapolated to the video, seconds, pairs)."""
+    import numpy as np
+    import torch
+    from oracle import dense_port
+    if threads:
+        torch.set_num_threads(threads)
+    labels = vid.labels.cpu().numpy()
+    T = labels.shape[0]
+    Nm = vid.tracks.shape[0]
+    qs = list(np.linspace(0, Nm - 1, nq).astype(int))
+    tracks = {int(q): vid.tracks[int(q)].cpu().numpy() for q in qs}
+    vis = {int(q): vid.vis[int(q)].cpu().numpy() for q in qs}
+    lab = torch.from_numpy(labels.astype(np.int64))[..., None]
+    t0 = time.perf_counter()
+    npairs = 0
+    for q in qs:
+        _ = dense_port.visibility_rows(torch.from_numpy(vis[int(q)][None].astype(bool)))
+        m, c, o = dense_port.match_query_dense(lab, torch.from_numpy(tracks[int(q)]), 0, T - 1,
+                                               labels.shape[1], labels.shape[2], 0.5)
+        npairs += len(c)
+    dt = time.perf_counter() - t0
+    per_video = dt / len(qs) * Nm
+    return T / per_video, dt, npairs, len(qs)
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (dense torch-CPU port, all host threads) on a
+    bounded sample of the same workload. Rank 0 only."""
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    nvid, T, H, W, M, P, desc = WORKLOADS[args.workload]
+    dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
+    from s2d_b200.pipeline import VideoInput
+    from s2d_b200.synth import make_scene_device
+    sc = make_scene_device(2024, T, H, W, M, P, dev)
+    vid = VideoInput(sc["labels"], sc["tracks"], sc["vis"], max_label=M)
+    nq = args.ref_queries
+    for _ in range(args.warmup):
+        cpu_sample(vid, 1)
+    vals, secs = [], []
+    for _ in range(args.steps):
+        fps, dt, npairs, n = cpu_sample(vid, nq)
+        vals.append(fps); secs.append(dt)
+    v = sum(vals) / len(vals)
+    cores = torch.get_num_threads()
+    sample = (f"{nq} of {vid.tracks.shape[0]} queries of one {args.workload} video per step, full-video window "
+              f"({T} frames x ~{M} masks per query), dense torch-CPU port of cotracker_matching.extract_mask_matches; "
+              f"frames/s extrapolated linearly in queries")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000 * sum(secs) / len(secs), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64/u8 (torch CPU)", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "videos_per_gpu": nvid},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-queries", type=int, default=2, help="queries per step of the reference arm")
+    ap.add_argument("--cpu-queries", type=int, default=48, help="queries in the cpu_baseline sample")
+    ap.add_argument("--videos", type=int, default=0, help="override videos per GPU (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.videos > 0:
+        w = WORKLOADS[args.workload]
+        WORKLOADS[args.workload] = (args.videos,) + w[1:]
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from s2d_b200.pipeline import Batch, Params
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    nvid, T, H, W, M, P, desc = WORKLOADS[args.workload]
+    vids = build_videos(args.workload, dev, 2024 + 1000 * rank)
+    batch = Batch(vids)
+    params = Params()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        batch.run(params)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    timers = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    launches = 0
+    for _ in range(args.steps):
+        launches += batch.run(params, timers=timers)
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    frames = nvid * T * world
+    value = frames * args.steps / (ms_max / 1000.0)
+
+    stage_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in timers.items()}
+
+    # ---- roofline of the dominant kernel (K2 point votes), algorithmic bytes / measured time
+    summ = batch.fetch_summary()
+    ri = summ["rowinfo"]
+    ok = np.repeat(summ["vidinfo"][:, 1] > 0, [d.Nm for d in batch.host_descs])
+    cand = (ri[:, 1] >= 0) & ok
+    tiles = int(((ri[:, 3] - ri[:, 2] + 1) * cand).sum())
+    alg_bytes = 8 * P * tiles + nvid * T * H * W + 4 * (M + 1 + 1) * tiles
+    peak, peak_src = _peaks()
+    k2_ms = stage_ms["point_votes"]
+    achieved = alg_bytes / (k2_ms / 1000.0) / 1e9
+    vr_bytes = sum(d.Nm * d.T * d.P + 8 * d.Nm * d.T for d in batch.host_descs)
+    roofline = {"kernel": "point_votes_kernel<256,16,true>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k2_ms, "tiles_per_launch": tiles,
+                "share_of_step": k2_ms / (ms / args.steps),
+                "vis_reduce": {"achieved": vr_bytes / (stage_ms["vis_reduce"] / 1000.0) / 1e9,
+                               "frac": vr_bytes / (stage_ms["vis_reduce"] / 1000.0) / 1e9 / peak,
+                               "algorithmic_bytes_per_launch": vr_bytes, "ms_per_launch": stage_ms["vis_reduce"]}}
+
+    # ---- parity spot check against the oracle (outside the timed region)
+    parity = "skipped"
+    if rank == 0:
+        from oracle import keymask_oracle as ko
+        v0 = vids[0]
+        lab_h = v0.labels.cpu().numpy()
+        d0 = batch.host_descs[0]
+        hits = batch.hits[d0.hits_off:d0.hits_off + d0.Nm * d0.T * d0.L].cpu().numpy().reshape(d0.Nm, d0.T, d0.L)
+        uniq = batch.uniq[d0.vt_off:d0.vt_off + d0.Nm * d0.T].cpu().numpy().reshape(d0.Nm, d0.T)
+        qs = [q for q in np.linspace(0, d0.Nm - 1, 6).astype(int) if ri[q, 1] >= 0]
+        good = True
+        for q in qs:
+            a, b = int(ri[q, 2]), int(ri[q, 3])
+            h, u = ko.point_votes(v0.tracks[int(q)].cpu().numpy(), lab_h, a, b, nbins=d0.L)
+            good &= bool(np.array_equal(u, uniq[q, a:b + 1]) and np.array_equal(h, hits[q, a:b + 1]))
+        Vd = batch.V[d0.vt_off:d0.vt_off + d0.Nm * d0.T].cpu().numpy().reshape(d0.Nm, d0.T)
+        good &= bool(np.array_equal(Vd[qs], ko.visibility_mean(v0.vis[qs].cpu().numpy())))
+        parity = "ok" if good else "MISMATCH"
+
+    # ---- e2e: host buffers, H2D of every video's inputs + D2H of the summary inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, vids, dev, world, params, barrier)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        fps, dt, npairs, n = cpu_sample(vids[0], args.cpu_queries)
+        cpu = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": (f"{n} of {vids[0].tracks.shape[0]} queries of video 0, full-video window, {npairs} (query,mask) "
+                          f"pairs in {dt:.1f} s with the dense torch-CPU port of the reference (oracle/dense_port.py); "
+                          f"frames/s extrapolated linearly in queries")}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (f32 tracks, f64 scores)",
+                "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {desc}", "videos_per_gpu": nvid, "frames_per_video": T,
+                           "resolution": [H, W], "masks_per_frame": M, "tracks_per_query": P,
+                           "queries_per_video": int(batch.host_descs[0].Nm), "partition": f"by video, {world} GPU(s)",
+                           "cache": "inputs per step (tracks+flags+labels) >> 126 MB L2, no flush needed",
+                           "input_bytes_per_step_per_gpu": int(sum(v.tracks.numel() * 4 + v.vis.numel() + v.labels.numel() for v in vids))},
+                "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "stage_ms": stage_ms, "parity_check": parity, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, vids, dev, world, params, barrier):
+    """Same metric through the public API with HOST buffers: every step copies every video's inputs
+    from pinned host memory (a pool of distinct videos, cycled), runs the path, reads the summary
+    back. Chunks of videos are double-buffered on two streams so copies overlap compute."""
+    import torch
+    import torch.distributed as dist
+    from s2d_b200.pipeline import Batch, VideoInput
+    nvid, T, H, W, M, P, _ = WORKLOADS[args.workload]
+    chunk = min(4, nvid)
+    npool = min(nvid, 2 * chunk)
+    pool = []
+    for i in range(npool):
+        v = vids[i]
+        pool.append((v.labels.cpu().pin_memory(), v.tracks.cpu().pin_memory(), v.vis.cpu().pin_memory()))
+    # two device staging sets of `chunk` videos each
+    sets = []
+    for s in range(2):
+        # set s, slot j always receives pool video (s*chunk + j) % npool -> same shapes every chunk
+        src = [vids[(s * chunk + j) % npool] for j in range(chunk)]
+        dv = [VideoInput(torch.empty_like(v.labels), torch.empty_like(v.tracks), torch.empty_like(v.vis),
+                         max_label=M) for v in src]
+        b = Batch(dv)
+        outs_host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                     for t in (b.vidinfo, b.clusterinfo, b.rowinfo, b.glabel, b.one2x)]
+        sets.append((dv, b, outs_host))
+    copy_st = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    comp_st = torch.cuda.Stream(dev)
+    nchunks = (nvid + chunk - 1) // chunk
+    h2d = sum(sum(x.numel() * x.element_size() for x in pool[(c * chunk + j) % npool])
+              for c in range(nchunks) for j in range(chunk))
+    d2h = 0
+    steps = max(2, min(args.steps, 5))
+
+    def one_step():
+        nonlocal d2h
+        d2h = 0
+        done = [None, None]
+        outs = []
+        for c in range(nchunks):
+            s = c % 2
+            dv, b, host = sets[s]
+            if done[s] is not None:
+                copy_st[s].wait_event(done[s])           # staging set free again
+            with torch.cuda.stream(copy_st[s]):
+                for j in range(chunk):
+                    hl, ht, hv = pool[(c * chunk + j) % npool]
+                    dv[j].labels.copy_(hl, non_blocking=True)
+                    dv[j].tracks.copy_(ht, non_blocking=True)
+                    dv[j].vis.copy_(hv, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record()
+            comp_st.wait_event(ready)
+            with torch.cuda.stream(comp_st):
+                b.run(params)
+                for hbuf, t in zip(host, (b.vidinfo, b.clusterinfo, b.rowinfo, b.glabel, b.one2x)):
+                    hbuf.copy_(t, non_blocking=True)
+                done[s] = torch.cuda.Event()
+                done[s].record()
+            outs.append(host)   # consumed by the caller after the step's final synchronize
+            d2h += sum(t.numel() * t.element_size() for t in host)
+        comp_st.synchronize()
+        return outs
+
+    one_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    return {"value": nvid * T * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": 1000 * dt / steps,
+            "note": f"{nchunks} chunks of {chunk} videos per step from a pinned pool of {npool} distinct videos, "
+                    f"copies double-buffered against compute; PCIe-bound"}
+
+
+if __name__ == "__main__":
+    main()

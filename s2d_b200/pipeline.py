@@ -23,12 +23,15 @@ from ._lib import (S2D_CLINFO_WORDS, S2D_MAX_CLUSTERS, S2D_MAX_LABELS, S2D_VIDIN
 @dataclass
 class VideoInput:
     """Device tensors of one video (see s2d_b200.synth for the layout)."""
-    labels: torch.Tensor                    # u8  [T,H,W]
-    tracks: torch.Tensor                    # f32 [Nm,T,P,2]
-    vis: torch.Tensor                       # u8/bool [Nm,T,P]
+    labels: Optional[torch.Tensor] = None   # u8  [T,H,W]
+    tracks: Optional[torch.Tensor] = None   # f32 [Nm,T,P,2]
+    vis: Optional[torch.Tensor] = None      # u8/bool [Nm,T,P]
     npts: Optional[torch.Tensor] = None     # i32 [Nm]
     max_label: Optional[int] = None         # upper bound of the label ids (default 255)
     name: str = ""
+    # stage-wise callers (the file-based drop-in modules) may omit tensors a stage does not read
+    # and give the missing dimensions here: keys T, H, W, P, Nm
+    dims: Optional[dict] = None
 
 
 @dataclass
@@ -57,7 +60,9 @@ class Batch:
     def __init__(self, videos: List[VideoInput], device=None, keep_votes: bool = True):
         assert len(videos) > 0
         self.videos = videos
-        self.device = device or videos[0].labels.device
+        first = next(t for t in (videos[0].labels, videos[0].tracks, videos[0].vis) if t is not None) \
+            if any(t is not None for t in (videos[0].labels, videos[0].tracks, videos[0].vis)) else None
+        self.device = device or (first.device if first is not None else torch.device("cuda:0"))
         dev = self.device
         nv = len(videos)
         descs = (VideoDesc * nv)()
@@ -67,22 +72,36 @@ class Batch:
         self.vec4 = 1
         self._keep = []
         for i, v in enumerate(videos):
-            T, H, W = v.labels.shape
-            Nm, T2, P, two = v.tracks.shape
-            assert two == 2 and T2 == T and tuple(v.vis.shape) == (Nm, T, P), "inconsistent video tensors"
-            assert v.labels.dtype == torch.uint8 and v.tracks.dtype == torch.float32
-            assert v.vis.dtype in (torch.uint8, torch.bool)
-            assert v.labels.is_contiguous() and v.tracks.is_contiguous() and v.vis.is_contiguous()
+            dm = dict(v.dims or {})
+            if v.labels is not None:
+                assert v.labels.dtype == torch.uint8 and v.labels.is_contiguous() and v.labels.dim() == 3
+                dm["T"], dm["H"], dm["W"] = v.labels.shape
+            if v.tracks is not None:
+                assert v.tracks.dtype == torch.float32 and v.tracks.is_contiguous() and v.tracks.dim() == 4
+                assert v.tracks.shape[3] == 2 and dm.setdefault("T", v.tracks.shape[1]) == v.tracks.shape[1]
+                dm["Nm"], dm["P"] = v.tracks.shape[0], v.tracks.shape[2]
+            if v.vis is not None:
+                assert v.vis.dtype in (torch.uint8, torch.bool) and v.vis.is_contiguous() and v.vis.dim() == 3
+                if v.tracks is not None:
+                    assert tuple(v.vis.shape) == (dm["Nm"], dm["T"], dm["P"]), "inconsistent video tensors"
+                else:
+                    assert dm.setdefault("T", v.vis.shape[1]) == v.vis.shape[1]
+                    dm["Nm"], dm["P"] = v.vis.shape[0], v.vis.shape[2]
+            T, H, W = dm["T"], dm.get("H", 1), dm.get("W", 1)
+            Nm, P = dm["Nm"], dm.get("P", 1)
+            assert Nm >= 1 and T >= 1
             assert H <= 65535 and W <= 65535 and P <= 32768 and T <= 1024
             L = min(S2D_MAX_LABELS, (v.max_label if v.max_label is not None else 255) + 1)
             d = descs[i]
             d.T, d.H, d.W, d.P, d.Nm, d.L = T, H, W, P, Nm, L
             d.TW, d.NW = (T + 31) // 32, (Nm + 31) // 32
             d.row0, d.frame0 = row0, frame0
-            d.labels, d.tracks, d.vis = v.labels.data_ptr(), v.tracks.data_ptr(), v.vis.data_ptr()
+            d.labels = v.labels.data_ptr() if v.labels is not None else None
+            d.tracks = v.tracks.data_ptr() if v.tracks is not None else None
+            d.vis = v.vis.data_ptr() if v.vis is not None else None
             d.npts = v.npts.data_ptr() if v.npts is not None else None
             d.vt_off, d.hits_off, d.xbits_off, d.mbits_off = vt, hits, xw, mw
-            if P % 2 or v.tracks.data_ptr() % 16:
+            if P % 2 or (v.tracks is not None and v.tracks.data_ptr() % 16):
                 self.vec4 = 0
             row0 += Nm; frame0 += T; vt += Nm * T; hits += Nm * T * L
             xw += Nm * d.TW; mw += Nm * d.NW
@@ -133,39 +152,52 @@ class Batch:
         self.kernel_launches_per_run = 0
 
     # ------------------------------------------------------------------ enqueue
-    def run(self, params: Params = Params(), stream=None, stages: str = "ABD"):
+    def run(self, params: Params = Params(), stream=None, stages: str = "LVBD", timers=None):
         """Enqueue the whole path on `stream` (default: torch's current stream). Returns the
-        number of kernel launches enqueued."""
+        number of kernel launches enqueued. `timers`: optional dict name -> list; a pair of CUDA
+        events is recorded around every C-ABI call on torch's current stream (bench.py)."""
         st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
         p = lambda t: t.data_ptr()
         d, nv = p(self.descs), self.nv
         launches = 0
-        if "A" in stages:
-            _lib.call("s2d_label_stats", d, nv, self.max_T, self.max_npix, self.total_frames, p(self.area),
-                      p(self.gid_of), p(self.frameinfo), p(self.qframe), p(self.qlabel), p(self.vidinfo), st)
-            _lib.call("s2d_vis_reduce", d, nv, self.max_rows_x_T, p(self.cnt), p(self.V), st)
-            launches += 3
+
+        def call(tag, nk, name, *args):
+            nonlocal launches
+            if timers is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _lib.call(name, *args)
+                e1.record()
+                timers.setdefault(tag, []).append((e0, e1))
+            else:
+                _lib.call(name, *args)
+            launches += nk
+
+        if "L" in stages:
+            call("label_stats", 2, "s2d_label_stats", d, nv, self.max_T, self.max_npix, self.total_frames,
+                 p(self.area), p(self.gid_of), p(self.frameinfo), p(self.qframe), p(self.qlabel), p(self.vidinfo), st)
+        if "V" in stages:
+            call("vis_reduce", 1, "s2d_vis_reduce", d, nv, self.max_rows_x_T, p(self.cnt), p(self.V), st)
         if "B" in stages:
-            _lib.call("s2d_binarize", d, nv, self.max_rows_x_TW, p(self.V),
-                      float(np.float32(params.visibility_threshold)), p(self.xbits), st)
-            _lib.call("s2d_dbscan_visibility", d, nv, self.max_Nm, self.max_TW, self.total_rows, p(self.xbits),
-                      params.dbscan1_eps, params.dbscan1_min_samples, p(self.dbwork), p(self.labels1),
-                      p(self.vidinfo), st)
-            _lib.call("s2d_windows", d, nv, self.max_rows_x_TW, self.max_TW, self.total_rows, self.total_vt,
-                      p(self.xbits), p(self.labels1), p(self.qframe), float(np.float32(params.winner_fraction)),
-                      p(self.ccount), p(self.clrow), p(self.majbits), p(self.rsbits), p(self.rebits),
-                      p(self.winbits), p(self.rowinfo), p(self.vidinfo), p(self.clusterinfo), st)
-            launches += 1 + 5 + 2
+            call("binarize", 1, "s2d_binarize", d, nv, self.max_rows_x_TW, p(self.V),
+                 float(np.float32(params.visibility_threshold)), p(self.xbits), st)
+            call("dbscan1", 5, "s2d_dbscan_visibility", d, nv, self.max_Nm, self.max_TW, self.total_rows,
+                 p(self.xbits), params.dbscan1_eps, params.dbscan1_min_samples, p(self.dbwork), p(self.labels1),
+                 p(self.vidinfo), st)
+            call("windows", 2, "s2d_windows", d, nv, self.max_rows_x_TW, self.max_TW, self.total_rows,
+                 self.total_vt, p(self.xbits), p(self.labels1), p(self.qframe),
+                 float(np.float32(params.winner_fraction)), p(self.ccount), p(self.clrow), p(self.majbits),
+                 p(self.rsbits), p(self.rebits), p(self.winbits), p(self.rowinfo), p(self.vidinfo),
+                 p(self.clusterinfo), st)
         if "D" in stages:
-            _lib.call("s2d_point_votes", d, nv, self.max_rows_x_T, self.max_P, self.vec4, p(self.rowinfo),
-                      p(self.vidinfo), p(self.hits), p(self.uniq), st)
-            _lib.call("s2d_select", d, nv, self.max_Nm, self.total_mw, p(self.hits), p(self.uniq), p(self.gid_of),
-                      p(self.rowinfo), params.matching_threshold, params.one2x_iou, params.one2x_frames,
-                      p(self.mbits), p(self.one2x), p(self.nmatch), p(self.vidinfo), st)
-            _lib.call("s2d_group", d, nv, self.max_Nm, self.max_NW, self.total_rows, p(self.mbits), p(self.rowinfo),
-                      p(self.one2x), p(self.grpwork), p(self.glabel), p(self.grp_n), p(self.grp_one2x),
-                      p(self.vidinfo), p(self.clusterinfo), st)
-            launches += 1 + 1 + 1 + 7
+            call("point_votes", 1, "s2d_point_votes", d, nv, self.max_rows_x_T, self.max_P, self.vec4,
+                 p(self.rowinfo), p(self.vidinfo), p(self.hits), p(self.uniq), st)
+            call("select", 1, "s2d_select", d, nv, self.max_Nm, self.total_mw, p(self.hits), p(self.uniq),
+                 p(self.gid_of), p(self.rowinfo), params.matching_threshold, params.one2x_iou,
+                 params.one2x_frames, p(self.mbits), p(self.one2x), p(self.nmatch), p(self.vidinfo), st)
+            call("group", 7, "s2d_group", d, nv, self.max_Nm, self.max_NW, self.total_rows, p(self.mbits),
+                 p(self.rowinfo), p(self.one2x), p(self.grpwork), p(self.glabel), p(self.grp_n),
+                 p(self.grp_one2x), p(self.vidinfo), p(self.clusterinfo), st)
         self.kernel_launches_per_run = launches
         return launches
 

@@ -173,12 +173,9 @@ def scene_object_map(scene: Scene) -> np.ndarray:
 
 def make_scene_device(seed: int, T: int, H: int, W: int, M: int, P: int, device, *,
                       noise: float = 0.7, occlude: bool = True):
-    """Same scene family as make_scene, built directly in HBM with torch ops.
-
-    Returns dict(labels u8 [T,H,W], tracks f32 [Nm,T,P,2], vis u8 [Nm,T,P],
-    query_frame i32 [Nm], query_label i32 [Nm]). Background is always present, every object
-    keeps a visible pixel (objects are painted small enough and re-checked on the host for
-    the tiny per-frame presence table only)."""
+    """Same scene family as make_scene, built directly in HBM with torch ops (vectorised per
+    frame). Returns dict(labels u8 [T,H,W], tracks f32 [Nm,T,P,2], vis u8 [Nm,T,P],
+    query_frame i32 [Nm], query_label i32 [Nm]). Background is always present."""
     import torch
 
     g = torch.Generator(device="cpu")
@@ -192,59 +189,68 @@ def make_scene_device(seed: int, T: int, H: int, W: int, M: int, P: int, device,
     vy = u(-0.006, 0.006, M) * H
     occl = (T // 3, (2 * T) // 3) if occlude else (0, 0)
 
-    yy = torch.arange(H, device=device, dtype=torch.float32)[:, None]
-    xx = torch.arange(W, device=device, dtype=torch.float32)[None, :]
+    f32 = torch.float32
+    yy = torch.arange(H, device=device, dtype=f32)[None, :, None]
+    xx = torch.arange(W, device=device, dtype=f32)[None, None, :]
+    ts = torch.arange(T, device=device, dtype=f32)[:, None, None]
     omap = torch.full((T, H, W), -1, dtype=torch.int16, device=device)
-    for t in range(T):
-        for k in range(M):
-            if k == 0 and occl[0] <= t < occl[1]:
-                continue
-            ccx = float(cx[k] + vx[k] * t)
-            ccy = float(cy[k] + vy[k] * t)
-            if k % 2:
-                m = ((xx - ccx) / float(rx[k])) ** 2 + ((yy - ccy) / float(ry[k])) ** 2 <= 1.0
-            else:
-                m = ((xx - ccx).abs() <= float(rx[k])) & ((yy - ccy).abs() <= float(ry[k]))
-            omap[t][m] = k
-    # presence [T,M] and rank labels
-    onehot_cnt = torch.zeros((T, M + 1), dtype=torch.int64, device=device)
-    onehot_cnt.scatter_add_(1, (omap.reshape(T, -1).long() + 1),
-                            torch.ones((T, H * W), dtype=torch.int64, device=device))
-    area = onehot_cnt[:, 1:]                                   # [T,M]
-    pres = area > 0
+    for k in range(M):
+        ccx = float(cx[k]) + float(vx[k]) * ts
+        ccy = float(cy[k]) + float(vy[k]) * ts
+        if k % 2:
+            m = ((xx - ccx) / float(rx[k])) ** 2 + ((yy - ccy) / float(ry[k])) ** 2 <= 1.0
+        else:
+            m = ((xx - ccx).abs() <= float(rx[k])) & ((yy - ccy).abs() <= float(ry[k]))
+        if k == 0 and occl[1] > occl[0]:
+            m[occl[0]:occl[1]] = False
+        omap[m] = k
+        del m
+    flat = omap.reshape(T, -1).long() + 1
+    area = torch.zeros((T, M + 1), dtype=torch.int64, device=device)
+    area.scatter_add_(1, flat, torch.ones_like(flat))
+    pres = area[:, 1:] > 0                                     # [T,M]
     rank = torch.cumsum(pres.long(), dim=1) * pres.long()      # 1-based rank among present
     lut = torch.cat([torch.zeros((T, 1), dtype=torch.long, device=device), rank], dim=1)
-    labels = torch.gather(lut, 1, omap.reshape(T, -1).long() + 1).reshape(T, H, W).to(torch.uint8)
+    labels = torch.gather(lut, 1, flat).reshape(T, H, W).to(torch.uint8)
+    del flat, omap
 
-    pres_h = pres.cpu()
-    rank_h = rank.cpu()
-    qf, ql, qk = [], [], []
-    for t in range(T):
-        for k in range(M):
-            if pres_h[t, k]:
-                qf.append(t); ql.append(int(rank_h[t, k])); qk.append(k)
-    Nm = len(qf)
-    qf_t = torch.tensor(qf, dtype=torch.int32, device=device)
-    ql_t = torch.tensor(ql, dtype=torch.int32, device=device)
-    qk_t = torch.tensor(qk, dtype=torch.long, device=device)
+    pres_h, rank_h = pres.cpu(), rank.cpu()
+    n_t = pres_h.sum(1).tolist()
+    Nm = int(sum(n_t))
+    qf = torch.repeat_interleave(torch.arange(T), torch.tensor(n_t)).to(torch.int32)
+    ql = torch.cat([torch.arange(1, n + 1) for n in n_t]).to(torch.int32)
 
     dg = torch.Generator(device=device)
     dg.manual_seed(seed * 7919 + 13)
-    tracks = torch.empty((Nm, T, P, 2), dtype=torch.float32, device=device)
+    tracks = torch.empty((Nm, T, P, 2), dtype=f32, device=device)
     vis = torch.empty((Nm, T, P), dtype=torch.uint8, device=device)
-    vx_d = vx.to(device=device, dtype=torch.float32)
-    vy_d = vy.to(device=device, dtype=torch.float32)
-    dts = torch.arange(T, device=device, dtype=torch.float32)
-    pvis_obj = torch.where(pres, 0.95, 0.05).to(torch.float32)  # [T,M]
-    for q in range(Nm):
-        t, lab, k = qf[q], ql[q], qk[q]
-        idx = torch.nonzero(labels[t].reshape(-1) == lab).squeeze(1)
-        sel = idx[torch.randint(0, idx.numel(), (P,), generator=dg, device=device)]
-        px = (sel % W).float() + (torch.rand(P, generator=dg, device=device) - 0.5) * 0.8
-        py = (sel // W).float() + (torch.rand(P, generator=dg, device=device) - 0.5) * 0.8
-        nz = torch.randn((T, P, 2), generator=dg, device=device) * noise
-        nz[t] = 0
-        tracks[q, :, :, 0] = px[None, :] + (vx_d[k] * (dts - t))[:, None] + nz[..., 0]
-        tracks[q, :, :, 1] = py[None, :] + (vy_d[k] * (dts - t))[:, None] + nz[..., 1]
-        vis[q] = (torch.rand((T, P), generator=dg, device=device) < pvis_obj[:, k][:, None]).to(torch.uint8)
-    return dict(labels=labels, tracks=tracks, vis=vis, query_frame=qf_t, query_label=ql_t)
+    vx_d = vx.to(device=device, dtype=f32)
+    vy_d = vy.to(device=device, dtype=f32)
+    dts = torch.arange(T, device=device, dtype=f32)
+    pvis_obj = torch.where(pres, 0.95, 0.05).to(f32)            # [T,M]
+    row = 0
+    for t in range(T):
+        n = n_t[t]
+        if n == 0:
+            continue
+        ks = torch.nonzero(pres[t]).squeeze(1)                  # object index per label 1..n
+        lab_flat = labels[t].reshape(-1)
+        order = torch.argsort(lab_flat, stable=True)
+        counts = torch.bincount(lab_flat.long(), minlength=n + 1)
+        starts = torch.cumsum(counts, 0) - counts
+        r = torch.rand((n, P), generator=dg, device=device)
+        idx = starts[1:n + 1, None] + (r * counts[1:n + 1, None]).long().clamp_(max=int(counts.max()) - 1)
+        idx = torch.minimum(idx, (starts[1:n + 1] + counts[1:n + 1] - 1)[:, None])
+        pix = order[idx]                                        # [n,P]
+        px = (pix % W).to(f32) + (torch.rand((n, P), generator=dg, device=device) - 0.5) * 0.8
+        py = (pix // W).to(f32) + (torch.rand((n, P), generator=dg, device=device) - 0.5) * 0.8
+        nz = torch.randn((n, T, P, 2), generator=dg, device=device) * noise
+        nz[:, t] = 0
+        dt = dts - t
+        blk = tracks[row:row + n]
+        blk[..., 0] = px[:, None, :] + (vx_d[ks][:, None] * dt[None, :])[:, :, None] + nz[..., 0]
+        blk[..., 1] = py[:, None, :] + (vy_d[ks][:, None] * dt[None, :])[:, :, None] + nz[..., 1]
+        pv = pvis_obj[:, ks].t()                                # [n,T]
+        vis[row:row + n] = (torch.rand((n, T, P), generator=dg, device=device) < pv[:, :, None]).to(torch.uint8)
+        row += n
+    return dict(labels=labels, tracks=tracks, vis=vis, query_frame=qf.to(device), query_label=ql.to(device))
