@@ -94,14 +94,14 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_videos(workload, device, seed0):
+def build_videos(workload, device, seed0, point_order="raster"):
     import torch
     from s2d_b200.pipeline import VideoInput
     from s2d_b200.synth import make_scene_device
     nvid, T, H, W, M, P, _ = WORKLOADS[workload]
     vids = []
     for i in range(nvid):
-        sc = make_scene_device(seed0 + i, T, H, W, M, P, device)
+        sc = make_scene_device(seed0 + i, T, H, W, M, P, device, point_order=point_order)
         vids.append(VideoInput(sc["labels"], sc["tracks"], sc["vis"], max_label=M, name=f"v{i}"))
     torch.cuda.synchronize(device)
     return vids
@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--ref-queries", type=int, default=2, help="queries per step of the reference arm")
     ap.add_argument("--cpu-queries", type=int, default=48, help="queries in the cpu_baseline sample")
     ap.add_argument("--videos", type=int, default=0, help="override videos per GPU (profiling runs)")
+    ap.add_argument("--point-order", default="raster", choices=["raster", "random"],
+                    help="order of a query's points: raster (CoTracker-like grid order) or random (worst case)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -203,7 +205,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     nvid, T, H, W, M, P, desc = WORKLOADS[args.workload]
-    vids = build_videos(args.workload, dev, 2024 + 1000 * rank)
+    vids = build_videos(args.workload, dev, 2024 + 1000 * rank, args.point_order)
     batch = Batch(vids)
     params = Params()
 
@@ -294,7 +296,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": f"{args.workload}: {desc}", "videos_per_gpu": nvid, "frames_per_video": T,
                            "resolution": [H, W], "masks_per_frame": M, "tracks_per_query": P,
-                           "queries_per_video": int(batch.host_descs[0].Nm), "partition": f"by video, {world} GPU(s)",
+                           "queries_per_video": int(batch.host_descs[0].Nm), "point_order": args.point_order, "partition": f"by video, {world} GPU(s)",
                            "cache": "inputs per step (tracks+flags+labels) >> 126 MB L2, no flush needed",
                            "input_bytes_per_step_per_gpu": int(sum(v.tracks.numel() * 4 + v.vis.numel() + v.labels.numel() for v in vids))},
                 "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,

@@ -128,10 +128,14 @@ int s2d_windows(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_TW,
  * outside [v0,v1] and videos whose vidinfo[1] < 0 are skipped (hits/uniq left untouched).
  * rowinfo == NULL votes every (q,t); vidinfo == NULL ignores the stage-B status.
  * vec4_ok != 0 promises P even and 16-byte aligned tracks for every video (128-bit loads).
- * H, W <= 65535; P <= 32768. */
-int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_T, int max_P,
-                    int vec4_ok, const int32_t* rowinfo, const int32_t* vidinfo, int32_t* hits,
-                    int32_t* uniq, void* stream);
+ * work: int32 scratch of s2d_point_votes_work_ints(total_rows) elements, 16-byte aligned; with it
+ * (and vec4_ok, P <= 8192) the persistent TMA-fed kernel runs: a device-side plan lists the
+ * (row, frame) tiles, 2 CTAs per SM stream them through a two-stage cp.async.bulk ring. Without
+ * it (work == NULL) the one-CTA-per-tile kernel runs. H, W <= 65535; P <= 32768. */
+int s2d_point_votes_work_ints(int64_t total_rows, int64_t* out);
+int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max_T, int max_Nm, int max_P,
+                    int vec4_ok, int64_t total_rows, const int32_t* rowinfo, const int32_t* vidinfo,
+                    int32_t* work, int32_t* hits, int32_t* uniq, void* stream);
 
 /* K4a. Scores and selection per candidate query: iou = hits/uniq (double), match bit when
  * iou > matching_threshold (cotracker_matching.py:710), one-to-many flag when >= one2x_frames

@@ -2,10 +2,11 @@
 //
 // One CTA per (query q, frame t) tile of P tracked points (8 B each, read exactly once with
 // 128-bit streaming loads). Rounded, in-bounds pixels are de-duplicated in a shared-memory
-// bitmap addressed relative to the tile's bounding box (XOR-swizzled so that neighbouring
-// pixels fall into different banks); the first thread to set a pixel's bit gathers the pixel's
-// label (u8 label map, L2/L1 resident: every query of a video re-reads the same T frames) and
-// votes into a shared histogram through per-thread run-length and warp-level aggregation.
+// bitmap that covers a band of whole frame rows starting at the tile's first occupied row
+// (word index XOR-swizzled so that regular grids of points spread over the banks); the first
+// thread to set a pixel's bit votes the pixel's label (u8 label map, L2/L1 resident: every
+// query of a video re-reads the same T frames) into a shared histogram through per-thread
+// run-length and warp-level aggregation.
 // Output per tile: hits[q,t,0..L) and uniq[q,t] - 4(L+1) bytes against 8P bytes read.
 //
 // Replaces pred_tracks_to_binary_masks + compute_point_mask_intersection over every mask of
@@ -14,157 +15,525 @@
 #include "common.cuh"
 
 #include <limits.h>
+#include <stdlib.h>
 
 namespace s2d {
 
-constexpr int PV_BM_WORDS = 4096;                 // 16 KB bitmap = 131072 pixels per band
+constexpr int PV_BM_WORDS = 8192;                 // 32 KB bitmap = 262144 pixels per band
 constexpr int PV_BM_BITS = PV_BM_WORDS * 32;
+constexpr int PV_WORD_SHIFT = 13;                 // log2(PV_BM_WORDS)
 constexpr uint32_t PV_INVALID = 0xFFFFFFFFu;
 
-__device__ __forceinline__ uint32_t pv_key(float x, float y, float Wf, float Hf) {
-    // torch .round() is round-half-to-even in float32; NaN/inf/huge fail the float compares
-    const float rx = rintf(x), ry = rintf(y);
-    const bool ok = (rx >= 0.f) && (rx < Wf) && (ry >= 0.f) && (ry < Hf);
-    return ok ? (((uint32_t)(int)ry << 16) | (uint32_t)(int)rx) : PV_INVALID;
+// Rounded pixel of one track point as a frame-linear index (iy*W + ix), PV_INVALID if the point
+// does not land inside the frame. cvt.rni is round-half-to-even like torch.round(). fmaxf(v,-1)
+// maps NaN (and everything below -1) to -1, i.e. out of bounds; +inf / huge values saturate to
+// INT_MAX and fail the unsigned compare (the reference's int64 conversion drops all of them too).
+__device__ __forceinline__ uint32_t pv_lin(float x, float y, uint32_t W, uint32_t H) {
+    const uint32_t ix = (uint32_t)__float2int_rn(fmaxf(x, -1.0f));
+    const uint32_t iy = (uint32_t)__float2int_rn(fmaxf(y, -1.0f));
+    return (ix < W && iy < H) ? iy * W + ix : PV_INVALID;
 }
 
+// PTX shl clamps shift amounts above 31: the result is 0 for them, which is exactly "not in
+// this band" below.
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
+}
+
+// Try to claim pixel `lin` in the bitmap band that starts at linear index `base` and covers
+// PV_BM_BITS pixels. Returns nonzero iff this call set the pixel's bit (first point on it).
+// Pixels outside the band (kk >= 2^18, including PV_INVALID and wrapped negatives) OR in 0.
+__device__ __forceinline__ uint32_t pv_claim(uint32_t* bm, uint32_t lin, uint32_t base) {
+    const uint32_t kk = lin - base;
+    const uint32_t w = (kk ^ (kk >> 5)) & (PV_BM_WORDS - 1);   // word index, XOR bank swizzle (bijective)
+    const uint32_t bit = shl_clamp(1u, kk >> PV_WORD_SHIFT);
+    const uint32_t old = atomicOr(&bm[w], bit);
+    return bit & ~old;
+}
+
+// expand the low 4 bits of m into a byte mask (bit i -> byte i = 0xFF)
+__device__ __forceinline__ uint32_t nib2bytes(uint32_t m) {
+    return (((m & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+}
+
+// Votes of one thread: `first` has bit k set when point k was the first on its pixel, lab4 holds
+// the points' labels (4 per word). Runs of equal labels are accumulated in (cur, cnt) and only
+// flushed to the shared histogram when the label changes.
+template <int PPT>
+__device__ __forceinline__ void pv_vote(uint32_t first, const uint32_t (&lab4)[PPT / 4], int& cur, int& cnt, int* hist) {
+#pragma unroll
+    for (int k4 = 0; k4 < PPT / 4; ++k4) {
+        const uint32_t f = (first >> (4 * k4)) & 0xFu;
+        if (f == 0) continue;
+        const uint32_t l4 = lab4[k4];
+        if (cur < 0) cur = (l4 >> (8 * (__ffs(f) - 1))) & 255;
+        const uint32_t diff = (l4 ^ ((uint32_t)cur * 0x01010101u)) & nib2bytes(f);
+        if (diff == 0) {
+            cnt += __popc(f);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!((f >> j) & 1u)) continue;
+                const int lab = (l4 >> (8 * j)) & 255;
+                if (lab != cur) {
+                    if (cnt) atomicAdd(&hist[cur], cnt);
+                    cur = lab; cnt = 0;
+                }
+                ++cnt;
+            }
+        }
+    }
+}
+
+// warp-aggregated flush of the per-thread runs (usually one label per warp)
+__device__ __forceinline__ void pv_flush(int cur, int cnt, int lane, int* hist) {
+    uint32_t remaining = __ballot_sync(0xffffffffu, cnt > 0);
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const int l0 = __shfl_sync(0xffffffffu, cur, leader);
+        const bool mine = (cnt > 0) && (cur == l0);
+        const int sm = __reduce_add_sync(0xffffffffu, mine ? cnt : 0);
+        if (lane == leader) atomicAdd(&hist[l0], sm);
+        remaining &= ~__ballot_sync(0xffffffffu, mine);
+    }
+}
+
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+// ==========================================================================================
+// One CTA per (query, frame) tile. Fallback for odd P / unaligned tracks / P > 8192, and the
+// path used when the caller passes no work buffer.
+// ==========================================================================================
 template <int THREADS, int PPT, bool VEC4>
 __global__ void __launch_bounds__(THREADS)
-point_votes_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __restrict__ rowinfo, const int32_t* __restrict__ vidinfo,
-                   int32_t* __restrict__ hits, int32_t* __restrict__ uniq) {
-    const s2d_video_desc d = descs[blockIdx.y];
-    const int64_t rt = blockIdx.x;
-    if (rt >= (int64_t)d.Nm * d.T) return;
-    if (vidinfo && vidinfo[(int64_t)blockIdx.y * S2D_VIDINFO_WORDS + 1] < 0) return;
-    const int q = (int)(rt / d.T), t = (int)(rt - (int64_t)q * d.T);
+point_votes_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __restrict__ rowinfo,
+                   const int32_t* __restrict__ vidinfo, int32_t* __restrict__ hits,
+                   int32_t* __restrict__ uniq) {
+    const s2d_video_desc* dp = descs + blockIdx.z;
+    const int T = dp->T, Nm = dp->Nm;
+    const int q = blockIdx.y, t = blockIdx.x;
+    if (q >= Nm || t >= T) return;
+    if (vidinfo && vidinfo[(int64_t)blockIdx.z * S2D_VIDINFO_WORDS + 1] < 0) return;
+    const int64_t rt = (int64_t)q * T + t;
     if (rowinfo) {
-        const int4 ri = reinterpret_cast<const int4*>(rowinfo)[d.row0 + q];
+        const int4 ri = reinterpret_cast<const int4*>(rowinfo)[dp->row0 + q];
         if (ri.y < 0 || t < ri.z || t > ri.w) return;
     }
-    const int n = d.npts ? min(max(d.npts[q], 0), d.P) : d.P;
+    const int P = dp->P;
+    const uint32_t W = dp->W, H = dp->H;
+    const int32_t* np = dp->npts;
+    const int n = np ? min(max(np[q], 0), P) : P;
 
     __shared__ __align__(16) uint32_t bm[PV_BM_WORDS];
-    __shared__ int hist[S2D_MAX_LABELS];
-    __shared__ int sbox[4];
+    __shared__ int hist[S2D_MAX_LABELS + 1];          // [256] = number of unique pixels
+    __shared__ uint32_t sbox[2];
 
     const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < PV_BM_WORDS / 4; i += THREADS) reinterpret_cast<uint4*>(bm)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < S2D_MAX_LABELS; i += THREADS) hist[i] = 0;
-    if (tid == 0) { sbox[0] = INT_MAX; sbox[1] = INT_MAX; sbox[2] = -1; sbox[3] = -1; }
+    const float* tp = dp->tracks + rt * P * 2;
+    const uint8_t* lbl = dp->labels + (int64_t)t * (int64_t)(W * H);
 
-    const float* tp = d.tracks + rt * (int64_t)d.P * 2;
-    const uint8_t* lbl = d.labels + (int64_t)t * d.H * d.W;
-    const float Wf = (float)d.W, Hf = (float)d.H;
-
-    // ---- pass 1: load, round, bounds, label gather, bounding box -------------------------
-    uint32_t key[PPT];
-    uint32_t lab4[(PPT + 3) / 4];
+    // ---- pass 1: all loads of the thread in flight at once, then round / bounds ----------
+    uint32_t lin[PPT];
+    if (VEC4) {
+        int4 raw[PPT / 2];
+        const int last4 = max(P / 2 - 1, 0);               // clamp: every load stays inside the tile
 #pragma unroll
-    for (int i = 0; i < (PPT + 3) / 4; ++i) lab4[i] = 0;
-    int xmin = INT_MAX, ymin = INT_MAX, xmax = -1, ymax = -1;
+        for (int i = 0; i < PPT / 2; ++i)
+            raw[i] = ld_stream(reinterpret_cast<const int4*>(tp) + min(i * THREADS + tid, last4));
 #pragma unroll
-    for (int i = 0; i < PPT / 2; ++i) {
-        const int p0 = 2 * (i * THREADS + tid);
-        float4 v = make_float4(-1.f, -1.f, -1.f, -1.f);
-        if (VEC4) {
-            if (p0 + 1 < n) {
-                const int4 r = ld_stream(reinterpret_cast<const int4*>(tp) + (i * THREADS + tid));
-                v = make_float4(__int_as_float(r.x), __int_as_float(r.y), __int_as_float(r.z), __int_as_float(r.w));
-            } else if (p0 < n) {
-                const float2 a = __ldg(reinterpret_cast<const float2*>(tp) + p0);
-                v.x = a.x; v.y = a.y;
-            }
-        } else {
-            if (p0 < n) { const float2 a = __ldg(reinterpret_cast<const float2*>(tp) + p0); v.x = a.x; v.y = a.y; }
-            if (p0 + 1 < n) { const float2 a = __ldg(reinterpret_cast<const float2*>(tp) + p0 + 1); v.z = a.x; v.w = a.y; }
+        for (int i = 0; i < PPT / 2; ++i) {
+            const int p0 = 2 * (i * THREADS + tid);
+            const uint32_t a = pv_lin(__int_as_float(raw[i].x), __int_as_float(raw[i].y), W, H);
+            const uint32_t b = pv_lin(__int_as_float(raw[i].z), __int_as_float(raw[i].w), W, H);
+            lin[2 * i] = (p0 < n) ? a : PV_INVALID;
+            lin[2 * i + 1] = (p0 + 1 < n) ? b : PV_INVALID;
         }
-        key[2 * i] = pv_key(v.x, v.y, Wf, Hf);
-        key[2 * i + 1] = pv_key(v.z, v.w, Wf, Hf);
+    } else {
+        float2 raw[PPT];
+        const int last = max(P - 1, 0);
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const int p = 2 * ((i >> 1) * THREADS + tid) + (i & 1);
+            raw[i] = __ldg(reinterpret_cast<const float2*>(tp) + min(p, last));
+        }
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            const int p = 2 * ((i >> 1) * THREADS + tid) + (i & 1);
+            const uint32_t a = pv_lin(raw[i].x, raw[i].y, W, H);
+            lin[i] = (p < n) ? a : PV_INVALID;
+        }
     }
+    uint32_t labr[PPT];
+    uint32_t lmin = PV_INVALID, lmax1 = 0;       // min of lin, max of lin+1 (invalid -> 0)
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
-        if (key[k] != PV_INVALID) {
-            const int ix = key[k] & 0xFFFF, iy = key[k] >> 16;
-            const uint32_t lab = __ldg(lbl + (int64_t)iy * d.W + ix);
-            lab4[k >> 2] |= lab << (8 * (k & 3));
-            xmin = min(xmin, ix); xmax = max(xmax, ix);
-            ymin = min(ymin, iy); ymax = max(ymax, iy);
-        }
+        const uint32_t l = lin[k];
+        labr[k] = 0;
+        if (l != PV_INVALID) labr[k] = __ldg(lbl + l);
+        lmin = min(lmin, l);
+        lmax1 = max(lmax1, l + 1u);
     }
-    xmin = __reduce_min_sync(0xffffffffu, xmin);
-    ymin = __reduce_min_sync(0xffffffffu, ymin);
-    xmax = __reduce_max_sync(0xffffffffu, xmax);
-    ymax = __reduce_max_sync(0xffffffffu, ymax);
-    __syncthreads();                      // smem init visible
-    if (lane == 0 && xmax >= 0) {
-        atomicMin(&sbox[0], xmin); atomicMin(&sbox[1], ymin);
-        atomicMax(&sbox[2], xmax); atomicMax(&sbox[3], ymax);
-    }
-    __syncthreads();
-    const int x0 = sbox[0], y0 = sbox[1], x1 = sbox[2], y1 = sbox[3];
-
-    // ---- pass 2: de-duplicate in the bitmap band by band, vote ---------------------------
-    if (x1 >= 0) {
-        const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
-        const int rpb = PV_BM_BITS / bw;                  // rows per band (bw <= 65535 -> >= 2)
-        int cur = -1, cnt = 0;
-        for (int ylo = y0; ylo <= y1; ylo += rpb) {
-            const int yhi = min(y1, ylo + rpb - 1);
 #pragma unroll
-            for (int k = 0; k < PPT; ++k) {
-                if (key[k] == PV_INVALID) continue;
-                const int ix = key[k] & 0xFFFF, iy = key[k] >> 16;
-                if (iy < ylo || iy > yhi) continue;
-                const uint32_t kk = (uint32_t)(iy - ylo) * (uint32_t)bw + (uint32_t)(ix - x0);
-                uint32_t w = kk & (PV_BM_WORDS - 1);
-                w ^= (w >> 5) & 31u;                       // bank swizzle
-                const uint32_t bit = 1u << (kk >> 12);
-                const uint32_t old = atomicOr(&bm[w], bit);
-                if (!(old & bit)) {                        // first point on this pixel
-                    const int lab = (lab4[k >> 2] >> (8 * (k & 3))) & 255;
-                    if (lab != cur) {
-                        if (cnt) atomicAdd(&hist[cur], cnt);
-                        cur = lab; cnt = 0;
-                    }
-                    ++cnt;
-                }
-            }
-            if (yhi < y1) {                                // more bands: recycle the bitmap
-                __syncthreads();
-                for (int i = tid; i < PV_BM_WORDS / 4; i += THREADS)
-                    reinterpret_cast<uint4*>(bm)[i] = make_uint4(0, 0, 0, 0);
-                __syncthreads();
-            }
+    for (int i = 0; i < PV_BM_WORDS / 4 / THREADS; ++i)
+        reinterpret_cast<uint4*>(bm)[i * THREADS + tid] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < S2D_MAX_LABELS + 1; i += THREADS) hist[i] = 0;
+    if (tid == 0) { sbox[0] = PV_INVALID; sbox[1] = 0; }
+    lmin = __reduce_min_sync(0xffffffffu, lmin);
+    lmax1 = __reduce_max_sync(0xffffffffu, lmax1);
+    __syncthreads();                      // smem init visible
+    if (lane == 0 && lmax1 != 0) { atomicMin(&sbox[0], lmin); atomicMax(&sbox[1], lmax1); }
+    __syncthreads();
+    lmin = sbox[0];
+    lmax1 = sbox[1];
+    uint32_t lab4[PPT / 4];
+#pragma unroll
+    for (int k4 = 0; k4 < PPT / 4; ++k4) lab4[k4] = pack4(labr[4 * k4], labr[4 * k4 + 1], labr[4 * k4 + 2], labr[4 * k4 + 3]);
+
+    // ---- pass 2: de-duplicate in the bitmap band by band, vote -----------------------------
+    if (lmax1 != 0) {
+        int cur = -1, cnt = 0, nfirst = 0;
+        for (uint32_t base = lmin;;) {
+            uint32_t first = 0;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) first |= pv_claim(bm, lin[k], base) ? (1u << k) : 0u;
+            nfirst += __popc(first);
+            pv_vote<PPT>(first, lab4, cur, cnt, hist);
+            if (lmax1 - base <= (uint32_t)PV_BM_BITS) break;       // uniform: extent is CTA-wide
+            base += PV_BM_BITS;
+            __syncthreads();                                       // recycle the bitmap for the next band
+#pragma unroll
+            for (int i = 0; i < PV_BM_WORDS / 4 / THREADS; ++i)
+                reinterpret_cast<uint4*>(bm)[i * THREADS + tid] = make_uint4(0, 0, 0, 0);
+            __syncthreads();
         }
-        // warp-aggregated flush of the per-thread runs (usually one label per warp)
-        uint32_t remaining = __ballot_sync(0xffffffffu, cnt > 0);
-        while (remaining) {
-            const int leader = __ffs(remaining) - 1;
-            const int l0 = __shfl_sync(0xffffffffu, cur, leader);
-            const bool mine = (cnt > 0) && (cur == l0);
-            const int s = __reduce_add_sync(0xffffffffu, mine ? cnt : 0);
-            if (lane == leader) atomicAdd(&hist[l0], s);
-            remaining &= ~__ballot_sync(0xffffffffu, mine);
-        }
-        (void)bh;
+        pv_flush(cur, cnt, lane, hist);
+        nfirst = __reduce_add_sync(0xffffffffu, nfirst);
+        if (lane == 0 && nfirst) atomicAdd(&hist[S2D_MAX_LABELS], nfirst);
     }
     __syncthreads();
 
     // ---- write out ------------------------------------------------------------------------
-    int32_t* hout = hits + d.hits_off + rt * d.L;
-    int part = 0;
-    for (int l = tid; l < S2D_MAX_LABELS; l += THREADS) {
+    const int L = dp->L;
+    int32_t* hout = hits + dp->hits_off + rt * L;
+    for (int l = tid; l < S2D_MAX_LABELS + 1; l += THREADS) {
         const int h = hist[l];
-        part += h;
-        if (l < d.L) hout[l] = h;
+        if (l < L) hout[l] = h;
+        if (l == S2D_MAX_LABELS) uniq[dp->vt_off + rt] = h;
     }
-    part = warp_sum(part);
-    __shared__ int s_tot;
-    if (tid == 0) s_tot = 0;
+}
+
+// ==========================================================================================
+// Persistent, TMA-fed variant (the production path for even P and 16-byte aligned tracks).
+//
+// A small plan pass turns (candidate rows x window frames) into a flat list of tiles; 2 CTAs per
+// SM pull chunks of consecutive tiles from an atomic counter. Each CTA has one producer warp that
+// keeps a two-stage ring of 8P-byte track tiles in shared memory filled by cp.async.bulk (one
+// instruction per tile, completion on an mbarrier) and THREADS consumer threads that software-
+// pipeline over tiles: while tile i is de-duplicated and voted, tile i+1 has already been pulled
+// out of its stage into registers and its label gathers are in flight.
+// ==========================================================================================
+struct PvTile {             // written by the producer thread, read by everybody after the mbarrier wait
+    const uint8_t* lbl;     // label map of the target frame
+    int32_t* hout;          // hits[q,t,:]
+    int32_t* uout;          // &uniq[q,t]
+    uint32_t W, H;
+    int32_t n, L;
+    int32_t valid, pad;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(smem_u32(bar)));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// plan: per batch row (tile0 filled by the scan, ntiles, first frame, video)
+__global__ void pv_plan_rows_kernel(const s2d_video_desc* __restrict__ descs, int nvideos, int64_t total_rows,
+                                    const int32_t* __restrict__ rowinfo, const int32_t* __restrict__ vidinfo,
+                                    int4* __restrict__ rowplan) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= total_rows) return;
+    int lo = 0, hi = nvideos;                       // last video with row0 <= r
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (descs[mid].row0 <= r) lo = mid; else hi = mid;
+    }
+    const int T = descs[lo].T;
+    int nt = T, t0 = 0;
+    if (vidinfo && vidinfo[(int64_t)lo * S2D_VIDINFO_WORDS + 1] < 0) nt = 0;
+    if (rowinfo) {
+        const int4 ri = reinterpret_cast<const int4*>(rowinfo)[r];
+        if (ri.y < 0) nt = 0;
+        else { t0 = max(ri.z, 0); nt = nt ? max(min(ri.w, T - 1) - t0 + 1, 0) : 0; }
+    }
+    rowplan[r] = make_int4(0, nt, t0, lo);
+}
+
+// exclusive scan of ntiles over all batch rows (one CTA), total -> ctrl[1], work counter ctrl[0] = 0
+__global__ void __launch_bounds__(1024) pv_scan_kernel(int4* __restrict__ rowplan, int64_t total_rows, int32_t* __restrict__ ctrl) {
+    __shared__ int wsum[32];
+    __shared__ int running;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) running = 0;
     __syncthreads();
-    if (lane == 0 && part) atomicAdd(&s_tot, part);
+    for (int64_t base = 0; base < total_rows; base += 1024) {
+        const int64_t r = base + tid;
+        const int v = r < total_rows ? rowplan[r].y : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 32; ++w) { const int s = wsum[w]; if (w < warp) before += s; total += s; }
+        if (r < total_rows) rowplan[r].x = running + before + x - v;
+        __syncthreads();
+        if (tid == 0) running += total;
+        __syncthreads();
+    }
+    if (tid == 0) { ctrl[0] = 0; ctrl[1] = running; }
+}
+
+constexpr int PV_CHUNK = 64;       // consecutive tiles claimed per atomic
+
+__device__ __forceinline__ void consumer_sync(int nthreads) {   // named barrier 1: consumer warps only
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+// THREADS consumer threads + one producer warp (the last warp of the CTA)
+template <int THREADS, int PPT>
+__global__ void __launch_bounds__(THREADS + 32, (THREADS * PPT <= 4096) ? 2 : 1)
+point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __restrict__ rowplan,
+                       int total_rows, int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
+                       int32_t* __restrict__ uniq) {
+    constexpr int STAGE_BYTES = THREADS * PPT * 8;
+    extern __shared__ __align__(128) uint8_t dsm[];
+    uint8_t* stage[2] = {dsm, dsm + STAGE_BYTES};
+    uint32_t* bm = reinterpret_cast<uint32_t*>(dsm + 2 * STAGE_BYTES);
+    __shared__ int hist[S2D_MAX_LABELS + 1];          // [256] = number of unique pixels
+    __shared__ uint32_t sbox[3][2];
+    __shared__ __align__(8) uint64_t full[2];
+    __shared__ __align__(8) uint64_t empty[2];
+    __shared__ PvTile tinfo[2];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int total = ctrl[1];
+
+    if (tid < THREADS) {
+        for (int i = tid; i < PV_BM_WORDS / 4; i += THREADS)
+            reinterpret_cast<uint4*>(bm)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < S2D_MAX_LABELS + 1; i += THREADS) hist[i] = 0;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) { sbox[i][0] = PV_INVALID; sbox[i][1] = 0; }
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_init(&empty[0], THREADS / 32);
+        mbar_init(&empty[1], THREADS / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    if (tid == 0) uniq[d.vt_off + rt] = s_tot;
+
+    if (tid >= THREADS) {
+        // =========================== producer warp ===========================================
+        int pi = 0, pi_end = 0, prow = 0;          // next tile index, end of claimed chunk, its row
+        int4 prp = make_int4(0, 0, 0, 0);          // rowplan[prow]
+        for (int j = 0;; ++j) {
+            const int s = j & 1;
+            if (j >= 2) mbar_wait(&empty[s], ((j >> 1) - 1) & 1);    // stage s drained by the consumers
+            bool done = false;
+            if (pi == pi_end) {
+                int c = 0;
+                if (lane == 0) c = atomicAdd(&ctrl[0], PV_CHUNK);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= total) {
+                    done = true;
+                } else {
+                    pi = c;
+                    pi_end = min(c + PV_CHUNK, total);
+                    int lo = 0, hi = total_rows;     // 32-ary search: last row with tile0 <= pi
+                    while (hi - lo > 32) {
+                        const int step = (hi - lo + 31) >> 5;
+                        const int probe = lo + lane * step;
+                        const bool ok = probe < hi && rowplan[probe].x <= pi;
+                        const uint32_t b = __ballot_sync(0xffffffffu, ok);
+                        const int k = 31 - __clz(b);
+                        lo += k * step;
+                        hi = min(hi, lo + step);
+                    }
+                    const int probe = lo + lane;
+                    const bool ok = probe < hi && rowplan[probe].x <= pi;
+                    const uint32_t b = __ballot_sync(0xffffffffu, ok);
+                    prow = lo + 31 - __clz(b);
+                    prp = rowplan[prow];
+                }
+            }
+            if (done) {
+                if (lane == 0) { tinfo[s].valid = 0; mbar_arrive(&full[s]); }
+                break;
+            }
+            while (pi >= prp.x + prp.y) { ++prow; prp = rowplan[prow]; }   // rows without tiles are skipped
+            if (lane == 0) {
+                const s2d_video_desc* dp = descs + prp.w;
+                const int q = prow - (int)dp->row0;
+                const int t = prp.z + (pi - prp.x);
+                const int P = dp->P, T = dp->T, L = dp->L;
+                const int64_t rt = (int64_t)q * T + t;
+                PvTile ti;
+                ti.lbl = dp->labels + (int64_t)t * dp->H * dp->W;
+                ti.hout = hits + dp->hits_off + rt * L;
+                ti.uout = uniq + dp->vt_off + rt;
+                ti.W = dp->W; ti.H = dp->H; ti.L = L;
+                const int32_t* np = dp->npts;
+                ti.n = np ? min(max(np[q], 0), P) : P;
+                ti.valid = 1; ti.pad = 0;
+                tinfo[s] = ti;
+                const uint32_t bytes = (uint32_t)P * 8u;
+                mbar_expect_tx(&full[s], bytes);
+                bulk_g2s(stage[s], dp->tracks + rt * P * 2, bytes, &full[s]);
+            }
+            ++pi;
+        }
+        return;
+    }
+
+    // =============================== consumer warps ==========================================
+    uint32_t lin_n[PPT], lab_n[PPT];          // next tile: pixel indices and raw gathered labels
+    PvTile ti_n;
+    auto stage_a = [&](int j) {               // j = tile sequence number of this CTA
+        const int s = j & 1;
+        mbar_wait(&full[s], (j >> 1) & 1);
+        ti_n = tinfo[s];
+        if (!ti_n.valid) return;
+        const uint32_t W = ti_n.W, H = ti_n.H;
+        const int n = ti_n.n;
+        const float4* sp = reinterpret_cast<const float4*>(stage[s]);
+        if (n >= THREADS * PPT) {             // full tile: no per-point tail checks
+#pragma unroll
+            for (int i = 0; i < PPT / 2; ++i) {
+                const float4 v = sp[i * THREADS + tid];
+                lin_n[2 * i] = pv_lin(v.x, v.y, W, H);
+                lin_n[2 * i + 1] = pv_lin(v.z, v.w, W, H);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PPT / 2; ++i) {
+                const int p0 = 2 * (i * THREADS + tid);
+                const float4 v = sp[i * THREADS + tid];
+                const uint32_t a = pv_lin(v.x, v.y, W, H), b = pv_lin(v.z, v.w, W, H);
+                lin_n[2 * i] = (p0 < n) ? a : PV_INVALID;
+                lin_n[2 * i + 1] = (p0 + 1 < n) ? b : PV_INVALID;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);     // this warp no longer reads stage s / tinfo[s]
+        uint32_t lmin = PV_INVALID, lmax1 = 0;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const uint32_t l = lin_n[k];
+            lab_n[k] = 0;
+            if (l != PV_INVALID) lab_n[k] = __ldg(ti_n.lbl + l);   // consumed one iteration later
+            lmin = min(lmin, l);
+            lmax1 = max(lmax1, l + 1u);
+        }
+        lmin = __reduce_min_sync(0xffffffffu, lmin);
+        lmax1 = __reduce_max_sync(0xffffffffu, lmax1);
+        uint32_t* sb = sbox[j % 3];
+        if (lane == 0 && lmax1 != 0) { atomicMin(&sb[0], lmin); atomicMax(&sb[1], lmax1); }
+    };
+
+    stage_a(0);
+    for (int it = 0;; ++it) {
+        const PvTile ti = ti_n;
+        if (!ti.valid) break;
+        uint32_t lin[PPT], lab4[PPT / 4];
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) lin[k] = lin_n[k];
+#pragma unroll
+        for (int k4 = 0; k4 < PPT / 4; ++k4)
+            lab4[k4] = pack4(lab_n[4 * k4], lab_n[4 * k4 + 1], lab_n[4 * k4 + 2], lab_n[4 * k4 + 3]);
+        stage_a(it + 1);
+        consumer_sync(THREADS);                // S1: extents complete; previous tile's resets visible
+        const uint32_t lmin = sbox[it % 3][0];
+        const uint32_t lmax1 = sbox[it % 3][1];
+        if (tid == 0) { sbox[(it + 2) % 3][0] = PV_INVALID; sbox[(it + 2) % 3][1] = 0; }
+
+        // ---- pass 2: de-duplicate in the bitmap band by band, vote -------------------------
+        if (lmax1 != 0) {
+            int cur = -1, cnt = 0, nfirst = 0;
+            for (uint32_t base = lmin;;) {
+                uint32_t first = 0;
+#pragma unroll
+                for (int k = 0; k < PPT; ++k) first |= pv_claim(bm, lin[k], base) ? (1u << k) : 0u;
+                nfirst += __popc(first);
+                pv_vote<PPT>(first, lab4, cur, cnt, hist);
+                if (lmax1 - base <= (uint32_t)PV_BM_BITS) break;
+                base += PV_BM_BITS;
+                consumer_sync(THREADS);
+                for (int i = tid; i < PV_BM_WORDS / 4; i += THREADS)
+                    reinterpret_cast<uint4*>(bm)[i] = make_uint4(0, 0, 0, 0);
+                consumer_sync(THREADS);
+            }
+            pv_flush(cur, cnt, lane, hist);
+            nfirst = __reduce_add_sync(0xffffffffu, nfirst);
+            if (lane == 0 && nfirst) atomicAdd(&hist[S2D_MAX_LABELS], nfirst);
+        }
+        consumer_sync(THREADS);                // S2: histogram complete
+
+        // ---- write out, then reset histogram and bitmap for the next tile --------------------
+        for (int l = tid; l < S2D_MAX_LABELS + 1; l += THREADS) {
+            const int h = hist[l];
+            if (l < ti.L) ti.hout[l] = h;
+            if (l == S2D_MAX_LABELS) *ti.uout = h;
+            hist[l] = 0;
+        }
+        if (lmax1 != 0) {
+            for (int i = tid; i < PV_BM_WORDS / 4; i += THREADS)
+                reinterpret_cast<uint4*>(bm)[i] = make_uint4(0, 0, 0, 0);
+        }
+        // the next tile's S1 orders these resets before its bitmap / histogram atomics
+    }
+}
+
+template <int THREADS, int PPT>
+static int launch_pv_tma(cudaStream_t st, int nsm, const s2d_video_desc* descs, const int4* rowplan,
+                         int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq) {
+    const int smem = 2 * THREADS * PPT * 8 + PV_BM_WORDS * 4;
+    auto kfn = point_votes_tma_kernel<THREADS, PPT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { set_error("point_votes_tma_kernel: cannot opt in to %d B of shared memory: %s", smem, cudaGetErrorString(e)); return -2; }
+        configured = true;
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, THREADS + 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    kfn<<<nsm * per_sm, THREADS + 32, smem, st>>>(descs, rowplan, total_rows, ctrl, hits, uniq);
+    S2D_CHECK_LAUNCH("point_votes_tma_kernel");
+    return 0;
 }
 
 template <int THREADS, int PPT>
@@ -182,16 +551,45 @@ static int launch_pv(bool vec4, dim3 grid, cudaStream_t st, const s2d_video_desc
 
 using namespace s2d;
 
-extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_T, int max_P,
-                               int vec4_ok, const int32_t* rowinfo, const int32_t* vidinfo,
-                               int32_t* hits, int32_t* uniq, void* stream) {
+extern "C" int s2d_point_votes_work_ints(int64_t total_rows, int64_t* out) {
+    if (!out) return -1;
+    *out = 4 * total_rows + 8;
+    return 0;
+}
+
+extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max_T, int max_Nm, int max_P,
+                               int vec4_ok, int64_t total_rows, const int32_t* rowinfo,
+                               const int32_t* vidinfo, int32_t* work, int32_t* hits, int32_t* uniq,
+                               void* stream) {
     S2D_CHECK_ARG(descs && hits && uniq, "s2d_point_votes: null pointer");
-    S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_rows_x_T > 0 && max_rows_x_T <= 2147483647LL,
+    S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_T > 0 && max_Nm > 0 && max_Nm <= 65535,
                   "s2d_point_votes: bad sizes");
     S2D_CHECK_ARG(max_P >= 1 && max_P <= 32768, "s2d_point_votes: P=%d not in [1, 32768]", max_P);
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)max_rows_x_T, nvideos);
     const bool v4 = vec4_ok != 0;
+    if (v4 && work && max_P <= 8192 && total_rows > 0 && total_rows <= 2147483647LL) {
+        // persistent TMA path
+        S2D_CHECK_ARG((((uintptr_t)work) & 15) == 0, "s2d_point_votes: work must be 16-byte aligned");
+        int dev = 0, nsm = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+        int32_t* ctrl = work;
+        int4* rowplan = reinterpret_cast<int4*>(work + 8);
+        pv_plan_rows_kernel<<<(unsigned)((total_rows + 255) / 256), 256, 0, st>>>(descs, nvideos, total_rows, rowinfo, vidinfo, rowplan);
+        S2D_CHECK_LAUNCH("pv_plan_rows_kernel");
+        pv_scan_kernel<<<1, 1024, 0, st>>>(rowplan, total_rows, ctrl);
+        S2D_CHECK_LAUNCH("pv_scan_kernel");
+        const int tr = (int)total_rows;
+        const char* cfg = getenv("S2D_PV_CFG");      // profiling knob: "256x16" selects the wide-thread variant
+        if (max_P <= 256 * 4) return launch_pv_tma<256, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+        if (max_P <= 256 * 8) return launch_pv_tma<256, 8>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+        if (max_P <= 4096) {
+            if (cfg && cfg[0] == '2') return launch_pv_tma<256, 16>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+            return launch_pv_tma<512, 8>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+        }
+        return launch_pv_tma<512, 16>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+    }
+    dim3 grid((unsigned)max_T, (unsigned)max_Nm, nvideos);
 #define PV_ARGS v4, grid, st, descs, rowinfo, vidinfo, hits, uniq
     if (max_P <= 256 * 4) return launch_pv<256, 4>(PV_ARGS);
     if (max_P <= 256 * 8) return launch_pv<256, 8>(PV_ARGS);

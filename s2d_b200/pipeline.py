@@ -10,6 +10,7 @@ groupings, one2x, coverage) - it only unpacks bit masks and index tables.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -139,6 +140,8 @@ class Batch:
         self.winbits = _i32(xw, dev)
         self.rowinfo = _i32(row0 * 4, dev)
         self.clusterinfo = _i32(nv * S2D_MAX_CLUSTERS * S2D_CLINFO_WORDS, dev, 0)
+        _lib.call("s2d_point_votes_work_ints", row0, C.byref(n))
+        self.pvwork = _i32(n.value + 4, dev)
         self.hits = _i32(hits, dev)
         self.uniq = _i32(vt, dev)
         self.mbits = _i32(mw, dev)
@@ -150,6 +153,9 @@ class Batch:
         self.grp_n = _i32(16 * row0, dev)
         self.grp_one2x = _i32(16 * row0, dev)
         self.kernel_launches_per_run = 0
+        # persistent TMA-fed votes kernel (the library falls back by itself when P is odd);
+        # S2D_PV_TMA=0 selects the one-CTA-per-tile kernel (profiling comparisons)
+        self.use_tma = os.environ.get("S2D_PV_TMA", "1") != "0"
 
     # ------------------------------------------------------------------ enqueue
     def run(self, params: Params = Params(), stream=None, stages: str = "LVBD", timers=None):
@@ -190,8 +196,9 @@ class Batch:
                  p(self.rsbits), p(self.rebits), p(self.winbits), p(self.rowinfo), p(self.vidinfo),
                  p(self.clusterinfo), st)
         if "D" in stages:
-            call("point_votes", 1, "s2d_point_votes", d, nv, self.max_rows_x_T, self.max_P, self.vec4,
-                 p(self.rowinfo), p(self.vidinfo), p(self.hits), p(self.uniq), st)
+            call("point_votes", 3 if self.use_tma else 1, "s2d_point_votes", d, nv, self.max_T, self.max_Nm, self.max_P,
+                 self.vec4, self.total_rows, p(self.rowinfo), p(self.vidinfo),
+                 p(self.pvwork) if self.use_tma else None, p(self.hits), p(self.uniq), st)
             call("select", 1, "s2d_select", d, nv, self.max_Nm, self.total_mw, p(self.hits), p(self.uniq),
                  p(self.gid_of), p(self.rowinfo), params.matching_threshold, params.one2x_iou,
                  params.one2x_frames, p(self.mbits), p(self.one2x), p(self.nmatch), p(self.vidinfo), st)
@@ -204,8 +211,9 @@ class Batch:
     def votes_all(self, stream=None):
         """K2 over every (query, frame) of every video, ignoring candidates/status (tests, bench)."""
         st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
-        _lib.call("s2d_point_votes", self.descs.data_ptr(), self.nv, self.max_rows_x_T, self.max_P, self.vec4,
-                  None, None, self.hits.data_ptr(), self.uniq.data_ptr(), st)
+        _lib.call("s2d_point_votes", self.descs.data_ptr(), self.nv, self.max_T, self.max_Nm, self.max_P, self.vec4,
+                  self.total_rows, None, None, self.pvwork.data_ptr() if self.use_tma else None,
+                  self.hits.data_ptr(), self.uniq.data_ptr(), st)
 
     # ------------------------------------------------------------------ results
     def fetch_summary(self):

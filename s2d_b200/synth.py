@@ -172,7 +172,7 @@ def scene_object_map(scene: Scene) -> np.ndarray:
 # --------------------------------------------------------------------------------------
 
 def make_scene_device(seed: int, T: int, H: int, W: int, M: int, P: int, device, *,
-                      noise: float = 0.7, occlude: bool = True):
+                      noise: float = 0.7, occlude: bool = True, point_order: str = "raster"):
     """Same scene family as make_scene, built directly in HBM with torch ops (vectorised per
     frame). Returns dict(labels u8 [T,H,W], tracks f32 [Nm,T,P,2], vis u8 [Nm,T,P],
     query_frame i32 [Nm], query_label i32 [Nm]). Background is always present."""
@@ -239,6 +239,8 @@ def make_scene_device(seed: int, T: int, H: int, W: int, M: int, P: int, device,
         counts = torch.bincount(lab_flat.long(), minlength=n + 1)
         starts = torch.cumsum(counts, 0) - counts
         r = torch.rand((n, P), generator=dg, device=device)
+        if point_order == "raster":
+            r = (torch.arange(P, device=device, dtype=f32)[None, :] + r) / P
         idx = starts[1:n + 1, None] + (r * counts[1:n + 1, None]).long().clamp_(max=int(counts.max()) - 1)
         idx = torch.minimum(idx, (starts[1:n + 1] + counts[1:n + 1] - 1)[:, None])
         pix = order[idx]                                        # [n,P]
