@@ -245,6 +245,8 @@ struct PvTile {             // written by the producer thread, read by everybody
     int32_t valid, pad;
 };
 
+struct PvOut { int32_t* hout; int32_t* uout; int32_t L, pad; };
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(smem_u32(bar)));
@@ -330,13 +332,14 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                        int32_t* __restrict__ uniq) {
     constexpr int STAGE_BYTES = THREADS * PPT * 8;
     extern __shared__ __align__(128) uint8_t dsm[];
-    uint8_t* stage[2] = {dsm, dsm + STAGE_BYTES};
     uint32_t* bm = reinterpret_cast<uint32_t*>(dsm + 2 * STAGE_BYTES);
     __shared__ int hist[S2D_MAX_LABELS + 1];          // [256] = number of unique pixels
     __shared__ uint32_t sbox[3][2];
     __shared__ __align__(8) uint64_t full[2];
     __shared__ __align__(8) uint64_t empty[2];
     __shared__ PvTile tinfo[2];
+    __shared__ PvOut tout[3];
+    static_assert(THREADS >= S2D_MAX_LABELS + 1, "output phase uses one thread per histogram bin");
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int total = ctrl[1];
@@ -412,7 +415,7 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                 tinfo[s] = ti;
                 const uint32_t bytes = (uint32_t)P * 8u;
                 mbar_expect_tx(&full[s], bytes);
-                bulk_g2s(stage[s], dp->tracks + rt * P * 2, bytes, &full[s]);
+                bulk_g2s(dsm + s * STAGE_BYTES, dp->tracks + rt * P * 2, bytes, &full[s]);
             }
             ++pi;
         }
@@ -420,16 +423,20 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     }
 
     // =============================== consumer warps ==========================================
-    uint32_t lin_n[PPT], lab_n[PPT];          // next tile: pixel indices and raw gathered labels
-    PvTile ti_n;
-    auto stage_a = [&](int j) {               // j = tile sequence number of this CTA
+    // Two register sets (A/B) ping-pong between "being gathered" and "being voted".
+    uint32_t linA[PPT], labA[PPT], linB[PPT], labB[PPT];
+    bool okA, okB;
+
+    // stage A of tile j: stage -> registers, round/bounds, issue label gathers, extent
+    auto stage_a = [&](int j, uint32_t (&lin_n)[PPT], uint32_t (&lab_n)[PPT]) -> bool {
         const int s = j & 1;
         mbar_wait(&full[s], (j >> 1) & 1);
-        ti_n = tinfo[s];
-        if (!ti_n.valid) return;
-        const uint32_t W = ti_n.W, H = ti_n.H;
-        const int n = ti_n.n;
-        const float4* sp = reinterpret_cast<const float4*>(stage[s]);
+        if (!tinfo[s].valid) return false;
+        const uint32_t W = tinfo[s].W, H = tinfo[s].H;
+        const int n = tinfo[s].n;
+        const uint8_t* lbl = tinfo[s].lbl;
+        if (tid == 0) { tout[j % 3].hout = tinfo[s].hout; tout[j % 3].uout = tinfo[s].uout; tout[j % 3].L = tinfo[s].L; }
+        const float4* sp = reinterpret_cast<const float4*>(dsm + s * STAGE_BYTES);
         if (n >= THREADS * PPT) {             // full tile: no per-point tail checks
 #pragma unroll
             for (int i = 0; i < PPT / 2; ++i) {
@@ -450,11 +457,12 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);     // this warp no longer reads stage s / tinfo[s]
         uint32_t lmin = PV_INVALID, lmax1 = 0;
+        const uint32_t lastpx = W * H - 1u;
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             const uint32_t l = lin_n[k];
-            lab_n[k] = 0;
-            if (l != PV_INVALID) lab_n[k] = __ldg(ti_n.lbl + l);   // consumed one iteration later
+            // unconditional gather (invalid points read the last pixel; they never claim a bit)
+            lab_n[k] = __ldg(lbl + min(l, lastpx));                // consumed one iteration later
             lmin = min(lmin, l);
             lmax1 = max(lmax1, l + 1u);
         }
@@ -462,58 +470,70 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         lmax1 = __reduce_max_sync(0xffffffffu, lmax1);
         uint32_t* sb = sbox[j % 3];
         if (lane == 0 && lmax1 != 0) { atomicMin(&sb[0], lmin); atomicMax(&sb[1], lmax1); }
+        return true;
     };
 
-    stage_a(0);
-    for (int it = 0;; ++it) {
-        const PvTile ti = ti_n;
-        if (!ti.valid) break;
-        uint32_t lin[PPT], lab4[PPT / 4];
-#pragma unroll
-        for (int k = 0; k < PPT; ++k) lin[k] = lin_n[k];
-#pragma unroll
-        for (int k4 = 0; k4 < PPT / 4; ++k4)
-            lab4[k4] = pack4(lab_n[4 * k4], lab_n[4 * k4 + 1], lab_n[4 * k4 + 2], lab_n[4 * k4 + 3]);
-        stage_a(it + 1);
+    // stage B of tile `it`: de-duplicate, vote, write out, reset
+    auto stage_b = [&](int it, const uint32_t (&lin)[PPT], const uint32_t (&lab)[PPT]) {
         consumer_sync(THREADS);                // S1: extents complete; previous tile's resets visible
         const uint32_t lmin = sbox[it % 3][0];
         const uint32_t lmax1 = sbox[it % 3][1];
         if (tid == 0) { sbox[(it + 2) % 3][0] = PV_INVALID; sbox[(it + 2) % 3][1] = 0; }
-
-        // ---- pass 2: de-duplicate in the bitmap band by band, vote -------------------------
         if (lmax1 != 0) {
-            int cur = -1, cnt = 0, nfirst = 0;
+            // common case: every first point of the thread carries the label of its point 0; those
+            // are counted in a register, the rest (object borders, other masks) vote one by one
+            const uint32_t cur = lab[0];
+            int cnt = 0;
             for (uint32_t base = lmin;;) {
-                uint32_t first = 0;
+                uint32_t odd = 0;
 #pragma unroll
-                for (int k = 0; k < PPT; ++k) first |= pv_claim(bm, lin[k], base) ? (1u << k) : 0u;
-                nfirst += __popc(first);
-                pv_vote<PPT>(first, lab4, cur, cnt, hist);
+                for (int k = 0; k < PPT; ++k) {
+                    const bool fst = pv_claim(bm, lin[k], base) != 0;
+                    const bool same = lab[k] == cur;
+                    cnt += (fst && same) ? 1 : 0;
+                    odd |= (fst && !same) ? (1u << k) : 0u;
+                }
+                if (odd) {
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k)
+                        if ((odd >> k) & 1u) { atomicAdd(&hist[lab[k]], 1); atomicAdd(&hist[S2D_MAX_LABELS], 1); }
+                }
                 if (lmax1 - base <= (uint32_t)PV_BM_BITS) break;
                 base += PV_BM_BITS;
                 consumer_sync(THREADS);
-                for (int i = tid; i < PV_BM_WORDS / 4; i += THREADS)
-                    reinterpret_cast<uint4*>(bm)[i] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int i = 0; i < PV_BM_WORDS / 4 / THREADS; ++i)
+                    reinterpret_cast<uint4*>(bm)[i * THREADS + tid] = make_uint4(0, 0, 0, 0);
                 consumer_sync(THREADS);
             }
-            pv_flush(cur, cnt, lane, hist);
-            nfirst = __reduce_add_sync(0xffffffffu, nfirst);
-            if (lane == 0 && nfirst) atomicAdd(&hist[S2D_MAX_LABELS], nfirst);
+            pv_flush((int)cur, cnt, lane, hist);
+            const int tot = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0 && tot) atomicAdd(&hist[S2D_MAX_LABELS], tot);
         }
         consumer_sync(THREADS);                // S2: histogram complete
-
-        // ---- write out, then reset histogram and bitmap for the next tile --------------------
-        for (int l = tid; l < S2D_MAX_LABELS + 1; l += THREADS) {
-            const int h = hist[l];
-            if (l < ti.L) ti.hout[l] = h;
-            if (l == S2D_MAX_LABELS) *ti.uout = h;
-            hist[l] = 0;
+        if (tid < S2D_MAX_LABELS + 1) {
+            const int h = hist[tid];
+            const PvOut o = tout[it % 3];
+            if (tid < o.L) o.hout[tid] = h;
+            if (tid == S2D_MAX_LABELS) *o.uout = h;
+            hist[tid] = 0;
         }
         if (lmax1 != 0) {
-            for (int i = tid; i < PV_BM_WORDS / 4; i += THREADS)
-                reinterpret_cast<uint4*>(bm)[i] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int i = 0; i < PV_BM_WORDS / 4 / THREADS; ++i)
+                reinterpret_cast<uint4*>(bm)[i * THREADS + tid] = make_uint4(0, 0, 0, 0);
         }
         // the next tile's S1 orders these resets before its bitmap / histogram atomics
+    };
+
+    okA = stage_a(0, linA, labA);
+    for (int it = 0;; it += 2) {
+        if (!okA) break;
+        okB = stage_a(it + 1, linB, labB);
+        stage_b(it, linA, labA);
+        if (!okB) break;
+        okA = stage_a(it + 2, linA, labA);
+        stage_b(it + 1, linB, labB);
     }
 }
 
@@ -580,11 +600,9 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
         pv_scan_kernel<<<1, 1024, 0, st>>>(rowplan, total_rows, ctrl);
         S2D_CHECK_LAUNCH("pv_scan_kernel");
         const int tr = (int)total_rows;
-        const char* cfg = getenv("S2D_PV_CFG");      // profiling knob: "256x16" selects the wide-thread variant
-        if (max_P <= 256 * 4) return launch_pv_tma<256, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
-        if (max_P <= 256 * 8) return launch_pv_tma<256, 8>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+        if (max_P <= 512 * 2) return launch_pv_tma<512, 2>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+        if (max_P <= 512 * 4) return launch_pv_tma<512, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
         if (max_P <= 4096) {
-            if (cfg && cfg[0] == '2') return launch_pv_tma<256, 16>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
             return launch_pv_tma<512, 8>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
         }
         return launch_pv_tma<512, 16>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
