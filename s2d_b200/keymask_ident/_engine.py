@@ -1,0 +1,134 @@
+"""Glue shared by the drop-in modules: device selection, per-process caches, tracker access,
+dataset/split naming, and the stage-wise GPU calls (through s2d_b200.pipeline / the C ABI)."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+from s2d_b200.pipeline import Batch, Params, VideoInput  # noqa: E402
+
+# substrings looked for in the video path, in the reference's order
+# (cotracker_occlusions.py:265-293, cotracker_matching.py:943-971)
+_DATASETS = [("DAVIS", "DAVIS"), ("ytvis2021", "ytvis2021"), ("ytvis2019", "ytvis2019"), ("ovis", "ovis"),
+             ("VIPSeg", "VIPSeg"), ("MOSE", "MOSE"), ("sa-v", "SA-V")]
+_SPLITS = ["train", "valid", "test", "val", "imgs"]
+
+
+def dataset_and_split(video_path: str):
+    for needle, name in _DATASETS:
+        if needle in video_path:
+            break
+    else:
+        raise ValueError("Unknown dataset")
+    for sp in _SPLITS:
+        if sp in video_path:
+            return name, sp
+    return name, "all"
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("s2d_b200 needs a CUDA device: the keymask kernels have no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def checkpoint_dir():
+    """same lookup as the reference (cotracker_occlusions.py:309-315)"""
+    for p in ("/mnt/data/checkpoints", "/mnt/hdd/leon/checkpoints/"):
+        if os.path.exists(p):
+            return p
+    raise FileNotFoundError("Checkpoint directory not found. Please ensure the path is correct. Add it for the new cluster")
+
+
+_tracker_factory = None
+
+
+def set_tracker_factory(factory):
+    """Install a callable `factory(checkpoint=...) -> model` used instead of
+    cotracker.predictor.CoTrackerPredictor (precomputed tracks, tests)."""
+    global _tracker_factory
+    _tracker_factory = factory
+
+
+def make_tracker():
+    """CoTracker is an upstream producer of this path (BASELINE.json north_star): use the real
+    predictor when the `cotracker` package is importable, else an installed factory."""
+    if _tracker_factory is not None:
+        return _tracker_factory(checkpoint=None)
+    from cotracker.predictor import CoTrackerPredictor   # third-party, as in the reference
+    model = CoTrackerPredictor(checkpoint=os.path.join(checkpoint_dir(), "scaled_offline.pth"))
+    if torch.cuda.is_available():
+        model = model.cuda()
+    return model
+
+
+# ---- label maps: loaded once per mask folder (the reference re-reads them three times) -------
+_label_cache = {}
+
+
+def cached_labels(mask_folder, loader):
+    key = os.path.abspath(mask_folder)
+    ent = _label_cache.get(key)
+    if ent is None:
+        masks = loader(mask_folder)
+        if masks is None:
+            return None
+        ent = masks
+        _label_cache.clear()          # one video at a time, like the driver
+        _label_cache[key] = ent
+    return ent
+
+
+def labels_u8_device(masks_thw1: torch.Tensor):
+    lab = masks_thw1[..., 0]
+    if int(lab.max()) > 255:
+        raise ValueError("s2d_b200 supports at most 255 masks per frame")
+    return lab.to(torch.uint8).contiguous().to(device())
+
+
+def enumerate_objects(labels_dev: torch.Tensor):
+    """K0 on the GPU: (qframe, qlabel, area[T,256]) of sort(unique(label[t]))[1:] per frame."""
+    T, H, W = labels_dev.shape
+    # Nm is not known yet: an upper bound of 255 objects per frame sizes the row arrays
+    b = Batch([VideoInput(labels=labels_dev, dims={"Nm": 255 * T, "P": 2})], stages="L")
+    b.run()
+    torch.cuda.synchronize(b.device)
+    nm = int(b.vidinfo[5].item())
+    return (b.qframe[:nm].cpu().numpy().astype(np.int64), b.qlabel[:nm].cpu().numpy().astype(np.int64),
+            b.area.cpu().numpy().reshape(T, 256))
+
+
+def visibility_mean(vis_rows, T: int):
+    """K3a on the GPU. vis_rows: list of [T,P_q] bool arrays/tensors (ragged P)."""
+    nm = len(vis_rows)
+    pmax = max(int(v.shape[1]) for v in vis_rows)
+    pmax += pmax % 2
+    dev = device()
+    vis = torch.zeros((nm, T, pmax), dtype=torch.uint8, device=dev)
+    npts = torch.empty(nm, dtype=torch.int32)
+    for q, v in enumerate(vis_rows):
+        v = torch.as_tensor(v)
+        vis[q, :, : v.shape[1]] = v.to(dev).to(torch.uint8)
+        npts[q] = v.shape[1]
+    b = Batch([VideoInput(vis=vis, npts=npts.to(dev))], stages="V")
+    b.run()
+    torch.cuda.synchronize(dev)
+    return b.V.cpu().numpy().reshape(nm, T)
+
+
+def visibility_windows(V: np.ndarray, qframe, qlabel, visibility_threshold: float):
+    """K3b/c on the GPU: returns the `clusters` list of the stage-B json."""
+    nm, T = V.shape
+    b = Batch([VideoInput(dims={"Nm": nm, "T": T, "P": 2})], device=device(), stages="B")
+    b.upload_visibility(V, np.asarray(qframe))
+    b.qlabel[:nm] = torch.from_numpy(np.asarray(qlabel, np.int32)).to(b.device)
+    b.run(Params(visibility_threshold=visibility_threshold))
+    torch.cuda.synchronize(b.device)
+    return b.decode(want_comps=False, check_rows=False)[0]["clusters"]

@@ -58,7 +58,7 @@ class Batch:
     """Descriptor table + workspace for a list of videos. Allocation happens here, once; `run`
     only enqueues kernels, so a Batch can be re-run (benchmarks) without touching the allocator."""
 
-    def __init__(self, videos: List[VideoInput], device=None, keep_votes: bool = True):
+    def __init__(self, videos: List[VideoInput], device=None, stages: str = "LVBD"):
         assert len(videos) > 0
         self.videos = videos
         first = next(t for t in (videos[0].labels, videos[0].tracks, videos[0].vis) if t is not None) \
@@ -112,53 +112,63 @@ class Batch:
             self.max_rows_x_T = max(self.max_rows_x_T, Nm * T)
             self.max_rows_x_TW = max(self.max_rows_x_TW, Nm * d.TW)
         self.nv = nv
+        self.stages = stages
         self.host_descs = descs
         self.total_rows, self.total_frames, self.total_vt = row0, frame0, vt
         self.total_hits, self.total_xw, self.total_mw = hits, xw, mw
         raw = np.frombuffer(bytes(descs), dtype=np.uint8)
         self.descs = torch.from_numpy(raw.copy()).to(dev)
 
-        # workspace / outputs
-        self.area = _i32(frame0 * S2D_MAX_LABELS, dev)
-        self.gid_of = _i32(frame0 * S2D_MAX_LABELS, dev)
-        self.frameinfo = _i32(frame0 * 4, dev)
-        self.qframe = _i32(row0, dev, 0)
-        self.qlabel = _i32(row0, dev, 0)
-        self.vidinfo = _i32(nv * S2D_VIDINFO_WORDS, dev, 0)
-        self.cnt = _i32(vt, dev)
-        self.V = torch.empty(vt, dtype=torch.float32, device=dev)
-        self.xbits = _i32(xw, dev)
-        self.labels1 = _i32(row0, dev)
+        # workspace / outputs: only what the requested stages touch
+        st = set(stages)
+        z = lambda n, fill=None: _i32(n, dev, fill)
         n = C.c_int64()
-        _lib.call("s2d_dbscan_work_ints", row0, nv, C.byref(n))
-        self.dbwork = _i32(n.value + 2, dev)
-        self.ccount = _i32(vt, dev)
-        self.clrow = _i32(row0 * 4, dev)
-        self.majbits = _i32(xw, dev)
-        self.rsbits = _i32(xw, dev)
-        self.rebits = _i32(xw, dev)
-        self.winbits = _i32(xw, dev)
-        self.rowinfo = _i32(row0 * 4, dev)
-        self.clusterinfo = _i32(nv * S2D_MAX_CLUSTERS * S2D_CLINFO_WORDS, dev, 0)
-        _lib.call("s2d_point_votes_work_ints", row0, C.byref(n))
-        self.pvwork = _i32(n.value + 4, dev)
-        self.hits = _i32(hits, dev)
-        self.uniq = _i32(vt, dev)
-        self.mbits = _i32(mw, dev)
-        self.one2x = _i32(row0, dev)
-        self.nmatch = _i32(row0, dev)
-        _lib.call("s2d_group_work_ints", row0, nv, C.byref(n))
-        self.grpwork = _i32(n.value + 2, dev)
-        self.glabel = _i32(row0, dev)
-        self.grp_n = _i32(16 * row0, dev)
-        self.grp_one2x = _i32(16 * row0, dev)
+        self.vidinfo = z(nv * S2D_VIDINFO_WORDS, 0)
+        self.qframe = z(row0, 0)
+        self.qlabel = z(row0, 0)
+        self.rowinfo = z(row0 * 4, -1)
+        self.clusterinfo = z(nv * S2D_MAX_CLUSTERS * S2D_CLINFO_WORDS, 0)
+        self.labels1 = z(row0, -1)
+        self.area = self.gid_of = self.frameinfo = None
+        if st & set("LD"):
+            self.area = z(frame0 * S2D_MAX_LABELS)
+            self.gid_of = z(frame0 * S2D_MAX_LABELS)
+            self.frameinfo = z(frame0 * 4)
+        self.cnt = self.V = None
+        if st & set("VB"):
+            self.cnt = z(vt)
+            self.V = torch.empty(vt, dtype=torch.float32, device=dev)
+        self.xbits = self.dbwork = self.ccount = self.clrow = None
+        self.majbits = self.rsbits = self.rebits = self.winbits = None
+        if "B" in st:
+            self.xbits = z(xw)
+            _lib.call("s2d_dbscan_work_ints", row0, nv, C.byref(n))
+            self.dbwork = z(n.value + 2)
+            self.ccount = z(vt)
+            self.clrow = z(row0 * 4)
+            self.majbits, self.rsbits, self.rebits, self.winbits = z(xw), z(xw), z(xw), z(xw)
+        self.pvwork = self.hits = self.uniq = self.mbits = self.one2x = self.nmatch = None
+        self.grpwork = self.glabel = self.grp_n = self.grp_one2x = None
+        if "D" in st:
+            _lib.call("s2d_point_votes_work_ints", row0, C.byref(n))
+            self.pvwork = z(n.value + 4)
+            self.hits = z(hits)
+            self.uniq = z(vt)
+            self.mbits = z(mw)
+            self.one2x = z(row0)
+            self.nmatch = z(row0)
+            _lib.call("s2d_group_work_ints", row0, nv, C.byref(n))
+            self.grpwork = z(n.value + 2)
+            self.glabel = z(row0)
+            self.grp_n = z(16 * row0)
+            self.grp_one2x = z(16 * row0)
         self.kernel_launches_per_run = 0
         # persistent TMA-fed votes kernel (the library falls back by itself when P is odd);
         # S2D_PV_TMA=0 selects the one-CTA-per-tile kernel (profiling comparisons)
         self.use_tma = os.environ.get("S2D_PV_TMA", "1") != "0"
 
     # ------------------------------------------------------------------ enqueue
-    def run(self, params: Params = Params(), stream=None, stages: str = "LVBD", timers=None):
+    def run(self, params: Params = Params(), stream=None, stages: Optional[str] = None, timers=None):
         """Enqueue the whole path on `stream` (default: torch's current stream). Returns the
         number of kernel launches enqueued. `timers`: optional dict name -> list; a pair of CUDA
         events is recorded around every C-ABI call on torch's current stream (bench.py)."""
@@ -166,6 +176,8 @@ class Batch:
         p = lambda t: t.data_ptr()
         d, nv = p(self.descs), self.nv
         launches = 0
+        stages = self.stages if stages is None else stages
+        assert set(stages) <= set(self.stages), f"batch was built for stages {self.stages!r}"
 
         def call(tag, nk, name, *args):
             nonlocal launches
@@ -225,41 +237,64 @@ class Batch:
                    glabel=self.glabel.cpu().numpy(), one2x=self.one2x.cpu().numpy())
         return out
 
-    def decode(self, want_comps: bool = True):
+    def upload_visibility(self, V: np.ndarray, qframe: np.ndarray, vi: int = 0):
+        """Stage-wise entry (file-based drop-in): place an existing visibility matrix [Nm,T] and
+        the rows' frame ids for video `vi` before run(stages="B")."""
+        d = self.host_descs[vi]
+        assert V.shape == (d.Nm, d.T)
+        self.V[d.vt_off:d.vt_off + d.Nm * d.T] = torch.from_numpy(np.ascontiguousarray(V, np.float32).reshape(-1)).to(self.device)
+        self.qframe[d.row0:d.row0 + d.Nm] = torch.from_numpy(np.ascontiguousarray(qframe, np.int32)).to(self.device)
+
+    def upload_stage_b(self, rowinfo: np.ndarray, nclusters: int, status: int, vi: int = 0):
+        """Stage-wise entry: rows' (cluster, candidate run, v0, v1) and the stage-B status as the
+        host derived them from the stage-B json / stage-C folder, before run(stages="LD")."""
+        d = self.host_descs[vi]
+        assert rowinfo.shape == (d.Nm, 4)
+        self.rowinfo[4 * d.row0:4 * (d.row0 + d.Nm)] = torch.from_numpy(np.ascontiguousarray(rowinfo, np.int32).reshape(-1)).to(self.device)
+        v = torch.tensor([nclusters, status, -1, -1, int((rowinfo[:, 1] >= 0).sum())], dtype=torch.int32, device=self.device)
+        self.vidinfo[vi * S2D_VIDINFO_WORDS:vi * S2D_VIDINFO_WORDS + 5] = v
+        self.labels1[d.row0:d.row0 + d.Nm] = torch.from_numpy(np.ascontiguousarray(rowinfo[:, 0], np.int32)).to(self.device)
+
+    def decode(self, want_comps: bool = True, check_rows: bool = True):
         """Full results in the reference's python structures, one dict per video (same schema as
         oracle.keymask_oracle.discover)."""
         h = {k: getattr(self, k).cpu().numpy() for k in
              ("qframe", "qlabel", "vidinfo", "V", "labels1", "clrow", "rsbits", "rebits", "winbits", "rowinfo",
-              "clusterinfo", "one2x", "nmatch", "mbits", "glabel", "grp_n", "grp_one2x", "area", "gid_of")}
-        if want_comps:
+              "clusterinfo", "one2x", "nmatch", "mbits", "glabel", "grp_n", "grp_one2x", "area", "gid_of")
+             if getattr(self, k) is not None}
+        have_b = self.xbits is not None
+        if want_comps and self.hits is not None:
             h["hits"] = self.hits.cpu().numpy()
             h["uniq"] = self.uniq.cpu().numpy()
         vidinfo = h["vidinfo"].reshape(self.nv, S2D_VIDINFO_WORDS)
         clinfo = h["clusterinfo"].reshape(self.nv, S2D_MAX_CLUSTERS, S2D_CLINFO_WORDS)
         rowinfo = h["rowinfo"].reshape(-1, 4)
-        clrow = h["clrow"].reshape(-1, 4)
-        area = h["area"].reshape(-1, S2D_MAX_LABELS)
-        gid_of = h["gid_of"].reshape(-1, S2D_MAX_LABELS)
+        clrow = h["clrow"].reshape(-1, 4) if have_b else None
+        area = h["area"].reshape(-1, S2D_MAX_LABELS) if "area" in h else None
+        gid_of = h["gid_of"].reshape(-1, S2D_MAX_LABELS) if "gid_of" in h else None
+        want_comps = want_comps and "hits" in h
         results = []
         for vi in range(self.nv):
             d = self.host_descs[vi]
             T, Nm, TW, NW, L = d.T, d.Nm, d.TW, d.NW, d.L
             r0, f0 = d.row0, d.frame0
-            if int(vidinfo[vi, 5]) != Nm:
+            if check_rows and int(vidinfo[vi, 5]) != Nm:
                 raise _lib.S2DError(f"video {vi}: tracks hold {Nm} queries but the label maps enumerate "
                                     f"{int(vidinfo[vi, 5])} objects")
             qf = h["qframe"][r0:r0 + Nm].astype(np.int64)
             ql = h["qlabel"][r0:r0 + Nm].astype(np.int64)
             res = {"query_frame": qf, "query_label": ql}
-            res["V"] = h["V"][d.vt_off:d.vt_off + Nm * T].reshape(Nm, T)
+            if "V" in h:
+                res["V"] = h["V"][d.vt_off:d.vt_off + Nm * T].reshape(Nm, T)
             lab1 = h["labels1"][r0:r0 + Nm].astype(np.int64)
             res["labels1"] = lab1
             ri = rowinfo[r0:r0 + Nm]
             bits = lambda name: h[name][d.xbits_off:d.xbits_off + Nm * TW].reshape(Nm, TW).view(np.uint32)
-            rs, re, wb = bits("rsbits"), bits("rebits"), bits("winbits")
+            if have_b:
+                rs, re, wb = bits("rsbits"), bits("rebits"), bits("winbits")
             k = int(vidinfo[vi, 0])
             clusters = []
-            for c in range(k):
+            for c in range(k if have_b else 0):
                 starts = _setbits(rs[c], T)
                 ends = _setbits(re[c], T)
                 rows = np.nonzero(lab1 == c)[0]
@@ -277,7 +312,7 @@ class Batch:
                                  "ranges": [[s, e] for s, e in zip(starts, ends)],
                                  "all_candidates": all_cands, "all_visible_masks": all_vis})
             res["clusters"] = clusters
-            status = int(vidinfo[vi, 3])
+            status = int(vidinfo[vi, 3]) if self.mbits is not None else -1
             res["status"] = status
             res["stage_b_status"] = int(vidinfo[vi, 1])
             res["queries"] = []
@@ -323,8 +358,8 @@ class Batch:
                             groups.setdefault(int(gl[g]), []).append((int(qf[g]), int(ql[g])))
                     groupings.append({"cluster_id": c, "visibility_to_temporal_factor": int(ci[11]),
                                       "overall_mask_ids_per_label": groups})
-                    cov.append(int(ci[12]) / int(ci[1]) if ci[1] else 0)
-                    tot_m += int(ci[12]); tot_n += int(ci[1])
+                    cov.append(int(ci[12]) / int(ci[14]) if ci[14] else 0)     # matched / candidates of the cluster
+                    tot_m += int(ci[12]); tot_n += int(ci[14])
                     od = {"avg_one2x_cluster": int(ci[13]) / int(ci[14]) if ci[14] else float("nan")}
                     base = 16 * r0 + c * Nm
                     for lab in groups:

@@ -1,0 +1,154 @@
+"""The file-based drop-in modules (s2d_b200/keymask_ident) driven in the reference driver's order on
+an on-disk video, compared with what the unmodified reference wrote for the same video (goldens)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_video(root, labels, name="vid0"):
+    import cv2
+    T, H, W = labels.shape
+    vdir = os.path.join(root, "ytvis2021", "train", "JPEGImages", name)
+    mdir = os.path.join(root, "masks", name)
+    os.makedirs(vdir); os.makedirs(mdir)
+    pal = np.zeros((256, 3), np.uint8)
+    for l in range(1, 256):      # strictly increasing lexicographically: rank order == label order
+        pal[l] = (10 + l // 2, (37 * l + 11) % 256, (91 * l + 5) % 256) if l > 1 else (10, 1, 1)
+    pal[1:, 0] = 10 + np.arange(1, 256) // 2
+    pal[1:, 1] = (np.arange(1, 256) % 2) * 100 + 7
+    for t in range(T):
+        rgb = pal[labels[t]]
+        cv2.imwrite(os.path.join(mdir, f"{t:05d}.png"), rgb[..., ::-1])
+        cv2.imwrite(os.path.join(vdir, f"{t:05d}.jpg"), np.full((H, W, 3), 127, np.uint8))
+    return vdir, mdir
+
+
+class _Replay:
+    """CoTrackerPredictor stand-in replaying the fixture's tracks / visibility."""
+
+    def __init__(self, labels, tracks, vis):
+        from oracle.keymask_oracle import global_id_lookup
+        self.labels, self.tracks, self.vis = labels, tracks, vis
+        _, _, self.lut = global_id_lookup(labels)
+        self.calls = []
+
+    def __call__(self, checkpoint=None):
+        return self
+
+    def cuda(self):
+        return self
+
+    def predict(self, video, grid_size, grid_query_frame, segm_mask, backward_tracking):
+        sm = segm_mask[0, 0].cpu().numpy()
+        ys, xs = np.nonzero(sm)
+        lab = int(self.labels[grid_query_frame][ys[0], xs[0]])
+        q = self.lut[(int(grid_query_frame), lab)]
+        self.calls.append([int(grid_query_frame), lab, int(grid_size), bool(backward_tracking)])
+        return torch.from_numpy(self.tracks[q][None].copy()), torch.from_numpy(self.vis[q][None].astype(bool))
+
+
+class _Model:
+    def __init__(self, rp):
+        self.rp = rp
+
+    def cuda(self):
+        return self
+
+    def __call__(self, video, grid_size=0, grid_query_frame=0, segm_mask=None, backward_tracking=False):
+        return self.rp.predict(video, grid_size, grid_query_frame, segm_mask, backward_tracking)
+
+
+def test_dropin_stages_match_reference_files(golden_case, tmp_path):
+    from oracle.compare import _close
+    from s2d_b200.keymask_ident import (_engine, cotracker_matching, cotracker_occlusions, crw_utils,
+                                       identify_visibility_windows, keymask_utils)
+    name, g, labels, tracks, vis = golden_case
+    root = str(tmp_path)
+    vdir, mdir = _write_video(root, labels)
+    rp = _Replay(labels, tracks, vis)
+    _engine.set_tracker_factory(lambda checkpoint=None: _Model(rp))
+    _engine._label_cache.clear()
+    try:
+        vismaps, visclus, save = os.path.join(root, "vm"), os.path.join(root, "vc"), os.path.join(root, "seg")
+        a = cotracker_occlusions.extract_object_visibility_data(vdir, mdir, os.path.join(root, "videos"), vismaps, False)
+        assert np.array_equal(cotracker_occlusions.load_masks(mdir)[..., 0].numpy(), labels.astype(np.int64))
+        if a is None:
+            assert g["visibility_rows"] in (None, [])
+            return
+        rows = [(fr["frame_id"], o["object_id"], o["visibility"]) for fr in a["video_data"] for o in fr["data"]]
+        assert len(rows) == len(g["visibility_rows"])
+        for (f, o, v), ref in zip(rows, g["visibility_rows"]):
+            assert (f, o) == (ref["frame_id"], ref["object_id"])
+            assert np.array_equal(np.asarray(v, np.float32), np.asarray(ref["visibility"], np.float32), equal_nan=True)
+        with open(os.path.join(vismaps, "ytvis2021", "train", "data", "vid0.json")) as f:
+            assert json.load(f)["video_data"] == json.loads(json.dumps(a["video_data"]))
+
+        w = identify_visibility_windows.get_visibility_windows_for_video(a, "ytvis2021", "train", "vid0", visclus,
+                                                                         g["visibility_threshold"], False)
+        assert json.loads(json.dumps(w["clusters"])) == g["clusters"]
+        imgs, imgs_orig, lbls, meta = crw_utils.load_frames_and_masks(vdir, mdir, w, "ytvis2021")
+        cm = keymask_utils.save_segmentation_masks(imgs, imgs_orig, lbls, meta, save, False)
+        cands = sorted(os.path.relpath(p, cm) for p in glob.glob(os.path.join(cm, "cluster_*", "*.png")))
+        assert cands == g["candidate_files"]
+        try:
+            status = cotracker_matching.temporal_correspondence_match(vdir, mdir, cm, vismaps, visclus,
+                                                                      g["matching_threshold"], False)
+        except Exception as e:  # noqa: BLE001
+            status = f"exception:{type(e).__name__}"
+        assert status == g["status"], (status, g["status"])
+        nm = len(g["visibility_rows"])
+        if g["status"] == 1:
+            assert rp.calls == [[c[0], c[1], c[2], bool(c[3])] for c in g["tracker_calls"]]
+            groups = sorted(os.path.relpath(p, cm) for p in glob.glob(os.path.join(cm, "cluster_*", "group_*", "*.png")))
+            assert groups == g["group_files"]
+            with open(os.path.join(cm, "video_coverage.txt")) as f:
+                assert f.read() == g["video_coverage_txt"]
+            for cname, txt in g["cluster_coverage_txt"].items():
+                with open(os.path.join(cm, cname, "cluster_coverage.txt")) as f:
+                    assert f.read() == txt
+            with open(os.path.join(cm, "video_one2x_data.json")) as f:
+                mine = json.load(f)
+            assert list(mine) == list(g["one2x"])
+            for ck, ref in g["one2x"].items():
+                assert list(mine[ck]) == list(ref), (list(mine[ck]), list(ref))
+                for k, v in ref.items():
+                    if k == "avg_one2x_cluster":
+                        assert _close(float(mine[ck][k]), float(v))
+                    else:
+                        assert _close(float(mine[ck][k]["avg_one2x"]), float(v["avg_one2x"]))
+                        assert mine[ck][k]["one2x_counts"] == v["one2x_counts"] and mine[ck][k]["noisy"] == v["noisy"]
+            # candidate PNG content: 0/255 masks of the right label
+            import cv2
+            p0 = os.path.join(cm, g["candidate_files"][0])
+            parts = os.path.basename(p0).split("_")
+            f0, m0 = int(parts[1][5:]), int(parts[2].split(".")[0][4:])
+            assert np.array_equal(cv2.imread(p0, cv2.IMREAD_UNCHANGED), (labels[f0] == m0).astype(np.uint8) * 255)
+        else:
+            assert len(rp.calls) >= nm
+    finally:
+        _engine.set_tracker_factory(None)
+
+
+def test_dropin_helpers_on_gpu():
+    from s2d_b200.keymask_ident import cotracker_matching as cm, identify_visibility_windows as ivw
+    rng = np.random.default_rng(0)
+    H, W, T, P = 40, 60, 3, 200
+    tracks = torch.from_numpy(rng.uniform(-5, 65, size=(1, T, P, 2)).astype(np.float32))
+    planes = cm.pred_tracks_to_binary_masks(tracks, H, W)
+    from oracle import keymask_oracle as ko
+    for t in range(T):
+        assert np.array_equal(planes[0, t].numpy(), ko.rasterise_tracks(tracks[0, t].numpy(), H, W))
+    mask = torch.from_numpy((rng.random((H, W)) < 0.4).astype(np.uint8) * 255)
+    iou = cm.compute_point_mask_intersection(planes[0, 0], mask, 25)
+    pm = planes[0, 0].numpy() > 0
+    assert iou == (pm & (mask.numpy() > 0)).sum() / pm.sum()
+    maj = torch.tensor([0, 1, 1, 0, 0, 1, 0, 1, 1, 1], dtype=torch.float32)
+    assert ivw.get_visible_ranges(maj) == [(1, 2), (5, 5), (7, 9)]
+    assert ivw.get_visible_ranges(torch.zeros(7)) == []
+    assert ivw.get_visible_ranges(torch.ones(40)) == [(0, 39)]
