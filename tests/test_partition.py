@@ -1,0 +1,80 @@
+"""Multi-GPU path on CPU: LPT partition by video + host gather over gloo (world_size 2)."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+
+from s2d_b200.partition import contiguous_partition, lpt_partition, video_cost
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_lpt_is_balanced_and_deterministic():
+    rng = np.random.default_rng(0)
+    costs = rng.integers(1, 100, size=57).astype(float)
+    for n in (1, 2, 4, 8):
+        parts = lpt_partition(costs, n)
+        assert sorted(i for p in parts for i in p) == list(range(57))
+        loads = [sum(costs[i] for i in p) for p in parts]
+        assert max(loads) <= sum(costs) / n + max(costs)            # LPT bound
+        assert parts == lpt_partition(costs, n)
+    # long videos first: mixed 20..300-frame videos are better balanced than contiguous slices
+    costs = np.asarray([video_cost(T, 720, 1280, 20 * T, 4096) for T in [300] * 4 + [30] * 60])
+    worst = lambda parts: max(sum(costs[i] for i in p) for p in parts)
+    assert worst(lpt_partition(costs, 8)) < worst(contiguous_partition(len(costs), 8))
+
+
+def test_contiguous_matches_reference_slicing():
+    # main_keymask_ident.py:20-23: start = job_id * videos_per_job
+    assert contiguous_partition(10, 4) == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9]]
+
+
+def test_two_rank_gloo_gather_matches_single_process(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys, json
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch.distributed as dist
+        from oracle import keymask_oracle as ko
+        from s2d_b200.partition import run_partitioned, video_cost
+        from s2d_b200.synth import make_scene
+        rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+        dist.init_process_group("gloo")
+        shapes = [(8, 48, 64, 3, 32), (12, 40, 56, 2, 24), (6, 32, 48, 4, 16), (10, 48, 64, 2, 32), (7, 40, 40, 3, 16)]
+        scenes = [make_scene(100 + i, T, H, W, M, P) for i, (T, H, W, M, P) in enumerate(shapes)]
+        costs = [video_cost(T, H, W, s.tracks.shape[0], P) for s, (T, H, W, M, P) in zip(scenes, shapes)]
+        def worker(idx):
+            out = []
+            for i in idx:
+                r = ko.discover(scenes[i].labels, scenes[i].tracks, scenes[i].vis)
+                out.append([r["status"], [[g["cluster_id"], sorted(map(str, g["overall_mask_ids_per_label"].items()))]
+                                          for g in (r["groupings"] or [])]])
+            return out
+        res = run_partitioned(scenes, costs, worker, rank, world)
+        if rank == 0:
+            json.dump(res, open({str(tmp_path / 'out.json')!r}, "w"))
+        dist.destroy_process_group()
+    """))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                    "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)], check=True, env=env,
+                   timeout=300)
+    import json
+    two = json.load(open(tmp_path / "out.json"))
+    # single process reference of the same thing
+    from oracle import keymask_oracle as ko
+    from s2d_b200.synth import make_scene
+    shapes = [(8, 48, 64, 3, 32), (12, 40, 56, 2, 24), (6, 32, 48, 4, 16), (10, 48, 64, 2, 32), (7, 40, 40, 3, 16)]
+    one = []
+    for i, (T, H, W, M, P) in enumerate(shapes):
+        sc = make_scene(100 + i, T, H, W, M, P)
+        r = ko.discover(sc.labels, sc.tracks, sc.vis)
+        one.append([r["status"], [[g["cluster_id"], sorted(map(str, g["overall_mask_ids_per_label"].items()))]
+                                  for g in (r["groupings"] or [])]])
+    assert two == one
