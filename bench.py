@@ -144,7 +144,7 @@ def reference_arm(args):
     dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
     from s2d_b200.pipeline import VideoInput
     from s2d_b200.synth import make_scene_device
-    sc = make_scene_device(2024, T, H, W, M, P, dev)
+    sc = make_scene_device(2024, T, H, W, M, P, dev, point_order=args.point_order)
     vid = VideoInput(sc["labels"], sc["tracks"], sc["vis"], max_label=M)
     nq = args.ref_queries
     for _ in range(args.warmup):
@@ -161,7 +161,10 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000 * sum(secs) / len(secs), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64/u8 (torch CPU)", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "videos_per_gpu": nvid},
+            "config": {"workload": f"{args.workload}: {desc}", "videos_per_gpu": nvid, "frames_per_video": T,
+                       "resolution": [H, W], "masks_per_frame": M, "tracks_per_query": P,
+                       "queries_per_video": int(vid.tracks.shape[0]), "point_order": args.point_order,
+                       "partition": "single process on the host CPU"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -250,7 +253,9 @@ def main():
     k2_ms = stage_ms["point_votes"]
     achieved = alg_bytes / (k2_ms / 1000.0) / 1e9
     vr_bytes = sum(d.Nm * d.T * d.P + 8 * d.Nm * d.T for d in batch.host_descs)
-    roofline = {"kernel": "point_votes_kernel<256,16,true>", "bound": "hbm", "achieved": achieved, "peak": peak,
+    pv_name = ("point_votes_tma_kernel (persistent, cp.async.bulk ring)" if batch.use_tma and batch.vec4 and P <= 8192
+               else "point_votes_kernel (one CTA per tile)")
+    roofline = {"kernel": pv_name, "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k2_ms, "tiles_per_launch": tiles,
                 "share_of_step": k2_ms / (ms / args.steps),
