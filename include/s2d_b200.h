@@ -173,6 +173,12 @@ int s2d_pack_bits(const uint8_t* planes, int N, int64_t npix, uint32_t* bits, vo
 int s2d_overlap_bits(const uint32_t* Abits, int Na, const uint32_t* Bbits, int Nb, int64_t nwords,
                      int32_t* I, int32_t* areaA, int32_t* areaB, void* stream);
 
+/* Tensor-core variant: u8 planes (values 0/1) [N][npix], npix % 16 == 0, 16-byte aligned bases.
+ * TMA (SWIZZLE_128B) -> 4-stage smem ring -> tcgen05.mma kind::i8 (M128 x N x K32, int32 in TMEM),
+ * split-K over pixels with int32 atomics into I (cleared inside). */
+int s2d_overlap_i8(const uint8_t* A, int Na, const uint8_t* B, int Nb, int64_t npix, int32_t* I,
+                   void* stream);
+
 /* Rasterise tracks of one query into a u8 plane per frame (pred_tracks_to_binary_masks,
  * return_mask=False, cotracker_matching.py:453-503) - the dense A operand of K1. */
 int s2d_rasterise_tracks(const float* tracks, int T, int P, int H, int W, uint8_t* planes,

@@ -210,3 +210,21 @@ def test_dense_overlap_equals_sparse_votes(golden_case):
             _lib.call("s2d_overlap_bits", bA.data_ptr(), 1, bB.data_ptr(), len(labs), nw, I.data_ptr(), None, None, st)
             torch.cuda.synchronize()
             assert np.array_equal(I.cpu().numpy(), hits[q, t, labs]), (name, q, t)
+
+
+@pytest.mark.parametrize("Na,Nb,H,W", [(5, 7, 32, 48), (200, 20, 96, 128), (130, 300, 64, 80), (64, 33, 480, 854)])
+def test_overlap_i8_tensor_core_vs_oracle(Na, Nb, H, W):
+    """tcgen05 kind::i8 contraction == numpy int64 contraction, bit-exact."""
+    from s2d_b200 import _lib
+    rng = np.random.default_rng(Na * 1000 + Nb)
+    dev = _dev()
+    st = torch.cuda.current_stream().cuda_stream
+    A = (rng.random((Na, H, W)) < 0.03).astype(np.uint8)
+    Bm = (rng.random((Nb, H, W)) < 0.5).astype(np.uint8)
+    Bm[0] = 1
+    dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(Bm).to(dev)
+    I = torch.full((Na * Nb,), -1, dtype=torch.int32, device=dev)
+    _lib.call("s2d_overlap_i8", dA.data_ptr(), Na, dB.data_ptr(), Nb, H * W, I.data_ptr(), st)
+    torch.cuda.synchronize()
+    rI, _, _ = ko.overlap_counts(A, Bm)
+    assert np.array_equal(I.cpu().numpy().reshape(Na, Nb), rI)
