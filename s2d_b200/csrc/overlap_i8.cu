@@ -16,6 +16,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace s2d {
 
@@ -180,6 +181,178 @@ overlap_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (warp == 2) tmem_dealloc<TCOLS>(tmem);
 }
 
+// ------------------------------------------------------------------------------------------
+// s2d_overlap_gram_labels: one-hot operands synthesised on-chip from label bytes.
+//   rows r = f * L + l  (f < F frames, l < L labels);  G[r, r'] = sum_px [lab_f[px]==l] [lab_f'[px]==l']
+// 8 producer warps build the A (128 rows) and B (BN rows) tiles of a 128-pixel k-block directly in
+// the SWIZZLE_128B K-major layout (16-byte chunk c of row r lives at chunk c ^ (r & 7)), warp 8
+// issues the MMAs, warps 0-3 drain TMEM at the end (split-K atomics).
+// ------------------------------------------------------------------------------------------
+constexpr int GR_PF = 4;                 // label k-blocks in flight (cp.async groups)
+constexpr int GR_STAGES = 3;             // operand stages
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One producer thread per operand row (128 A rows + BN B rows): the row's frame / label are fixed
+// for the whole kernel, so a k-block costs 8 x (LDS.128 of the frame's label bytes, 4 byte-wise
+// compares, STS.128 into the SWIZZLE_128B K-major slot: chunk c of row r lives at chunk c ^ (r & 7)).
+// A warp covers 32 consecutive rows of one chunk: 1-3 distinct label addresses (broadcast) and
+// 512 B of conflict-free stores per instruction.
+template <int BN>
+__global__ void __launch_bounds__(GM_BLOCK_M + BN + 32, 1)
+gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npix, int kblocks_total,
+                   int kblocks_per_split, int nfr_max, int32_t* __restrict__ G) {
+    constexpr int STAGES = GR_STAGES;
+    constexpr int PRODUCERS = GM_BLOCK_M + BN;
+    constexpr int A_BYTES = GM_BLOCK_M * GM_BLOCK_K;
+    constexpr int B_BYTES = BN * GM_BLOCK_K;
+    extern __shared__ __align__(1024) uint8_t gsm_raw[];
+    uint8_t* gsm = gsm_raw + ((1024u - (s_u32(gsm_raw) & 1023u)) & 1023u);
+    uint8_t* sOps = gsm;                                         // STAGES x (A tile | B tile)
+    uint8_t* sLab = gsm + STAGES * (A_BYTES + B_BYTES);          // (GR_PF + 1) slots x nfr_max x 128 B
+    __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], accum_full;
+    __shared__ uint32_t tmem_base;
+
+    const int R = F * L;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * GM_BLOCK_M, n0 = blockIdx.y * BN;
+    const int kb0 = blockIdx.z * kblocks_per_split;
+    const int nkb = min(kblocks_total, kb0 + kblocks_per_split) - kb0;
+    // frames whose labels the two operand tiles need
+    const int fa0 = m0 / L, fa1 = min(R - 1, m0 + GM_BLOCK_M - 1) / L;
+    const int fb0 = min(n0, R - 1) / L, fb1 = min(R - 1, n0 + BN - 1) / L;
+    const int nfa = fa1 - fa0 + 1, nfb = fb1 - fb0 + 1;
+    const int slot_bytes = nfr_max * 128;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], PRODUCERS); bar_init(&empty[s], 1); }
+        bar_init(&accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc<BN>(&tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base;
+
+    if (nkb > 0) {
+        if (tid < PRODUCERS) {
+            // ---- operand producers: this thread's row ----
+            const bool isA = tid < GM_BLOCK_M;
+            const int rl = isA ? tid : tid - GM_BLOCK_M;                 // row inside the A or B tile
+            const int r = (isA ? m0 : n0) + rl;
+            const bool rvalid = r < R;
+            const int f = rvalid ? r / L : 0;
+            const uint32_t sp = rvalid ? (uint32_t)(r - f * L) * 0x01010101u : 0xFEFEFEFEu;   // 0xFE never matches (L <= 254)
+            const int lab_off = (isA ? (f - fa0) : nfa + (f - fb0)) * 128;
+            const int row_off = (isA ? 0 : A_BYTES) + rl * 128;
+            const int r7 = rl & 7;
+
+            auto issue_labels = [&](int i) {        // label bytes of k-block i -> ring slot i % (GR_PF + 1)
+                if (i < nkb) {
+                    uint8_t* slot = sLab + (i % (GR_PF + 1)) * slot_bytes;
+                    const int64_t px0 = (int64_t)(kb0 + i) * GM_BLOCK_K;
+                    for (int j = tid; j < (nfa + nfb) * 8; j += PRODUCERS) {
+                        const int fr = j >> 3, c = j & 7;
+                        const int ff = fr < nfa ? fa0 + fr : fb0 + (fr - nfa);
+                        const int64_t px = px0 + 16 * c;
+                        if (px < npix) cp_async16(slot + fr * 128 + 16 * c, labels + (int64_t)ff * npix + px);
+                        else *reinterpret_cast<uint4*>(slot + fr * 128 + 16 * c) = make_uint4(~0u, ~0u, ~0u, ~0u);   // 0xFF: no label
+                    }
+                }
+                cp_async_commit();
+            };
+            for (int j = 0; j < GR_PF; ++j) issue_labels(j);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                cp_async_wait<GR_PF - 1>();          // this thread's copies of k-block i have landed
+                asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");   // everybody's; k-block i-1 fully consumed
+                issue_labels(i + GR_PF);             // refills the slot k-block i-1 used
+                if (i >= STAGES) bar_wait(&empty[s], ((i / STAGES) - 1) & 1);
+                const uint8_t* lab = sLab + (i % (GR_PF + 1)) * slot_bytes + lab_off;
+                uint8_t* dst = sOps + s * (A_BYTES + B_BYTES) + row_off;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(lab + 16 * c);
+                    uint4 o;
+                    o.x = __vcmpeq4(w.x, sp) & 0x01010101u;
+                    o.y = __vcmpeq4(w.y, sp) & 0x01010101u;
+                    o.z = __vcmpeq4(w.z, sp) & 0x01010101u;
+                    o.w = __vcmpeq4(w.w, sp) & 0x01010101u;
+                    *reinterpret_cast<uint4*>(dst + ((c ^ r7) << 4)) = o;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (MMA) reads
+                bar_arrive(&full[s]);
+            }
+            cp_async_wait<0>();
+            // ---- epilogue (first four producer warps own the four TMEM lane quarters) ----
+            if (warp < 4) {
+                bar_wait(&accum_full, 0);
+                tc_fence_after();
+                const int row = m0 + warp * 32 + lane;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+                    if (row < R) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = n0 + c0 + j;
+                            if (col < R && v[j]) atomicAdd(&G[(int64_t)row * R + col], (int)v[j]);
+                        }
+                    }
+                }
+            }
+        } else if (lane == 0) {
+            // ---- MMA issuer ----
+            constexpr uint32_t idesc = umma_idesc_i8(BN);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                bar_wait(&full[s], (i / STAGES) & 1);
+                tc_fence_after();
+                const uint64_t ad = umma_desc(s_u32(sOps + s * (A_BYTES + B_BYTES)));
+                const uint64_t bd = umma_desc(s_u32(sOps + s * (A_BYTES + B_BYTES) + A_BYTES));
+#pragma unroll
+                for (int k = 0; k < GM_BLOCK_K / GM_UMMA_K; ++k)
+                    umma_i8(tmem, ad + (uint64_t)(k * GM_UMMA_K >> 4), bd + (uint64_t)(k * GM_UMMA_K >> 4), idesc, (i | k) != 0);
+                tc_commit(&empty[s]);
+            }
+            tc_commit(&accum_full);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<BN>(tmem);
+}
+
+template <int BN>
+static int launch_gram(const uint8_t* labels, int F, int L, int64_t npix, int32_t* G, cudaStream_t st) {
+    const int R = F * L;
+    const int nfr_max = (GM_BLOCK_M / L + 2) + (BN / L + 2);
+    const int smem = GR_STAGES * (GM_BLOCK_M + BN) * GM_BLOCK_K + (GR_PF + 1) * nfr_max * 128 + 1024;
+    if (smem > 227 * 1024) { set_error("s2d_overlap_gram_labels: nlab=%d is too small for the label ring (needs %d B of shared memory)", L, smem); return -1; }
+    auto kfn = gram_labels_kernel<BN>;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("gram_labels_kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return -2; }
+    const int mt = (R + GM_BLOCK_M - 1) / GM_BLOCK_M, nt = (R + BN - 1) / BN;
+    const int kblocks = (int)((npix + GM_BLOCK_K - 1) / GM_BLOCK_K);
+    int splits = 148 / (mt * nt);            // one wave of CTAs (1 CTA per SM)
+    if (splits > kblocks) splits = kblocks;
+    if (splits < 1) splits = 1;
+    const int per = (kblocks + splits - 1) / splits;
+    splits = (kblocks + per - 1) / per;
+    cudaMemsetAsync(G, 0, (size_t)R * R * sizeof(int32_t), st);
+    dim3 grid(mt, nt, splits);
+    kfn<<<grid, GM_BLOCK_M + BN + 32, smem, st>>>(labels, F, L, npix, kblocks, per, nfr_max, G);
+    S2D_CHECK_LAUNCH("gram_labels_kernel");
+    return 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -248,4 +421,15 @@ extern "C" int s2d_overlap_i8(const uint8_t* A, int Na, const uint8_t* B, int Nb
     if (Nb <= 64) return launch_overlap_i8<64>(A, Na, B, Nb, npix, I, st);
     if (Nb <= 128) return launch_overlap_i8<128>(A, Na, B, Nb, npix, I, st);
     return launch_overlap_i8<256>(A, Na, B, Nb, npix, I, st);
+}
+
+extern "C" int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int nlab, int64_t npix, int32_t* G, void* stream) {
+    S2D_CHECK_ARG(labels && G && nframes > 0 && nlab > 0 && nlab <= 254 && npix > 0, "s2d_overlap_gram_labels: bad arguments");
+    S2D_CHECK_ARG(npix % 16 == 0 && (((uintptr_t)labels) & 15) == 0,
+                  "s2d_overlap_gram_labels: label maps must be 16-byte aligned with a pixel count that is a multiple of 16");
+    S2D_CHECK_ARG((int64_t)nframes * nlab <= 46340, "s2d_overlap_gram_labels: too many rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = nframes * nlab;
+    if (R <= 128) return launch_gram<128>(labels, nframes, nlab, npix, G, st);
+    return launch_gram<256>(labels, nframes, nlab, npix, G, st);
 }

@@ -228,3 +228,20 @@ def test_overlap_i8_tensor_core_vs_oracle(Na, Nb, H, W):
     torch.cuda.synchronize()
     rI, _, _ = ko.overlap_counts(A, Bm)
     assert np.array_equal(I.cpu().numpy().reshape(Na, Nb), rI)
+
+
+@pytest.mark.parametrize("F,L,H,W", [(3, 4, 16, 32), (6, 21, 48, 64), (36, 21, 96, 128), (13, 30, 120, 160)])
+def test_gram_labels_tensor_core_vs_oracle(F, L, H, W):
+    """one-hot Gram matrix synthesised on-chip + tcgen05 kind::i8 == numpy one-hot contraction."""
+    from s2d_b200 import _lib
+    rng = np.random.default_rng(F * 100 + L)
+    dev = _dev()
+    labels = rng.integers(0, L, size=(F, H, W)).astype(np.uint8)
+    labels[:, : H // 3] = 0
+    d = torch.from_numpy(labels).to(dev)
+    R = F * L
+    G = torch.full((R * R,), -1, dtype=torch.int32, device=dev)
+    _lib.call("s2d_overlap_gram_labels", d.data_ptr(), F, L, H * W, G.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    X = (labels.reshape(F, 1, -1) == np.arange(L, dtype=np.uint8)[None, :, None]).reshape(R, -1).astype(np.int64)
+    assert np.array_equal(G.cpu().numpy().reshape(R, R), X @ X.T)
