@@ -180,11 +180,13 @@ int s2d_overlap_i8(const uint8_t* A, int Na, const uint8_t* B, int Nb, int64_t n
                    void* stream);
 
 /* One-hot Gram form straight from label maps: rows r = f * nlab + l for `nframes` frames and labels
- * 0..nlab-1 (4 <= nlab <= 254); G[r, r'] = |mask(f,l) AND mask(f',l')| (int32 [R][R], cleared inside). The u8 0/1
+ * 0..nlab-1 (4 <= nlab <= 254); G[r, r'] = |mask(f,l) AND mask(f',l')| (int32 [R][R]). `work`: int32 scratch
+ * of s2d_overlap_gram_work_ints() elements (per-split partial tiles, summed by a second kernel). The u8 0/1
  * operand tiles are synthesised in shared memory from the 1 B/px label bytes, so HBM traffic is
  * nframes*npix bytes for 2*R^2*npix tensor-core ops (the tensor-bound form). */
-int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int nlab, int64_t npix, int32_t* G,
-                            void* stream);
+int s2d_overlap_gram_work_ints(int nframes, int nlab, int64_t npix, int64_t* out);
+int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int nlab, int64_t npix, int32_t* work,
+                            int32_t* G, void* stream);
 
 /* Rasterise tracks of one query into a u8 plane per frame (pred_tracks_to_binary_masks,
  * return_mask=False, cotracker_matching.py:453-503) - the dense A operand of K1. */

@@ -206,7 +206,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int BN>
 __global__ void __launch_bounds__(GM_BLOCK_M + BN + 32, 1)
 gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npix, int kblocks_total,
-                   int kblocks_per_split, int nfr_max, int32_t* __restrict__ G) {
+                   int kblocks_per_split, int nfr_max, int Rp, int32_t* __restrict__ part) {
     constexpr int STAGES = GR_STAGES;
     constexpr int PRODUCERS = GM_BLOCK_M + BN;
     constexpr int A_BYTES = GM_BLOCK_M * GM_BLOCK_K;
@@ -215,6 +215,7 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
     uint8_t* gsm = gsm_raw + ((1024u - (s_u32(gsm_raw) & 1023u)) & 1023u);
     uint8_t* sOps = gsm;                                         // STAGES x (A tile | B tile)
     uint8_t* sLab = gsm + STAGES * (A_BYTES + B_BYTES);          // (GR_PF + 1) slots x nfr_max x 128 B
+    uint8_t* sDesc = sLab + (GR_PF + 1) * nfr_max * 128;         // 2 slots x nfr_max x 8 chunk descriptors
     __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], accum_full;
     __shared__ uint32_t tmem_base;
 
@@ -230,7 +231,7 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
     const int slot_bytes = nfr_max * 128;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], PRODUCERS); bar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], PRODUCERS / 32); bar_init(&empty[s], 1); }
         bar_init(&accum_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -267,43 +268,74 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
                 }
                 cp_async_commit();
             };
+            // chunk descriptors of k-block i: the single label of a 16-pixel chunk, 0xFF when it is mixed.
+            // Label maps are piecewise constant, so almost every chunk is uniform and a row's 16 output
+            // bytes are all-ones or all-zeros without looking at the pixels.
+            auto make_desc = [&](int i) {
+                if (i < nkb) {
+                    const uint8_t* slot = sLab + (i % (GR_PF + 1)) * slot_bytes;
+                    for (int j = tid; j < (nfa + nfb) * 8; j += PRODUCERS) {
+                        const uint4 w = *reinterpret_cast<const uint4*>(slot + j * 16);
+                        const bool uni = (w.x == w.y) & (w.y == w.z) & (w.z == w.w) & (w.x == __byte_perm(w.x, 0, 0x0000));
+                        sDesc[(i & 1) * nfr_max * 8 + j] = uni ? (uint8_t)(w.x & 255u) : (uint8_t)0xFF;
+                    }
+                }
+            };
             for (int j = 0; j < GR_PF; ++j) issue_labels(j);
+            cp_async_wait<GR_PF - 1>();
+            asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");
+            make_desc(0);
+            const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+            const uint4 zeros = make_uint4(0, 0, 0, 0);
+            const uint32_t mylab = sp & 255u;
+            const int desc_off = (isA ? (f - fa0) : nfa + (f - fb0)) * 8;
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES;
-                cp_async_wait<GR_PF - 1>();          // this thread's copies of k-block i have landed
-                asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");   // everybody's; k-block i-1 fully consumed
+                cp_async_wait<GR_PF - 2>();          // this thread's copies of k-blocks <= i+1 have landed
+                asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");   // everybody's; desc(i) visible; k-block i-1 consumed
                 issue_labels(i + GR_PF);             // refills the slot k-block i-1 used
+                make_desc(i + 1);
                 if (i >= STAGES) bar_wait(&empty[s], ((i / STAGES) - 1) & 1);
                 const uint8_t* lab = sLab + (i % (GR_PF + 1)) * slot_bytes + lab_off;
                 uint8_t* dst = sOps + s * (A_BYTES + B_BYTES) + row_off;
+                const uint2 d8 = *reinterpret_cast<const uint2*>(sDesc + (i & 1) * nfr_max * 8 + desc_off);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const uint4 w = *reinterpret_cast<const uint4*>(lab + 16 * c);
-                    uint4 o;
-                    o.x = __vcmpeq4(w.x, sp) & 0x01010101u;
-                    o.y = __vcmpeq4(w.y, sp) & 0x01010101u;
-                    o.z = __vcmpeq4(w.z, sp) & 0x01010101u;
-                    o.w = __vcmpeq4(w.w, sp) & 0x01010101u;
-                    *reinterpret_cast<uint4*>(dst + ((c ^ r7) << 4)) = o;
+                    const uint32_t u = ((c < 4 ? d8.x : d8.y) >> (8 * (c & 3))) & 255u;
+                    uint4* out = reinterpret_cast<uint4*>(dst + ((c ^ r7) << 4));
+                    if (u != 0xFFu) {
+                        *out = (u == mylab && rvalid) ? ones : zeros;
+                    } else {                          // mixed chunk (object border): compare the 16 pixels
+                        const uint4 w = *reinterpret_cast<const uint4*>(lab + 16 * c);
+                        uint4 o;
+                        o.x = __vcmpeq4(w.x, sp) & 0x01010101u;
+                        o.y = __vcmpeq4(w.y, sp) & 0x01010101u;
+                        o.z = __vcmpeq4(w.z, sp) & 0x01010101u;
+                        o.w = __vcmpeq4(w.w, sp) & 0x01010101u;
+                        *out = o;
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (MMA) reads
-                bar_arrive(&full[s]);
+                __syncwarp();
+                if (lane == 0) bar_arrive(&full[s]);                           // one arrival per producer warp
             }
             cp_async_wait<0>();
-            // ---- epilogue (first four producer warps own the four TMEM lane quarters) ----
+            // ---- epilogue (first four producer warps own the four TMEM lane quarters): the split's
+            // partial tile goes out with plain 128-bit stores; gram_reduce_kernel sums the splits ----
             if (warp < 4) {
                 bar_wait(&accum_full, 0);
                 tc_fence_after();
                 const int row = m0 + warp * 32 + lane;
+                int32_t* prow = part + ((int64_t)blockIdx.z * R + row) * Rp;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
                     if (row < R) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
+                        for (int j = 0; j < 32; j += 4) {
                             const int col = n0 + c0 + j;
-                            if (col < R && v[j]) atomicAdd(&G[(int64_t)row * R + col], (int)v[j]);
+                            if (col < Rp) *reinterpret_cast<uint4*>(prow + col) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                         }
                     }
                 }
@@ -330,26 +362,44 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
     if (warp == 0) tmem_dealloc<BN>(tmem);
 }
 
+// G[r][c] = sum over splits of part[s][r][c]  (row pitch Rp in part, R in G)
+__global__ void gram_reduce_kernel(const int32_t* __restrict__ part, int splits, int R, int Rp, int32_t* __restrict__ G) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)R * R) return;
+    const int r = (int)(i / R), c = (int)(i - (int64_t)r * R);
+    int acc = 0;
+    for (int s = 0; s < splits; ++s) acc += part[((int64_t)s * R + r) * Rp + c];
+    G[i] = acc;
+}
+
+static void gram_plan(int R, int BN, int64_t npix, int* mt, int* nt, int* kblocks, int* per, int* splits, int* Rp) {
+    *mt = (R + GM_BLOCK_M - 1) / GM_BLOCK_M;
+    *nt = (R + BN - 1) / BN;
+    *kblocks = (int)((npix + GM_BLOCK_K - 1) / GM_BLOCK_K);
+    int sp = 148 / (*mt * *nt);              // one wave of CTAs (1 CTA per SM)
+    if (sp > *kblocks) sp = *kblocks;
+    if (sp < 1) sp = 1;
+    *per = (*kblocks + sp - 1) / sp;
+    *splits = (*kblocks + *per - 1) / *per;
+    *Rp = *nt * BN;                          // every column an epilogue may store exists
+}
+
 template <int BN>
-static int launch_gram(const uint8_t* labels, int F, int L, int64_t npix, int32_t* G, cudaStream_t st) {
+static int launch_gram(const uint8_t* labels, int F, int L, int64_t npix, int32_t* work, int32_t* G, cudaStream_t st) {
     const int R = F * L;
-    const int nfr_max = (GM_BLOCK_M / L + 2) + (BN / L + 2);
-    const int smem = GR_STAGES * (GM_BLOCK_M + BN) * GM_BLOCK_K + (GR_PF + 1) * nfr_max * 128 + 1024;
+    const int nfr_max = (F < GM_BLOCK_M / L + 2 ? F : GM_BLOCK_M / L + 2) + (F < BN / L + 2 ? F : BN / L + 2);
+    const int smem = GR_STAGES * (GM_BLOCK_M + BN) * GM_BLOCK_K + (GR_PF + 1) * nfr_max * 128 + 2 * nfr_max * 8 + 1024;
     if (smem > 227 * 1024) { set_error("s2d_overlap_gram_labels: nlab=%d is too small for the label ring (needs %d B of shared memory)", L, smem); return -1; }
     auto kfn = gram_labels_kernel<BN>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("gram_labels_kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return -2; }
-    const int mt = (R + GM_BLOCK_M - 1) / GM_BLOCK_M, nt = (R + BN - 1) / BN;
-    const int kblocks = (int)((npix + GM_BLOCK_K - 1) / GM_BLOCK_K);
-    int splits = 148 / (mt * nt);            // one wave of CTAs (1 CTA per SM)
-    if (splits > kblocks) splits = kblocks;
-    if (splits < 1) splits = 1;
-    const int per = (kblocks + splits - 1) / splits;
-    splits = (kblocks + per - 1) / per;
-    cudaMemsetAsync(G, 0, (size_t)R * R * sizeof(int32_t), st);
+    int mt, nt, kblocks, per, splits, Rp;
+    gram_plan(R, BN, npix, &mt, &nt, &kblocks, &per, &splits, &Rp);
     dim3 grid(mt, nt, splits);
-    kfn<<<grid, GM_BLOCK_M + BN + 32, smem, st>>>(labels, F, L, npix, kblocks, per, nfr_max, G);
+    kfn<<<grid, GM_BLOCK_M + BN + 32, smem, st>>>(labels, F, L, npix, kblocks, per, nfr_max, Rp, work);
     S2D_CHECK_LAUNCH("gram_labels_kernel");
+    gram_reduce_kernel<<<(unsigned)(((int64_t)R * R + 255) / 256), 256, 0, st>>>(work, splits, R, Rp, G);
+    S2D_CHECK_LAUNCH("gram_reduce_kernel");
     return 0;
 }
 
@@ -423,13 +473,23 @@ extern "C" int s2d_overlap_i8(const uint8_t* A, int Na, const uint8_t* B, int Nb
     return launch_overlap_i8<256>(A, Na, B, Nb, npix, I, st);
 }
 
-extern "C" int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int nlab, int64_t npix, int32_t* G, void* stream) {
-    S2D_CHECK_ARG(labels && G && nframes > 0 && nlab > 0 && nlab <= 254 && npix > 0, "s2d_overlap_gram_labels: bad arguments");
-    S2D_CHECK_ARG(npix % 16 == 0 && (((uintptr_t)labels) & 15) == 0,
-                  "s2d_overlap_gram_labels: label maps must be 16-byte aligned with a pixel count that is a multiple of 16");
+extern "C" int s2d_overlap_gram_work_ints(int nframes, int nlab, int64_t npix, int64_t* out) {
+    if (!out || nframes <= 0 || nlab <= 0 || npix <= 0) return -1;
+    const int R = nframes * nlab, BN = R <= 128 ? 128 : 256;
+    int mt, nt, kblocks, per, splits, Rp;
+    gram_plan(R, BN, npix, &mt, &nt, &kblocks, &per, &splits, &Rp);
+    *out = (int64_t)splits * R * Rp + 4;
+    return 0;
+}
+
+extern "C" int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int nlab, int64_t npix, int32_t* work,
+                                       int32_t* G, void* stream) {
+    S2D_CHECK_ARG(labels && G && work && nframes > 0 && nlab > 0 && nlab <= 254 && npix > 0, "s2d_overlap_gram_labels: bad arguments");
+    S2D_CHECK_ARG(npix % 16 == 0 && (((uintptr_t)labels) & 15) == 0 && (((uintptr_t)work) & 15) == 0,
+                  "s2d_overlap_gram_labels: label maps / work must be 16-byte aligned with a pixel count that is a multiple of 16");
     S2D_CHECK_ARG((int64_t)nframes * nlab <= 46340, "s2d_overlap_gram_labels: too many rows");
     cudaStream_t st = (cudaStream_t)stream;
     const int R = nframes * nlab;
-    if (R <= 128) return launch_gram<128>(labels, nframes, nlab, npix, G, st);
-    return launch_gram<256>(labels, nframes, nlab, npix, G, st);
+    if (R <= 128) return launch_gram<128>(labels, nframes, nlab, npix, work, G, st);
+    return launch_gram<256>(labels, nframes, nlab, npix, work, G, st);
 }

@@ -241,7 +241,12 @@ def test_gram_labels_tensor_core_vs_oracle(F, L, H, W):
     d = torch.from_numpy(labels).to(dev)
     R = F * L
     G = torch.full((R * R,), -1, dtype=torch.int32, device=dev)
-    _lib.call("s2d_overlap_gram_labels", d.data_ptr(), F, L, H * W, G.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    import ctypes as C
+    n = C.c_int64()
+    _lib.call("s2d_overlap_gram_work_ints", F, L, H * W, C.byref(n))
+    work = torch.full((n.value,), -7, dtype=torch.int32, device=dev)
+    _lib.call("s2d_overlap_gram_labels", d.data_ptr(), F, L, H * W, work.data_ptr(), G.data_ptr(),
+              torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     X = (labels.reshape(F, 1, -1) == np.arange(L, dtype=np.uint8)[None, :, None]).reshape(R, -1).astype(np.int64)
     assert np.array_equal(G.cpu().numpy().reshape(R, R), X @ X.T)
