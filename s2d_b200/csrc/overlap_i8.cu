@@ -188,8 +188,10 @@ overlap_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 // the SWIZZLE_128B K-major layout (16-byte chunk c of row r lives at chunk c ^ (r & 7)), warp 8
 // issues the MMAs, warps 0-3 drain TMEM at the end (split-K atomics).
 // ------------------------------------------------------------------------------------------
-constexpr int GR_PF = 4;                 // label k-blocks in flight (cp.async groups)
-constexpr int GR_STAGES = 3;             // operand stages
+constexpr int GR_PF = 3;                 // label k-blocks in flight per producer group (cp.async groups)
+constexpr int GR_STAGES = 4;             // operand stages
+constexpr int GR_GROUPS = 2;             // independent producer groups working on alternate k-blocks
+static_assert(GR_STAGES == 2 * GR_GROUPS, "each producer group alternates between exactly two stages");
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -204,7 +206,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // A warp covers 32 consecutive rows of one chunk: 1-3 distinct label addresses (broadcast) and
 // 512 B of conflict-free stores per instruction.
 template <int BN>
-__global__ void __launch_bounds__(GM_BLOCK_M + BN + 32, 1)
+__global__ void __launch_bounds__(GR_GROUPS * (GM_BLOCK_M + BN) + 32, 1)
 gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npix, int kblocks_total,
                    int kblocks_per_split, int nfr_max, int Rp, int32_t* __restrict__ part) {
     constexpr int STAGES = GR_STAGES;
@@ -214,13 +216,15 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
     extern __shared__ __align__(1024) uint8_t gsm_raw[];
     uint8_t* gsm = gsm_raw + ((1024u - (s_u32(gsm_raw) & 1023u)) & 1023u);
     uint8_t* sOps = gsm;                                         // STAGES x (A tile | B tile)
-    uint8_t* sLab = gsm + STAGES * (A_BYTES + B_BYTES);          // (GR_PF + 1) slots x nfr_max x 128 B
-    uint8_t* sDesc = sLab + (GR_PF + 1) * nfr_max * 128;         // 2 slots x nfr_max x 8 chunk descriptors
+    // per producer group: (GR_PF + 1) label slots x nfr_max x 128 B, then 2 slots x nfr_max x 8 chunk descriptors
+    const int grp = threadIdx.x / PRODUCERS;                     // 0, 1: producer groups; 2: MMA warp
+    uint8_t* sLab = gsm + STAGES * (A_BYTES + B_BYTES) + (grp & 1) * ((GR_PF + 1) * nfr_max * 128 + 2 * nfr_max * 8);
+    uint8_t* sDesc = sLab + (GR_PF + 1) * nfr_max * 128;
     __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], accum_full;
     __shared__ uint32_t tmem_base;
 
     const int R = F * L;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x % PRODUCERS, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // tid: index inside the group
     const int m0 = blockIdx.x * GM_BLOCK_M, n0 = blockIdx.y * BN;
     const int kb0 = blockIdx.z * kblocks_per_split;
     const int nkb = min(kblocks_total, kb0 + kblocks_per_split) - kb0;
@@ -230,7 +234,7 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
     const int nfa = fa1 - fa0 + 1, nfb = fb1 - fb0 + 1;
     const int slot_bytes = nfr_max * 128;
 
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], PRODUCERS / 32); bar_init(&empty[s], 1); }
         bar_init(&accum_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -242,8 +246,8 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
     const uint32_t tmem = tmem_base;
 
     if (nkb > 0) {
-        if (tid < PRODUCERS) {
-            // ---- operand producers: this thread's row ----
+        if (grp < GR_GROUPS) {
+            // ---- operand producers: this thread's row; group g builds k-blocks g, g+2, g+4, ... ----
             const bool isA = tid < GM_BLOCK_M;
             const int rl = isA ? tid : tid - GM_BLOCK_M;                 // row inside the A or B tile
             const int r = (isA ? m0 : n0) + rl;
@@ -254,9 +258,10 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
             const int row_off = (isA ? 0 : A_BYTES) + rl * 128;
             const int r7 = rl & 7;
 
-            auto issue_labels = [&](int i) {        // label bytes of k-block i -> ring slot i % (GR_PF + 1)
+            auto issue_labels = [&](int ii) {       // label bytes of local k-block ii -> ring slot ii % (GR_PF + 1)
+                const int i = ii * GR_GROUPS + grp;
                 if (i < nkb) {
-                    uint8_t* slot = sLab + (i % (GR_PF + 1)) * slot_bytes;
+                    uint8_t* slot = sLab + (ii % (GR_PF + 1)) * slot_bytes;
                     const int64_t px0 = (int64_t)(kb0 + i) * GM_BLOCK_K;
                     for (int j = tid; j < (nfa + nfb) * 8; j += PRODUCERS) {
                         const int fr = j >> 3, c = j & 7;
@@ -271,34 +276,40 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
             // chunk descriptors of k-block i: the single label of a 16-pixel chunk, 0xFF when it is mixed.
             // Label maps are piecewise constant, so almost every chunk is uniform and a row's 16 output
             // bytes are all-ones or all-zeros without looking at the pixels.
-            auto make_desc = [&](int i) {
-                if (i < nkb) {
-                    const uint8_t* slot = sLab + (i % (GR_PF + 1)) * slot_bytes;
+            auto make_desc = [&](int ii) {
+                if (ii * GR_GROUPS + grp < nkb) {
+                    const uint8_t* slot = sLab + (ii % (GR_PF + 1)) * slot_bytes;
                     for (int j = tid; j < (nfa + nfb) * 8; j += PRODUCERS) {
                         const uint4 w = *reinterpret_cast<const uint4*>(slot + j * 16);
                         const bool uni = (w.x == w.y) & (w.y == w.z) & (w.z == w.w) & (w.x == __byte_perm(w.x, 0, 0x0000));
-                        sDesc[(i & 1) * nfr_max * 8 + j] = uni ? (uint8_t)(w.x & 255u) : (uint8_t)0xFF;
+                        sDesc[(ii & 1) * nfr_max * 8 + j] = uni ? (uint8_t)(w.x & 255u) : (uint8_t)0xFF;
                     }
                 }
             };
+            // local sequence number ii <-> global k-block i = ii * GR_GROUPS + grp
+            const int nloc = (nkb - grp + GR_GROUPS - 1) / GR_GROUPS;
             for (int j = 0; j < GR_PF; ++j) issue_labels(j);
             cp_async_wait<GR_PF - 1>();
-            asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");
+            if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");
+            else asm volatile("bar.sync 2, %0;" ::"n"(PRODUCERS) : "memory");
             make_desc(0);
             const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
             const uint4 zeros = make_uint4(0, 0, 0, 0);
             const uint32_t mylab = sp & 255u;
             const int desc_off = (isA ? (f - fa0) : nfa + (f - fb0)) * 8;
-            for (int i = 0; i < nkb; ++i) {
+            for (int ii = 0; ii < nloc; ++ii) {
+                const int i = ii * GR_GROUPS + grp;
                 const int s = i % STAGES;
-                cp_async_wait<GR_PF - 2>();          // this thread's copies of k-blocks <= i+1 have landed
-                asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");   // everybody's; desc(i) visible; k-block i-1 consumed
-                issue_labels(i + GR_PF);             // refills the slot k-block i-1 used
-                make_desc(i + 1);
+                cp_async_wait<GR_PF - 2>();          // this thread's copies of local k-blocks <= ii+1 have landed
+                // everybody's; desc(ii) visible; local k-block ii-1 consumed
+                if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");
+                else asm volatile("bar.sync 2, %0;" ::"n"(PRODUCERS) : "memory");
+                issue_labels(ii + GR_PF);            // refills the slot local k-block ii-1 used
+                make_desc(ii + 1);
                 if (i >= STAGES) bar_wait(&empty[s], ((i / STAGES) - 1) & 1);
-                const uint8_t* lab = sLab + (i % (GR_PF + 1)) * slot_bytes + lab_off;
+                const uint8_t* lab = sLab + (ii % (GR_PF + 1)) * slot_bytes + lab_off;
                 uint8_t* dst = sOps + s * (A_BYTES + B_BYTES) + row_off;
-                const uint2 d8 = *reinterpret_cast<const uint2*>(sDesc + (i & 1) * nfr_max * 8 + desc_off);
+                const uint2 d8 = *reinterpret_cast<const uint2*>(sDesc + (ii & 1) * nfr_max * 8 + desc_off);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const uint32_t u = ((c < 4 ? d8.x : d8.y) >> (8 * (c & 3))) & 255u;
@@ -319,7 +330,6 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
                 __syncwarp();
                 if (lane == 0) bar_arrive(&full[s]);                           // one arrival per producer warp
             }
-            cp_async_wait<0>();
             // ---- epilogue (first four producer warps own the four TMEM lane quarters): the split's
             // partial tile goes out with plain 128-bit stores; gram_reduce_kernel sums the splits ----
             if (warp < 4) {
@@ -388,7 +398,7 @@ template <int BN>
 static int launch_gram(const uint8_t* labels, int F, int L, int64_t npix, int32_t* work, int32_t* G, cudaStream_t st) {
     const int R = F * L;
     const int nfr_max = (F < GM_BLOCK_M / L + 2 ? F : GM_BLOCK_M / L + 2) + (F < BN / L + 2 ? F : BN / L + 2);
-    const int smem = GR_STAGES * (GM_BLOCK_M + BN) * GM_BLOCK_K + (GR_PF + 1) * nfr_max * 128 + 2 * nfr_max * 8 + 1024;
+    const int smem = GR_STAGES * (GM_BLOCK_M + BN) * GM_BLOCK_K + GR_GROUPS * ((GR_PF + 1) * nfr_max * 128 + 2 * nfr_max * 8) + 1024;
     if (smem > 227 * 1024) { set_error("s2d_overlap_gram_labels: nlab=%d is too small for the label ring (needs %d B of shared memory)", L, smem); return -1; }
     auto kfn = gram_labels_kernel<BN>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -396,7 +406,7 @@ static int launch_gram(const uint8_t* labels, int F, int L, int64_t npix, int32_
     int mt, nt, kblocks, per, splits, Rp;
     gram_plan(R, BN, npix, &mt, &nt, &kblocks, &per, &splits, &Rp);
     dim3 grid(mt, nt, splits);
-    kfn<<<grid, GM_BLOCK_M + BN + 32, smem, st>>>(labels, F, L, npix, kblocks, per, nfr_max, Rp, work);
+    kfn<<<grid, GR_GROUPS * (GM_BLOCK_M + BN) + 32, smem, st>>>(labels, F, L, npix, kblocks, per, nfr_max, Rp, work);
     S2D_CHECK_LAUNCH("gram_labels_kernel");
     gram_reduce_kernel<<<(unsigned)(((int64_t)R * R + 255) / 256), 256, 0, st>>>(work, splits, R, Rp, G);
     S2D_CHECK_LAUNCH("gram_reduce_kernel");
