@@ -184,6 +184,7 @@ def main():
                     help="order of a query's points: raster (CoTracker-like grid order) or random (worst case)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-k1", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -287,6 +288,11 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(args, vids, dev, world, params, barrier)
 
+    # ---- K1 on the tensor cores: one-hot Gram matrix of each video's label maps (outside the timed step)
+    k1 = None
+    if rank == 0 and not args.no_k1:
+        k1 = run_k1(vids, batch, M + 1)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         fps, dt, npairs, n = cpu_sample(vids[0], args.cpu_queries)
@@ -305,10 +311,65 @@ def main():
                            "cache": "inputs per step (tracks+flags+labels) >> 126 MB L2, no flush needed",
                            "input_bytes_per_step_per_gpu": int(sum(v.tracks.numel() * 4 + v.vis.numel() + v.labels.numel() for v in vids))},
                 "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "stage_ms": stage_ms, "parity_check": parity, "cpu_baseline": cpu}
+                "stage_ms": stage_ms, "parity_check": parity, "overlap_gemm": k1, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_k1(vids, batch, L):
+    """Cross-frame mask-overlap matrix of a video (all (frame,label) masks against each other) as an int8
+    contraction on the tensor cores, operands synthesised on-chip from the label maps. Reports achieved
+    TOP/s against an int8 GEMM peak measured here with cuBLASLt (torch._int_mm 8192^3)."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from s2d_b200 import _lib
+    dev = vids[0].labels.device
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def timeit(fn, iters, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / iters
+
+    n = 8192
+    x = torch.randint(-3, 3, (n, n), dtype=torch.int8, device=dev)
+    y = torch.randint(-3, 3, (n, n), dtype=torch.int8, device=dev)
+    peak = 2.0 * n ** 3 / (timeit(lambda: torch._int_mm(x, y), 10) * 1e-3) / 1e12
+    del x, y
+    T, H, W = vids[0].labels.shape
+    if (H * W) % 16:
+        return {"skipped": "pixel count is not a multiple of 16"}
+    R = T * L
+    nv = min(8, len(vids))
+    nw = C.c_int64()
+    _lib.call("s2d_overlap_gram_work_ints", T, L, H * W, C.byref(nw))
+    work = torch.empty(nw.value, dtype=torch.int32, device=dev)
+    G = torch.empty(R * R, dtype=torch.int32, device=dev)
+
+    def run():
+        for v in vids[:nv]:
+            _lib.call("s2d_overlap_gram_labels", v.labels.data_ptr(), T, L, H * W, work.data_ptr(), G.data_ptr(), st)
+    ms = timeit(run, 5) / nv
+    # exact check: the diagonal of the Gram matrix is the mask area table of K0 (last video run)
+    d = batch.host_descs[nv - 1]
+    area = batch.area[d.frame0 * 256:(d.frame0 + T) * 256].reshape(T, 256)[:, :L].reshape(-1).cpu().numpy()
+    diag = G.reshape(R, R).diagonal().cpu().numpy()
+    ops = 2.0 * R * R * H * W
+    tops = ops / (ms * 1e-3) / 1e12
+    return {"kernel": "gram_labels_kernel: one-hot operands synthesised in smem, tcgen05.mma kind::i8, int32 in TMEM",
+            "rows": R, "pixels": H * W, "ms_per_video": ms, "achieved": tops, "unit": "TOP/s",
+            "peak": peak, "peak_source": "measured here: torch._int_mm 8192^3 (cuBLASLt int8)", "frac": tops / peak,
+            "frac_of_nominal_4500": tops / 4500.0, "hbm_bytes_per_video": int(T * H * W),
+            "check": "ok" if np.array_equal(diag, area) else "MISMATCH"}
 
 
 def run_e2e(args, vids, dev, world, params, barrier):
