@@ -408,6 +408,7 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                 ti.lbl = dp->labels + (int64_t)t * dp->H * dp->W;
                 ti.hout = hits + dp->hits_off + rt * L;
                 ti.uout = uniq + dp->vt_off + rt;
+                *ti.uout = 0;        // consumers accumulate per-warp partial sums (ordered by the mbarrier release/acquire)
                 ti.W = dp->W; ti.H = dp->H; ti.L = L;
                 const int32_t* np = dp->npts;
                 ti.n = np ? min(max(np[q], 0), P) : P;
@@ -496,7 +497,7 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                 if (odd) {
 #pragma unroll
                     for (int k = 0; k < PPT; ++k)
-                        if ((odd >> k) & 1u) { atomicAdd(&hist[lab[k]], 1); atomicAdd(&hist[S2D_MAX_LABELS], 1); }
+                        if ((odd >> k) & 1u) atomicAdd(&hist[lab[k]], 1);
                 }
                 if (lmax1 - base <= (uint32_t)PV_BM_BITS) break;
                 base += PV_BM_BITS;
@@ -507,16 +508,15 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                 consumer_sync(THREADS);
             }
             pv_flush((int)cur, cnt, lane, hist);
-            const int tot = __reduce_add_sync(0xffffffffu, cnt);
-            if (lane == 0 && tot) atomicAdd(&hist[S2D_MAX_LABELS], tot);
         }
         consumer_sync(THREADS);                // S2: histogram complete
-        if (tid < S2D_MAX_LABELS + 1) {
+        if (tid < S2D_MAX_LABELS) {            // 8 warps: write hits, uniq = sum of the histogram
             const int h = hist[tid];
             const PvOut o = tout[it % 3];
             if (tid < o.L) o.hout[tid] = h;
-            if (tid == S2D_MAX_LABELS) *o.uout = h;
             hist[tid] = 0;
+            const int ws = __reduce_add_sync(0xffffffffu, h);
+            if (lane == 0 && ws) atomicAdd(o.uout, ws);        // *uout was cleared by the producer-side plan
         }
         if (lmax1 != 0) {
 #pragma unroll
