@@ -193,6 +193,17 @@ int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int nlab, int64_
 int s2d_rasterise_tracks(const float* tracks, int T, int P, int H, int W, uint8_t* planes,
                          void* stream);
 
+/* f1 (first "next" row of the scope table). Colour-coded mask frames -> per-frame label ids:
+ * label = 1 + rank of the pixel's (R,G,B) tuple among the frame's non-black colours in
+ * lexicographic order, 0 for black. Replaces load_masks / convert_lblimg_to_maskid
+ * (cotracker_occlusions.py:22-85, cotracker_matching.py:22-84, crw_utils.py:688-767).
+ * rgb: u8 [F][npix][3] (R,G,B), labels: u8 [F][npix], ncolors: i32 [F] = number of non-black colours
+ * (> 255: the frame does not fit u8 labels and its labels are undefined). work: u32 scratch of
+ * s2d_color_to_labels_work_ints(F) elements. */
+int s2d_color_to_labels_work_ints(int nframes, int64_t* out);
+int s2d_color_to_labels(const uint8_t* rgb, int nframes, int64_t npix, uint32_t* work, uint8_t* labels,
+                        int32_t* ncolors, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

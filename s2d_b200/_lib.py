@@ -54,6 +54,8 @@ SIGNATURES = {
     "s2d_overlap_i8": [_P, _I, _P, _I, _L, _P, _P],
     "s2d_overlap_gram_work_ints": [_I, _I, _L, C.POINTER(C.c_int64)],
     "s2d_overlap_gram_labels": [_P, _I, _I, _L, _P, _P, _P],
+    "s2d_color_to_labels_work_ints": [_I, C.POINTER(C.c_int64)],
+    "s2d_color_to_labels": [_P, _I, _L, _P, _P, _P, _P],
     "s2d_rasterise_tracks": [_P, _I, _I, _I, _I, _P, _P],
 }
 _RESTYPES = {"s2d_last_error": C.c_char_p}

@@ -132,3 +132,24 @@ def visibility_windows(V: np.ndarray, qframe, qlabel, visibility_threshold: floa
     b.run(Params(visibility_threshold=visibility_threshold))
     torch.cuda.synchronize(b.device)
     return b.decode(want_comps=False, check_rows=False)[0]["clusters"]
+
+
+def color_frames_to_labels(rgb_frames: np.ndarray):
+    """f1 on the GPU: [F,H,W,3] uint8 RGB frames -> ([F,H,W] uint8 label ids on the device, colours per
+    frame). Same ids as crw_utils.rgb_to_label_ids (rank of the RGB tuple among the non-black colours)."""
+    import ctypes as C
+    from s2d_b200 import _lib
+    F, H, W, _ = rgb_frames.shape
+    dev = device()
+    rgb = torch.from_numpy(np.ascontiguousarray(rgb_frames)).to(dev)
+    n = C.c_int64()
+    _lib.call("s2d_color_to_labels_work_ints", F, C.byref(n))
+    work = torch.empty(n.value, dtype=torch.int32, device=dev)
+    labels = torch.empty((F, H, W), dtype=torch.uint8, device=dev)
+    ncol = torch.empty(F, dtype=torch.int32, device=dev)
+    _lib.call("s2d_color_to_labels", rgb.data_ptr(), F, H * W, work.data_ptr(), labels.data_ptr(), ncol.data_ptr(),
+              torch.cuda.current_stream(dev).cuda_stream)
+    ncol_h = ncol.cpu().numpy()
+    if int(ncol_h.max()) > 255:
+        raise ValueError("s2d_b200 supports at most 255 masks per frame")
+    return labels, ncol_h

@@ -118,15 +118,23 @@ def load_masks(mask_folder: str):
     paths = sorted(glob.glob(os.path.join(mask_folder, "*.png")))
     if not paths:
         raise ValueError(f"No .png masks found in {mask_folder!r}")
-    maps = []
+    frames = []
     for p in paths:
         bgr = load_image_robust(p)
         if bgr is None:
             continue
-        maps.append(rgb_to_label_ids(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB))[..., None])
-    if not maps:
+        frames.append(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB))
+    if not frames:
         raise RuntimeError("No valid mask images could be read.")
-    return torch.from_numpy(np.stack(maps, axis=0))
+    if torch.cuda.is_available() and len({f.shape for f in frames}) == 1:
+        # colour -> id on the GPU (s2d_color_to_labels); the host only decodes the PNGs
+        try:
+            from . import _engine
+        except ImportError:
+            import _engine
+        labels, _ = _engine.color_frames_to_labels(np.stack(frames, axis=0))
+        return labels.cpu().to(torch.int64)[..., None]
+    return torch.from_numpy(np.stack([rgb_to_label_ids(f)[..., None] for f in frames], axis=0))
 
 
 def make_paths(folder_path, label_path, dataset_name="DAVIS"):

@@ -250,3 +250,27 @@ def test_gram_labels_tensor_core_vs_oracle(F, L, H, W):
     torch.cuda.synchronize()
     X = (labels.reshape(F, 1, -1) == np.arange(L, dtype=np.uint8)[None, :, None]).reshape(R, -1).astype(np.int64)
     assert np.array_equal(G.cpu().numpy().reshape(R, R), X @ X.T)
+
+
+def test_color_to_labels_vs_host_rule():
+    """f1: colour PNG frames -> label ids on the GPU == rank of the RGB tuple among the non-black colours."""
+    from s2d_b200.keymask_ident import _engine
+    from s2d_b200.keymask_ident.crw_utils import rgb_to_label_ids
+    rng = np.random.default_rng(4)
+    for (F, H, W, ncol, black) in [(3, 33, 47, 5, True), (2, 64, 96, 40, True), (2, 30, 50, 7, False), (1, 17, 19, 255, True)]:
+        pal = rng.integers(0, 256, size=(ncol, 3)).astype(np.uint8)
+        pal[pal.sum(1) == 0] = 1
+        if ncol >= 3:
+            pal[1] = pal[0]; pal[1, 2] ^= 1          # colours differing in the last channel only
+            pal[2] = pal[0]; pal[2, 0] ^= 128        # ... and in the first
+        idx = rng.integers(0, ncol, size=(F, H, W))
+        idx = np.repeat(np.repeat(idx[:, ::4, ::4], 4, axis=1), 4, axis=2)[:, :H, :W]   # piecewise constant
+        rgb = pal[idx]
+        if black:
+            rgb[:, : H // 3] = 0
+        labels, ncols = _engine.color_frames_to_labels(rgb)
+        got = labels.cpu().numpy()
+        for f in range(F):
+            ref = rgb_to_label_ids(rgb[f])
+            assert np.array_equal(got[f], ref.astype(np.uint8)), (F, H, W, ncol, f)
+            assert ncols[f] == len(np.unique(ref[ref > 0]))
