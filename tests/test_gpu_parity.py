@@ -274,3 +274,52 @@ def test_color_to_labels_vs_host_rule():
             ref = rgb_to_label_ids(rgb[f])
             assert np.array_equal(got[f], ref.astype(np.uint8)), (F, H, W, ncol, f)
             assert ncols[f] == len(np.unique(ref[ref > 0]))
+
+
+def test_c1_shape_full_pipeline_vs_oracle():
+    """BASELINE.json configs[0]: one 24-frame 480x854 video, 10 masks/frame, 1000 tracks per query -
+    the whole device pipeline against the CPU oracle (counts, windows, matches, groups bit-exact)."""
+    from s2d_b200.pipeline import Params, discover_keymasks
+    from s2d_b200.synth import make_scene
+    sc = make_scene(1234, T=24, H=480, W=854, M=10, P=1000, specials=True)
+    res = discover_keymasks([_video(sc.labels, sc.tracks, sc.vis, max_label=10)], Params())[0]
+    ref = ko.discover(sc.labels, sc.tracks, sc.vis)
+    assert res["status"] == ref["status"] == 1
+    assert np.array_equal(res["V"], ref["V"], equal_nan=True)
+    assert np.array_equal(res["labels1"], ref["labels1"])
+    assert json_eq(res["clusters"], ref["clusters"])
+    assert len(res["queries"]) == len(ref["queries"]) > 200
+    for a, b in zip(res["queries"], ref["queries"]):
+        assert (a["cluster_id"], a["frame_id"], a["mask_id"], a["one2x"]) == (b["cluster_id"], b["frame_id"], b["mask_id"], b["one2x"])
+        assert a["matches"] == b["matches"]
+        assert [c[:5] for c in a["comps"]] == [c[:5] for c in b["comps"]]
+    ga = [(g["cluster_id"], g["visibility_to_temporal_factor"], g["overall_mask_ids_per_label"]) for g in res["groupings"]]
+    gb = [(g["cluster_id"], g["visibility_to_temporal_factor"], g["overall_mask_ids_per_label"]) for g in ref["groupings"]]
+    assert ga == gb
+    assert res["video_coverage"] == ref["video_coverage"] and res["cluster_coverages"] == ref["cluster_coverages"]
+    assert res["one2x"] == ref["one2x"]
+
+
+def json_eq(a, b):
+    import json
+    return json.loads(json.dumps(a)) == json.loads(json.dumps(b))
+
+
+def test_query_permutation_and_batch_invariance():
+    """the result of a video does not depend on which other videos share its batch, and K2 does not
+    depend on the order of a query's points (property tests)."""
+    from s2d_b200.pipeline import Batch, Params, discover_keymasks
+    from s2d_b200.synth import make_scene
+    a = make_scene(77, T=10, H=72, W=96, M=4, P=96, specials=True)
+    b = make_scene(78, T=14, H=60, W=80, M=3, P=64)
+    alone = discover_keymasks([_video(a.labels, a.tracks, a.vis)], Params())[0]
+    both = discover_keymasks([_video(b.labels, b.tracks, b.vis), _video(a.labels, a.tracks, a.vis)], Params())[1]
+    assert alone["status"] == both["status"]
+    assert [q["matches"] for q in alone["queries"]] == [q["matches"] for q in both["queries"]]
+    assert json_eq(alone["groupings"], both["groupings"]) and json_eq(alone["clusters"], both["clusters"])
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(a.tracks.shape[2])
+    b1 = Batch([_video(a.labels, a.tracks, a.vis)]); b1.votes_all()
+    b2 = Batch([_video(a.labels, np.ascontiguousarray(a.tracks[:, :, perm]), np.ascontiguousarray(a.vis[:, :, perm]))]); b2.votes_all()
+    torch.cuda.synchronize()
+    assert torch.equal(b1.hits, b2.hits) and torch.equal(b1.uniq, b2.uniq)
