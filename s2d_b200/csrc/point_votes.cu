@@ -52,6 +52,15 @@ __device__ __forceinline__ uint32_t pv_claim(uint32_t* bm, uint32_t lin, uint32_
     const uint32_t old = atomicOr(&bm[w], bit);
     return bit & ~old;
 }
+// same with the bitmap given as a 32-bit shared-window address (no generic -> shared conversion)
+__device__ __forceinline__ uint32_t pv_claim_s(uint32_t bm_saddr, uint32_t lin, uint32_t base) {
+    const uint32_t kk = lin - base;
+    const uint32_t w4 = ((kk ^ (kk >> 5)) & (PV_BM_WORDS - 1)) << 2;
+    const uint32_t bit = shl_clamp(1u, kk >> PV_WORD_SHIFT);
+    uint32_t old;
+    asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(bm_saddr + w4), "r"(bit) : "memory");
+    return bit & ~old;
+}
 
 // expand the low 4 bits of m into a byte mask (bit i -> byte i = 0xFF)
 __device__ __forceinline__ uint32_t nib2bytes(uint32_t m) {
@@ -437,22 +446,21 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         const int n = tinfo[s].n;
         const uint8_t* lbl = tinfo[s].lbl;
         if (tid == 0) { tout[j % 3].hout = tinfo[s].hout; tout[j % 3].uout = tinfo[s].uout; tout[j % 3].L = tinfo[s].L; }
-        const float4* sp = reinterpret_cast<const float4*>(dsm + s * STAGE_BYTES);
+        // thread tid takes points tid, tid + THREADS, ...: the 32 lanes of a warp hold 32 consecutive
+        // points, i.e. (for grid-ordered tracks) neighbouring pixels -> few cache lines per label gather
+        const float2* sp = reinterpret_cast<const float2*>(dsm + s * STAGE_BYTES);
         if (n >= THREADS * PPT) {             // full tile: no per-point tail checks
 #pragma unroll
-            for (int i = 0; i < PPT / 2; ++i) {
-                const float4 v = sp[i * THREADS + tid];
-                lin_n[2 * i] = pv_lin(v.x, v.y, W, H);
-                lin_n[2 * i + 1] = pv_lin(v.z, v.w, W, H);
+            for (int k = 0; k < PPT; ++k) {
+                const float2 v = sp[k * THREADS + tid];
+                lin_n[k] = pv_lin(v.x, v.y, W, H);
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < PPT / 2; ++i) {
-                const int p0 = 2 * (i * THREADS + tid);
-                const float4 v = sp[i * THREADS + tid];
-                const uint32_t a = pv_lin(v.x, v.y, W, H), b = pv_lin(v.z, v.w, W, H);
-                lin_n[2 * i] = (p0 < n) ? a : PV_INVALID;
-                lin_n[2 * i + 1] = (p0 + 1 < n) ? b : PV_INVALID;
+            for (int k = 0; k < PPT; ++k) {
+                const float2 v = sp[k * THREADS + tid];
+                const uint32_t a = pv_lin(v.x, v.y, W, H);
+                lin_n[k] = (k * THREADS + tid < n) ? a : PV_INVALID;
             }
         }
         __syncwarp();
@@ -474,6 +482,7 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         return true;
     };
 
+    const uint32_t bm_s = (uint32_t)__cvta_generic_to_shared(bm);
     // stage B of tile `it`: de-duplicate, vote, write out, reset
     auto stage_b = [&](int it, const uint32_t (&lin)[PPT], const uint32_t (&lab)[PPT]) {
         consumer_sync(THREADS);                // S1: extents complete; previous tile's resets visible
@@ -489,7 +498,7 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                 uint32_t odd = 0;
 #pragma unroll
                 for (int k = 0; k < PPT; ++k) {
-                    const bool fst = pv_claim(bm, lin[k], base) != 0;
+                    const bool fst = pv_claim_s(bm_s, lin[k], base) != 0;
                     const bool same = lab[k] == cur;
                     cnt += (fst && same) ? 1 : 0;
                     odd |= (fst && !same) ? (1u << k) : 0u;
