@@ -52,6 +52,9 @@ typedef struct s2d_video_desc {
     const float*   tracks;  /* device, f32 [Nm][T][P][2]  CoTracker pred_tracks (x, y)        */
     const uint8_t* vis;     /* device, u8  [Nm][T][P]     CoTracker pred_visibility bytes     */
     const int32_t* npts;    /* device, i32 [Nm] valid points per query (<= P) or NULL = all P  */
+    const int32_t* tstart;  /* device, i32 [Nm] first frame stored in `tracks` per query, NULL = 0:  */
+    int32_t Ttr;            /* tracks is [Nm][Ttr][P][2]; Ttr == T unless only the window is stored */
+    int32_t pad0;           /* (long videos: SA-V-shaped configs keep Tw <= 64 frames per query)    */
     int64_t vt_off;      /* elements of [Nm][T] arrays                                       */
     int64_t hits_off;    /* int32 elements                                                   */
     int64_t xbits_off;   /* u32 words of [Nm][TW] arrays                                     */

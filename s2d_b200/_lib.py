@@ -24,6 +24,7 @@ class VideoDesc(C.Structure):
         ("Nm", C.c_int32), ("L", C.c_int32), ("TW", C.c_int32), ("NW", C.c_int32),
         ("row0", C.c_int64), ("frame0", C.c_int64),
         ("labels", C.c_void_p), ("tracks", C.c_void_p), ("vis", C.c_void_p), ("npts", C.c_void_p),
+        ("tstart", C.c_void_p), ("Ttr", C.c_int32), ("pad0", C.c_int32),
         ("vt_off", C.c_int64), ("hits_off", C.c_int64), ("xbits_off", C.c_int64), ("mbits_off", C.c_int64),
     ]
 

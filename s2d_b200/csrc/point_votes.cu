@@ -142,7 +142,10 @@ point_votes_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __re
     __shared__ uint32_t sbox[2];
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const float* tp = dp->tracks + rt * P * 2;
+    const int32_t* tsp = dp->tstart;
+    const int ts = t - (tsp ? tsp[q] : 0);                 // frame index inside the stored track window
+    if (ts < 0 || ts >= dp->Ttr) return;
+    const float* tp = dp->tracks + ((int64_t)q * dp->Ttr + ts) * P * 2;
     const uint8_t* lbl = dp->labels + (int64_t)t * (int64_t)(W * H);
 
     // ---- pass 1: all loads of the thread in flight at once, then round / bounds ----------
@@ -293,11 +296,17 @@ __global__ void pv_plan_rows_kernel(const s2d_video_desc* __restrict__ descs, in
     }
     const int T = descs[lo].T;
     int nt = T, t0 = 0;
+    const int32_t* tsp = descs[lo].tstart;
+    const int ts0 = tsp ? tsp[r - descs[lo].row0] : 0;     // frames [ts0, ts0 + Ttr) have tracks
     if (vidinfo && vidinfo[(int64_t)lo * S2D_VIDINFO_WORDS + 1] < 0) nt = 0;
     if (rowinfo) {
         const int4 ri = reinterpret_cast<const int4*>(rowinfo)[r];
         if (ri.y < 0) nt = 0;
         else { t0 = max(ri.z, 0); nt = nt ? max(min(ri.w, T - 1) - t0 + 1, 0) : 0; }
+    }
+    if (nt) {                                              // clip to the stored track window
+        const int a = max(t0, ts0), b = min(t0 + nt, ts0 + descs[lo].Ttr);
+        t0 = a; nt = max(b - a, 0);
     }
     rowplan[r] = make_int4(0, nt, t0, lo);
 }
@@ -425,7 +434,9 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                 tinfo[s] = ti;
                 const uint32_t bytes = (uint32_t)P * 8u;
                 mbar_expect_tx(&full[s], bytes);
-                bulk_g2s(dsm + s * STAGE_BYTES, dp->tracks + rt * P * 2, bytes, &full[s]);
+                const int32_t* tsp = dp->tstart;
+                const int64_t ts = t - (tsp ? tsp[q] : 0);           // frame index inside the stored track window
+                bulk_g2s(dsm + s * STAGE_BYTES, dp->tracks + ((int64_t)q * dp->Ttr + ts) * P * 2, bytes, &full[s]);
             }
             ++pi;
         }

@@ -28,6 +28,7 @@ class VideoInput:
     tracks: Optional[torch.Tensor] = None   # f32 [Nm,T,P,2]
     vis: Optional[torch.Tensor] = None      # u8/bool [Nm,T,P]
     npts: Optional[torch.Tensor] = None     # i32 [Nm]
+    tstart: Optional[torch.Tensor] = None   # i32 [Nm]: tracks hold frames [tstart[q], tstart[q] + tracks.shape[1]) only
     max_label: Optional[int] = None         # upper bound of the label ids (default 255)
     name: str = ""
     # stage-wise callers (the file-based drop-in modules) may omit tensors a stage does not read
@@ -79,7 +80,9 @@ class Batch:
                 dm["T"], dm["H"], dm["W"] = v.labels.shape
             if v.tracks is not None:
                 assert v.tracks.dtype == torch.float32 and v.tracks.is_contiguous() and v.tracks.dim() == 4
-                assert v.tracks.shape[3] == 2 and dm.setdefault("T", v.tracks.shape[1]) == v.tracks.shape[1]
+                assert v.tracks.shape[3] == 2
+                if v.tstart is None:
+                    assert dm.setdefault("T", v.tracks.shape[1]) == v.tracks.shape[1]
                 dm["Nm"], dm["P"] = v.tracks.shape[0], v.tracks.shape[2]
             if v.vis is not None:
                 assert v.vis.dtype in (torch.uint8, torch.bool) and v.vis.is_contiguous() and v.vis.dim() == 3
@@ -101,6 +104,8 @@ class Batch:
             d.tracks = v.tracks.data_ptr() if v.tracks is not None else None
             d.vis = v.vis.data_ptr() if v.vis is not None else None
             d.npts = v.npts.data_ptr() if v.npts is not None else None
+            d.tstart = v.tstart.data_ptr() if v.tstart is not None else None
+            d.Ttr = v.tracks.shape[1] if v.tracks is not None else T
             d.vt_off, d.hits_off, d.xbits_off, d.mbits_off = vt, hits, xw, mw
             if P % 2 or (v.tracks is not None and v.tracks.data_ptr() % 16):
                 self.vec4 = 0

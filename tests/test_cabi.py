@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_descriptor_layout_and_version():
     from s2d_b200 import _lib
     lib = _lib.load()
-    assert lib.s2d_desc_size() == C.sizeof(_lib.VideoDesc) == 112
+    assert lib.s2d_desc_size() == C.sizeof(_lib.VideoDesc) == 128
     assert lib.s2d_version() >= 100
     assert lib.s2d_last_error() is not None
 

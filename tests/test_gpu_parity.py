@@ -323,3 +323,36 @@ def test_query_permutation_and_batch_invariance():
     b2 = Batch([_video(a.labels, np.ascontiguousarray(a.tracks[:, :, perm]), np.ascontiguousarray(a.vis[:, :, perm]))]); b2.votes_all()
     torch.cuda.synchronize()
     assert torch.equal(b1.hits, b2.hits) and torch.equal(b1.uniq, b2.uniq)
+
+
+@pytest.mark.parametrize("P", [64, 6000])
+def test_windowed_track_storage(P):
+    """long-video layout: only the frames of a query's window are stored ([Nm][Tw][P][2] + tstart);
+    also exercises the P > 4096 kernel variant."""
+    from s2d_b200.pipeline import Batch, VideoInput
+    rng = np.random.default_rng(P)
+    T, H, W, Nm, Tw = 20, 50, 70, 9, 6
+    labels = rng.integers(0, 5, size=(T, H, W)).astype(np.uint8)
+    full = rng.uniform(-3, 75, size=(Nm, T, P, 2)).astype(np.float32)
+    v0 = rng.integers(0, T - Tw + 1, size=Nm)
+    v1 = v0 + rng.integers(0, Tw, size=Nm)
+    win = np.stack([full[q, v0[q]:v0[q] + Tw] for q in range(Nm)])
+    d = _dev()
+    vid = VideoInput(labels=torch.from_numpy(labels).to(d), tracks=torch.from_numpy(np.ascontiguousarray(win)).to(d),
+                     tstart=torch.from_numpy(v0.astype(np.int32)).to(d), max_label=4)
+    b = Batch([vid], stages="LD")
+    rowinfo = np.stack([np.zeros(Nm), np.zeros(Nm), v0, v1], axis=1).astype(np.int32)
+    rowinfo[3, 1] = -1                                   # not a candidate: untouched
+    b.upload_stage_b(rowinfo, 1, 1)
+    b.hits.fill_(-5); b.uniq.fill_(-5)
+    b.run()
+    torch.cuda.synchronize()
+    hits = b.hits.cpu().numpy().reshape(Nm, T, 5)
+    uniq = b.uniq.cpu().numpy().reshape(Nm, T)
+    for q in range(Nm):
+        inside = np.zeros(T, bool)
+        if q != 3:
+            inside[v0[q]:v1[q] + 1] = True
+            h, u = ko.point_votes(full[q], labels, int(v0[q]), int(v1[q]), nbins=5)
+            assert np.array_equal(uniq[q, inside], u) and np.array_equal(hits[q, inside], h), q
+        assert (uniq[q, ~inside] == -5).all() and (hits[q, ~inside] == -5).all(), q
