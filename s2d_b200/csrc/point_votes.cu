@@ -344,7 +344,7 @@ __device__ __forceinline__ void consumer_sync(int nthreads) {   // named barrier
 
 // THREADS consumer threads + one producer warp (the last warp of the CTA)
 template <int THREADS, int PPT>
-__global__ void __launch_bounds__(THREADS + 32, (THREADS * PPT <= 4096) ? 2 : 1)
+__global__ void __launch_bounds__(THREADS + 32, (THREADS * PPT <= 1024) ? 4 : ((THREADS * PPT <= 4096) ? 2 : 1))
 point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __restrict__ rowplan,
                        int total_rows, int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
                        int32_t* __restrict__ uniq) {
@@ -357,7 +357,7 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     __shared__ __align__(8) uint64_t empty[2];
     __shared__ PvTile tinfo[2];
     __shared__ PvOut tout[3];
-    static_assert(THREADS >= S2D_MAX_LABELS + 1, "output phase uses one thread per histogram bin");
+    static_assert(THREADS >= S2D_MAX_LABELS, "output phase uses one thread per histogram bin");
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int total = ctrl[1];
@@ -620,7 +620,7 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
         pv_scan_kernel<<<1, 1024, 0, st>>>(rowplan, total_rows, ctrl);
         S2D_CHECK_LAUNCH("pv_scan_kernel");
         const int tr = (int)total_rows;
-        if (max_P <= 512 * 2) return launch_pv_tma<512, 2>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+        if (max_P <= 256 * 4) return launch_pv_tma<256, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);   // 4 CTAs/SM
         if (max_P <= 512 * 4) return launch_pv_tma<512, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
         if (max_P <= 4096) {
             return launch_pv_tma<512, 8>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
