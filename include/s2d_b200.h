@@ -132,9 +132,14 @@ int s2d_windows(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_TW,
  * rowinfo == NULL votes every (q,t); vidinfo == NULL ignores the stage-B status.
  * vec4_ok != 0 promises P even and 16-byte aligned tracks for every video (128-bit loads).
  * work: int32 scratch of s2d_point_votes_work_ints(total_rows) elements, 16-byte aligned; with it
- * (and vec4_ok, P <= 8192) the persistent TMA-fed kernel runs: a device-side plan lists the
- * (row, frame) tiles, 2 CTAs per SM stream them through a two-stage cp.async.bulk ring. Without
- * it (work == NULL) the one-CTA-per-tile kernel runs. H, W <= 65535; P <= 32768. */
+ * (and vec4_ok, P <= 8192) a persistent kernel runs: a device-side plan lists the (row, frame)
+ * tiles and 2-4 CTAs per SM stream them through cp.async.bulk. Variant 0 (default) pulls the
+ * tile's bounding box of the label map into shared memory and resolves de-duplication and label
+ * lookup with one shared-memory atomic per point; variant 1 de-duplicates in a shared bitmap and
+ * gathers labels from global memory; variant 2 (also used when work == NULL or the promises above
+ * do not hold) is the one-CTA-per-tile kernel. All variants give identical results.
+ * H, W <= 65535; P <= 32768. */
+int s2d_point_votes_variant(int variant);   /* process-wide; 0 label table, 1 bitmap, 2 CTA per tile */
 int s2d_point_votes_work_ints(int64_t total_rows, int64_t* out);
 int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max_T, int max_Nm, int max_P,
                     int vec4_ok, int64_t total_rows, const int32_t* rowinfo, const int32_t* vidinfo,

@@ -44,6 +44,7 @@ SIGNATURES = {
     "s2d_dbscan_work_ints": [_L, _I, C.POINTER(C.c_int64)],
     "s2d_dbscan_visibility": [_P, _I, _I, _I, _L, _P, _D, _I, _P, _P, _P, _P],
     "s2d_windows": [_P, _I, _L, _I, _L, _L, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "s2d_point_votes_variant": [_I],
     "s2d_point_votes_work_ints": [_L, C.POINTER(C.c_int64)],
     "s2d_point_votes": [_P, _I, _I, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P],
     "s2d_select": [_P, _I, _I, _L, _P, _P, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P],

@@ -557,6 +557,332 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     }
 }
 
+// ==========================================================================================
+// Label-table variant: ONE shared-memory atomic per point does both the de-duplication and the
+// label lookup (the production path when it applies: even P, 16-byte aligned tracks, P <= 8192).
+//
+// Per tile the consumers round the points (phase A), reduce their bounding box, and pull exactly
+// that region of the target frame's u8 label map into shared memory - one cp.async.bulk per bbox
+// row, issued by as many threads in parallel, completion on one mbarrier. Rows keep their global
+// 16-byte phase: the row pitch is chosen congruent to W modulo 16, so pixel (x, y) always sits at
+// (y - y0) * pitch + (x - x0) + const and unaligned widths (W = 854) cost nothing extra. Phase B
+// then claims each point's pixel with atomicOr(word, 0xFF << 8*(offset & 3)): the returned byte is
+// the pixel's label if this point is the first on the pixel, 0xFF if the pixel was already taken.
+// No bitmap, no zeroing (the next tile's copy overwrites the table), no global gather.
+// Bounding boxes taller than the table are processed in bands of rows. Tiles the table cannot
+// serve (label id 255 in use, or a bbox that would need more than PV_MAX_BANDS bands) fall back,
+// inside the same kernel, to the bitmap + global-gather method with the table memory as bitmap.
+// One producer warp per CTA plans tiles and prefetches the next tile's tracks (single stage,
+// cp.async.bulk) while the current tile is processed; several CTAs per SM overlap the phases.
+// ==========================================================================================
+constexpr int PV_MAX_BANDS = 6;
+constexpr uint32_t PV_PK_INVALID = 0xFFFFFFFFu;
+
+__host__ __device__ constexpr int pv_tab_bytes(int threads, int ppt, int ctas) {
+    // 228 KB per SM, 1 KB reserved per CTA, ~1.5 KB static shared memory, 64 B slack behind the table
+    return ((233472 / ctas - 1024 - 1536 - threads * ppt * 8 - 64) / 128) * 128;
+}
+
+// (iy << 16 | ix) of a point that lands inside the frame, PV_PK_INVALID otherwise (W, H <= 65535)
+__device__ __forceinline__ uint32_t pv_pack(float x, float y, uint32_t W, uint32_t H) {
+    const uint32_t ix = (uint32_t)__float2int_rn(fmaxf(x, -1.0f));
+    const uint32_t iy = (uint32_t)__float2int_rn(fmaxf(y, -1.0f));
+    return (ix < W && iy < H) ? (iy << 16) + ix : PV_PK_INVALID;
+}
+
+__device__ __forceinline__ void bulk_g2s_addr(uint32_t smem_dst, uint64_t gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int THREADS, int PPT, int CTAS>
+__global__ void __launch_bounds__(THREADS + 32, CTAS)
+point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __restrict__ rowplan,
+                       int total_rows, int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
+                       int32_t* __restrict__ uniq) {
+    constexpr int STAGE_BYTES = THREADS * PPT * 8;
+    constexpr int TAB_BYTES = pv_tab_bytes(THREADS, PPT, CTAS);
+    constexpr int NWARPS = THREADS / 32;
+    static_assert(TAB_BYTES >= PV_BM_WORDS * 4, "the fallback bitmap lives in the table");
+    static_assert(THREADS >= S2D_MAX_LABELS, "output phase uses one thread per histogram bin");
+    static_assert(PPT % 2 == 0, "points are read two at a time");
+    extern __shared__ __align__(128) uint8_t dsm[];
+    uint8_t* tab = dsm + STAGE_BYTES;
+    __shared__ int hist[S2D_MAX_LABELS];
+    __shared__ __align__(8) uint2 wred[NWARPS];        // per-warp packed (min, max + 1) of (iy, ix)
+    __shared__ uint32_t dummy[32];                     // all ones: target of points outside the band
+    __shared__ __align__(8) uint64_t full, empty, tabbar;
+    __shared__ PvTile tinfo[2];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int total = ctrl[1];
+
+    if (tid < THREADS)
+        for (int i = tid; i < S2D_MAX_LABELS; i += THREADS) hist[i] = 0;
+    if (tid < 32) dummy[tid] = 0xFFFFFFFFu;
+    if (tid == 0) {
+        mbar_init(&full, 1);
+        mbar_init(&empty, NWARPS);
+        mbar_init(&tabbar, THREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= THREADS) {
+        // =========================== producer warp ===========================================
+        int pi = 0, pi_end = 0, prow = 0;          // next tile index, end of claimed chunk, its row
+        int4 prp = make_int4(0, 0, 0, 0);          // rowplan[prow]
+        for (int j = 0;; ++j) {
+            const int s = j & 1;
+            if (j >= 1) mbar_wait(&empty, (j - 1) & 1);    // tile j-1 is in registers: stage and tinfo[s] are free
+            bool done = false;
+            if (pi == pi_end) {
+                int c = 0;
+                if (lane == 0) c = atomicAdd(&ctrl[0], PV_CHUNK);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= total) {
+                    done = true;
+                } else {
+                    pi = c;
+                    pi_end = min(c + PV_CHUNK, total);
+                    int lo = 0, hi = total_rows;     // 32-ary search: last row with tile0 <= pi
+                    while (hi - lo > 32) {
+                        const int step = (hi - lo + 31) >> 5;
+                        const int probe = lo + lane * step;
+                        const bool ok = probe < hi && rowplan[probe].x <= pi;
+                        const uint32_t b = __ballot_sync(0xffffffffu, ok);
+                        const int k = 31 - __clz(b);
+                        lo += k * step;
+                        hi = min(hi, lo + step);
+                    }
+                    const int probe = lo + lane;
+                    const bool ok = probe < hi && rowplan[probe].x <= pi;
+                    const uint32_t b = __ballot_sync(0xffffffffu, ok);
+                    prow = lo + 31 - __clz(b);
+                    prp = rowplan[prow];
+                }
+            }
+            if (done) {
+                if (lane == 0) { tinfo[s].valid = 0; mbar_arrive(&full); }
+                break;
+            }
+            while (pi >= prp.x + prp.y) { ++prow; prp = rowplan[prow]; }   // rows without tiles are skipped
+            if (lane == 0) {
+                const s2d_video_desc* dp = descs + prp.w;
+                const int q = prow - (int)dp->row0;
+                const int t = prp.z + (pi - prp.x);
+                const int P = dp->P, T = dp->T, L = dp->L;
+                const int64_t rt = (int64_t)q * T + t;
+                PvTile ti;
+                ti.lbl = dp->labels + (int64_t)t * dp->H * dp->W;
+                ti.hout = hits + dp->hits_off + rt * L;
+                ti.uout = uniq + dp->vt_off + rt;
+                *ti.uout = 0;        // consumers accumulate per-warp partial sums (ordered by the mbarrier release/acquire)
+                ti.W = dp->W; ti.H = dp->H; ti.L = L;
+                const int32_t* np = dp->npts;
+                ti.n = np ? min(max(np[q], 0), P) : P;
+                ti.valid = 1; ti.pad = 0;
+                tinfo[s] = ti;
+                const uint32_t bytes = (uint32_t)P * 8u;
+                mbar_expect_tx(&full, bytes);
+                const int32_t* tsp = dp->tstart;
+                const int64_t ts = t - (tsp ? tsp[q] : 0);           // frame index inside the stored track window
+                bulk_g2s(dsm, dp->tracks + ((int64_t)q * dp->Ttr + ts) * P * 2, bytes, &full);
+            }
+            ++pi;
+        }
+        return;
+    }
+
+    // =============================== consumer warps ==========================================
+    const int warp = tid >> 5;
+    const uint32_t tab_s = smem_u32(tab);
+    const uint32_t dummy_s = smem_u32(&dummy[lane]);
+    uint32_t tabphase = 0;
+    for (int j = 0;; ++j) {
+        const PvTile* ti = &tinfo[j & 1];
+        mbar_wait(&full, j & 1);
+        if (!ti->valid) break;
+        const uint32_t W = ti->W, H = ti->H;
+        if (W > 65535u || H > 65535u) __trap();      // packed 16-bit coordinates (documented limit)
+        const int n = ti->n;
+
+        // ---- phase A: stage -> registers, round / bounds / pack, bounding box -----------------
+        uint32_t pk[PPT];
+        uint32_t mn = 0xFFFFFFFFu, mx = 0;
+        const float4* sp = reinterpret_cast<const float4*>(dsm);
+        if (n >= THREADS * PPT) {
+#pragma unroll
+            for (int k = 0; k < PPT / 2; ++k) {
+                const float4 v = sp[k * THREADS + tid];
+                pk[2 * k] = pv_pack(v.x, v.y, W, H);
+                pk[2 * k + 1] = pv_pack(v.z, v.w, W, H);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < PPT / 2; ++k) {
+                const float4 v = sp[k * THREADS + tid];
+                const int p0 = 2 * (k * THREADS + tid);
+                const uint32_t a = pv_pack(v.x, v.y, W, H), b = pv_pack(v.z, v.w, W, H);
+                pk[2 * k] = (p0 < n) ? a : PV_PK_INVALID;
+                pk[2 * k + 1] = (p0 + 1 < n) ? b : PV_PK_INVALID;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty);           // this warp no longer reads the stage
+#pragma unroll
+        for (int k = 0; k < PPT / 2; ++k) {
+            // per-halfword min / max; an invalid point is (0xFFFF, 0xFFFF) for the min and, after the
+            // +0x00010001, (1, 0) for the max: harmless, any valid point has iy + 1 >= 1
+            mn = __vimin3_u16x2(mn, pk[2 * k], pk[2 * k + 1]);
+            mx = __vimax3_u16x2(mx, pk[2 * k] + 0x00010001u, pk[2 * k + 1] + 0x00010001u);
+        }
+        {
+            const uint32_t mnx = __reduce_min_sync(0xffffffffu, mn & 0xFFFFu), mny = __reduce_min_sync(0xffffffffu, mn >> 16);
+            const uint32_t mxx = __reduce_max_sync(0xffffffffu, mx & 0xFFFFu), mxy = __reduce_max_sync(0xffffffffu, mx >> 16);
+            if (lane == 0) wred[warp] = make_uint2((mny << 16) | mnx, (mxy << 16) | mxx);
+        }
+        consumer_sync(THREADS);                       // S1: per-warp boxes complete; previous tile fully retired
+        uint32_t bmn = 0xFFFFFFFFu, bmx = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) {
+            const uint2 v = wred[w];
+            bmn = __vminu2(bmn, v.x);
+            bmx = __vmaxu2(bmx, v.y);
+        }
+        const int L = ti->L;
+        if (bmn != 0xFFFFFFFFu) {                     // at least one point inside the frame
+            const uint32_t x0 = bmn & 0xFFFFu, y0 = bmn >> 16;
+            const uint32_t bw = (bmx & 0xFFFFu) - x0, bh = (bmx >> 16) - y0;      // max holds coordinate + 1
+            uint32_t pitch = bw + 15u;
+            pitch += (W - pitch) & 15u;               // pitch = W (mod 16), pitch >= bw + 15
+            const uint32_t R = (uint32_t)TAB_BYTES / pitch;                       // rows per band
+            const uint8_t* lbl = ti->lbl;
+            if (L <= 255 && R * PV_MAX_BANDS >= bh) {
+                // ---- table mode ---------------------------------------------------------------
+                for (uint32_t b0 = 0; b0 < bh; b0 += R) {
+                    const uint32_t rows = min(R, bh - b0);
+                    const uint64_t A = (uint64_t)(uintptr_t)lbl + (uint64_t)(y0 + b0) * W + x0;
+                    const uint32_t a15 = (uint32_t)A & 15u;
+                    uint32_t bytes = 0;
+                    for (uint32_t r = tid; r < rows; r += THREADS) {
+                        const uint32_t ph = (uint32_t)(A + (uint64_t)r * W) & 15u;
+                        bytes += (ph + bw + 15u) & ~15u;
+                    }
+                    mbar_expect_tx(&tabbar, bytes);                                // one arrival per consumer thread
+                    for (uint32_t r = tid; r < rows; r += THREADS) {
+                        const uint64_t g = A + (uint64_t)r * W;
+                        const uint32_t ph = (uint32_t)g & 15u;
+                        bulk_g2s_addr(tab_s + r * pitch + a15 - ph, g - ph, (ph + bw + 15u) & ~15u, &tabbar);
+                    }
+                    mbar_wait(&tabbar, tabphase);
+                    tabphase ^= 1u;
+
+                    // phase B: e = (dy << 16) + dx for points of this band, >= lim otherwise (rows above
+                    // wrap around, rows below and PV_PK_INVALID keep a high half >= rows: y0 + b0 + rows <= H)
+                    const uint32_t pk0 = ((y0 + b0) << 16) + x0;
+                    const uint32_t tabc = tab_s + a15;
+                    const uint32_t lim = rows << 16;
+                    const uint32_t negc = pitch - 65536u;
+                    // Groups of G points: all G atomics are issued before the first result is used.
+                    // Points outside the band (and invalid ones) hit a per-lane dummy word that is all
+                    // ones, so they read back 0xFF = "not first" without a branch. First points that
+                    // carry the warp's reference label `cur` are counted in a register; the rest
+                    // (object borders, other masks) vote one by one.
+                    constexpr int G = PPT < 8 ? PPT : 8;
+                    uint32_t cur = 0x100u;             // warp-uniform reference label, chosen in group 0
+                    int cnt = 0;
+#pragma unroll
+                    for (int g = 0; g < PPT; g += G) {
+                        uint32_t old[G], sh[G];
+#pragma unroll
+                        for (int k = 0; k < G; ++k) {
+                            const uint32_t e = pk[g + k] - pk0;
+                            const uint32_t off = (e >> 16) * negc + e + tabc;      // table + dy * pitch + dx + a15
+                            sh[k] = (off << 3) & 24u;
+                            const uint32_t addr = (e < lim) ? (off & ~3u) : dummy_s;
+                            asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old[k]) : "r"(addr), "r"(0xFFu << sh[k]));
+                        }
+                        if (g == 0) {
+                            const uint32_t l0 = (old[0] >> sh[0]) & 0xFFu;
+                            const uint32_t have = __ballot_sync(0xffffffffu, l0 != 0xFFu);
+                            const uint32_t lsel = __shfl_sync(0xffffffffu, l0, have ? __ffs(have) - 1 : 0);
+                            cur = have ? lsel : 0x100u;
+                        }
+                        uint32_t odd = 0;
+#pragma unroll
+                        for (int k = 0; k < G; ++k) {
+                            const uint32_t lab = (old[k] >> sh[k]) & 0xFFu;        // 0xFF: not first / not in band
+                            cnt += (lab == cur) ? 1 : 0;
+                            odd |= (lab != cur && lab != 0xFFu) ? (1u << k) : 0u;
+                        }
+                        if (odd) {
+#pragma unroll
+                            for (int k = 0; k < G; ++k)
+                                if ((odd >> k) & 1u) atomicAdd(&hist[(old[k] >> sh[k]) & 0xFFu], 1);
+                        }
+                    }
+                    if (cur != 0x100u) {               // warp-uniform label: one reduction, one atomic
+                        const int ws = __reduce_add_sync(0xffffffffu, cnt);
+                        if (lane == 0 && ws) atomicAdd(&hist[cur], ws);
+                    }
+                    if (b0 + R < bh) {                 // the next band's copies overwrite the table
+                        fence_proxy_async();
+                        consumer_sync(THREADS);
+                    }
+                }
+            } else {
+                // ---- fallback: bitmap in the table memory + global label gather ----------------
+                uint32_t* bm = reinterpret_cast<uint32_t*>(tab);
+                const uint32_t lend = (y0 + bh - 1u) * W + x0 + bw;            // last pixel + 1
+                for (uint32_t base = y0 * W + x0;; base += PV_BM_BITS) {
+                    for (int i = tid; i < PV_BM_WORDS / 4; i += THREADS)
+                        reinterpret_cast<uint4*>(bm)[i] = make_uint4(0, 0, 0, 0);
+                    consumer_sync(THREADS);
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) {
+                        const uint32_t p = pk[k];
+                        const uint32_t lin = (p == PV_PK_INVALID) ? PV_INVALID : (p >> 16) * W + (p & 0xFFFFu);
+                        if (pv_claim_s(tab_s, lin, base)) atomicAdd(&hist[__ldg(lbl + lin)], 1);
+                    }
+                    if (lend - base <= (uint32_t)PV_BM_BITS) break;
+                    consumer_sync(THREADS);
+                }
+            }
+        }
+        fence_proxy_async();                          // table atomics before the next tile's bulk copies
+        consumer_sync(THREADS);                       // S2: histogram complete
+        if (tid < S2D_MAX_LABELS) {                   // 8 warps: write hits, uniq = sum of the histogram
+            const int h = hist[tid];
+            if (tid < L) ti->hout[tid] = h;
+            hist[tid] = 0;
+            const int ws = __reduce_add_sync(0xffffffffu, h);
+            if (lane == 0 && ws) atomicAdd(ti->uout, ws);      // *uout was cleared by the producer
+        }
+        // the next tile's S1 orders these resets before its histogram atomics
+    }
+}
+
+template <int THREADS, int PPT, int CTAS>
+static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, const int4* rowplan,
+                         int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq) {
+    const int smem = THREADS * PPT * 8 + pv_tab_bytes(THREADS, PPT, CTAS) + 64;
+    auto kfn = point_votes_tab_kernel<THREADS, PPT, CTAS>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { set_error("point_votes_tab_kernel: cannot opt in to %d B of shared memory: %s", smem, cudaGetErrorString(e)); return -2; }
+        configured = true;
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, THREADS + 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    kfn<<<nsm * per_sm, THREADS + 32, smem, st>>>(descs, rowplan, total_rows, ctrl, hits, uniq);
+    S2D_CHECK_LAUNCH("point_votes_tab_kernel");
+    return 0;
+}
+
 template <int THREADS, int PPT>
 static int launch_pv_tma(cudaStream_t st, int nsm, const s2d_video_desc* descs, const int4* rowplan,
                          int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq) {
@@ -591,6 +917,14 @@ static int launch_pv(bool vec4, dim3 grid, cudaStream_t st, const s2d_video_desc
 
 using namespace s2d;
 
+static int g_pv_variant = 0;
+
+extern "C" int s2d_point_votes_variant(int variant) {
+    S2D_CHECK_ARG(variant >= 0 && variant <= 2, "s2d_point_votes_variant: %d not in {0 label table, 1 bitmap, 2 one CTA per tile}", variant);
+    g_pv_variant = variant;
+    return 0;
+}
+
 extern "C" int s2d_point_votes_work_ints(int64_t total_rows, int64_t* out) {
     if (!out) return -1;
     *out = 4 * total_rows + 8;
@@ -607,7 +941,8 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
     S2D_CHECK_ARG(max_P >= 1 && max_P <= 32768, "s2d_point_votes: P=%d not in [1, 32768]", max_P);
     cudaStream_t st = (cudaStream_t)stream;
     const bool v4 = vec4_ok != 0;
-    if (v4 && work && max_P <= 8192 && total_rows > 0 && total_rows <= 2147483647LL) {
+    const int variant = g_pv_variant;
+    if (variant != 2 && v4 && work && max_P <= 8192 && total_rows > 0 && total_rows <= 2147483647LL) {
         // persistent TMA path
         S2D_CHECK_ARG((((uintptr_t)work) & 15) == 0, "s2d_point_votes: work must be 16-byte aligned");
         int dev = 0, nsm = 148;
@@ -620,6 +955,12 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
         pv_scan_kernel<<<1, 1024, 0, st>>>(rowplan, total_rows, ctrl);
         S2D_CHECK_LAUNCH("pv_scan_kernel");
         const int tr = (int)total_rows;
+        if (variant == 0) {      // label-table kernels
+            if (max_P <= 256 * 4) return launch_pv_tab<256, 4, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+            if (max_P <= 256 * 8) return launch_pv_tab<256, 8, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+            if (max_P <= 256 * 16) return launch_pv_tab<256, 16, 3>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+            return launch_pv_tab<256, 32, 2>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+        }
         if (max_P <= 256 * 4) return launch_pv_tma<256, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);   // 4 CTAs/SM
         if (max_P <= 512 * 4) return launch_pv_tma<512, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
         if (max_P <= 4096) {

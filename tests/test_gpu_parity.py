@@ -61,8 +61,17 @@ def test_point_votes_all_pairs_vs_oracle(golden_case):
         assert np.array_equal(h, hits[q]), (name, q)
 
 
+@pytest.fixture(params=[0, 1, 2], ids=["table", "bitmap", "cta_per_tile"])
+def pv_variant(request):
+    """run a test once per point-votes kernel variant (include/s2d_b200.h: s2d_point_votes_variant)"""
+    from s2d_b200 import _lib
+    _lib.call("s2d_point_votes_variant", request.param)
+    yield request.param
+    _lib.call("s2d_point_votes_variant", 0)
+
+
 @pytest.mark.parametrize("P,H,W", [(1000, 480, 854), (4096, 720, 1280), (777, 33, 1900), (8192, 1080, 1920), (20000, 64, 64)])
-def test_point_votes_shapes_and_bands(P, H, W):
+def test_point_votes_shapes_and_bands(P, H, W, pv_variant):
     """odd P (no 128-bit path), P above the register tile, bounding boxes that need several
     bitmap bands (points spread over the whole 1080p frame), heavy duplication (P >> H*W)."""
     from s2d_b200.pipeline import Batch
@@ -94,7 +103,43 @@ def test_point_votes_shapes_and_bands(P, H, W):
     assert np.array_equal(b.V.cpu().numpy().reshape(Nm, T), ko.visibility_mean(vis))
 
 
-def test_ragged_npts():
+@pytest.mark.parametrize("H,W,P,M,lab255", [(480, 854, 1000, 10, False), (720, 1280, 4096, 20, False),
+                                            (1080, 1920, 2048, 6, False), (97, 131, 512, 5, True),
+                                            (480, 854, 4096, 20, True)])
+def test_point_votes_scene_geometry(H, W, P, M, lab255, pv_variant):
+    """Object-shaped point clouds (compact bounding boxes: the label-table kernel's main path, one
+    or several bands), widths that are not a multiple of 16, a label map that does not start on a
+    16-byte boundary, and label id 255 in use (the table kernel must take its bitmap fallback)."""
+    from s2d_b200.pipeline import Batch, VideoInput
+    from s2d_b200.synth import make_scene
+    sc = make_scene(31 + H, 5, H, W, M, P, specials=True, dup_rate=0.05)
+    labels = sc.labels.copy()
+    maxlab = int(labels.max())
+    if lab255:
+        labels[labels == maxlab] = 255
+        maxlab = 255
+    d = _dev()
+    raw = torch.zeros(labels.size + 64, dtype=torch.uint8, device=d)
+    off = 5                                                    # misaligned label map
+    raw[off:off + labels.size] = torch.from_numpy(labels.reshape(-1)).to(d)
+    lab_dev = raw[off:off + labels.size].view(labels.shape)
+    vid = VideoInput(labels=lab_dev, tracks=torch.from_numpy(sc.tracks).to(d), vis=torch.from_numpy(sc.vis).to(d),
+                     max_label=maxlab)
+    b = Batch([vid])
+    b.hits.fill_(-3); b.uniq.fill_(-3)
+    b.votes_all()
+    torch.cuda.synchronize()
+    Nm, T = sc.tracks.shape[:2]
+    L = maxlab + 1
+    hits = b.hits.cpu().numpy().reshape(Nm, T, L)
+    uniq = b.uniq.cpu().numpy().reshape(Nm, T)
+    for q in range(Nm):
+        h, u = ko.point_votes(sc.tracks[q], labels, 0, T - 1, nbins=L)
+        assert np.array_equal(u, uniq[q]), (q, u, uniq[q])
+        assert np.array_equal(h, hits[q]), q
+
+
+def test_ragged_npts(pv_variant):
     from s2d_b200.pipeline import Batch
     rng = np.random.default_rng(5)
     T, Nm, P, H, W = 4, 6, 512, 90, 120
