@@ -273,10 +273,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: park instead of spinning
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -561,26 +561,30 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
 // Label-table variant: ONE shared-memory atomic per point does both the de-duplication and the
 // label lookup (the production path when it applies: even P, 16-byte aligned tracks, P <= 8192).
 //
-// Per tile the consumers round the points (phase A), reduce their bounding box, and pull exactly
-// that region of the target frame's u8 label map into shared memory - one cp.async.bulk per bbox
-// row, issued by as many threads in parallel, completion on one mbarrier. Rows keep their global
-// 16-byte phase: the row pitch is chosen congruent to W modulo 16, so pixel (x, y) always sits at
-// (y - y0) * pitch + (x - x0) + const and unaligned widths (W = 854) cost nothing extra. Phase B
-// then claims each point's pixel with atomicOr(word, 0xFF << 8*(offset & 3)): the returned byte is
-// the pixel's label if this point is the first on the pixel, 0xFF if the pixel was already taken.
-// No bitmap, no zeroing (the next tile's copy overwrites the table), no global gather.
-// Bounding boxes taller than the table are processed in bands of rows. Tiles the table cannot
-// serve (label id 255 in use, or a bbox that would need more than PV_MAX_BANDS bands) fall back,
-// inside the same kernel, to the bitmap + global-gather method with the table memory as bitmap.
-// One producer warp per CTA plans tiles and prefetches the next tile's tracks (single stage,
-// cp.async.bulk) while the current tile is processed; several CTAs per SM overlap the phases.
+// A tile lives in ONE shared-memory buffer that is first the landing zone of its 8P bytes of
+// tracks (cp.async.bulk) and then, once the points are rounded into registers (phase A) and their
+// bounding box is known, the table: exactly that region of the target frame's u8 label map, one
+// cp.async.bulk per bbox row issued by as many threads in parallel, completion on one mbarrier.
+// Rows keep their global 16-byte phase: the row pitch is chosen congruent to W modulo 16, so pixel
+// (x, y) always sits at (y - y0) * pitch + (x - x0) + const and unaligned widths (W = 854) cost
+// nothing extra. Phase B claims each point's pixel with atomicOr(word, 0xFF << 8*(offset & 3)):
+// the returned byte is the pixel's label if this point is the first on the pixel, 0xFF if the
+// pixel was already taken. No bitmap, no zeroing (the next copy overwrites the buffer), no global
+// gather. Bounding boxes taller than the buffer are processed in bands of rows. Tiles the table
+// cannot serve (label id 255 in use, or a bbox that would need more than PV_MAX_BANDS bands) fall
+// back, inside the same kernel, to the bitmap + global-gather method with the buffer as bitmap.
+// Nothing overlaps inside a CTA - the chain tracks -> bbox -> table -> votes is serial by nature -
+// so the buffer is kept small enough for 4-5 CTAs per SM, which overlap each other's waits.
+// Warp 0 also plans: it claims chunks of tiles and prepares the next tile's record while the
+// CTA waits for its table.
 // ==========================================================================================
 constexpr int PV_MAX_BANDS = 6;
 constexpr uint32_t PV_PK_INVALID = 0xFFFFFFFFu;
 
-__host__ __device__ constexpr int pv_tab_bytes(int threads, int ppt, int ctas) {
+__host__ __device__ constexpr int pv_buf_bytes(int threads, int ppt, int ctas) {
     // 228 KB per SM, 1 KB reserved per CTA, ~1.5 KB static shared memory, 64 B slack behind the table
-    return ((233472 / ctas - 1024 - 1536 - threads * ppt * 8 - 64) / 128) * 128;
+    const int cap = ((233472 / ctas - 1024 - 1536 - 64) / 128) * 128;
+    return cap < threads * ppt * 8 ? threads * ppt * 8 : cap;
 }
 
 // (iy << 16 | ix) of a point that lands inside the frame, PV_PK_INVALID otherwise (W, H <= 65535)
@@ -596,122 +600,136 @@ __device__ __forceinline__ void bulk_g2s_addr(uint32_t smem_dst, uint64_t gsrc, 
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+struct PvPlan {              // warp-0 state of the tile scheduler (identical in all its lanes)
+    int pi, pi_end, prow;    // next tile index, end of the claimed chunk, row of tile pi
+    int4 prp;                // rowplan[prow]
+};
+
+// Claim / locate the next tile (warp 0, all lanes) and let lane 0 write its record. Returns false
+// when the work list is exhausted (the record is then marked invalid).
+__device__ __forceinline__ bool pv_plan_next(PvPlan& pl, PvTile* rec, int lane, const s2d_video_desc* __restrict__ descs,
+                                             const int4* __restrict__ rowplan, int total_rows, int total,
+                                             int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
+                                             int32_t* __restrict__ uniq, const float** src) {
+    if (pl.pi == pl.pi_end) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&ctrl[0], PV_CHUNK);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= total) {
+            if (lane == 0) rec->valid = 0;
+            return false;
+        }
+        pl.pi = c;
+        pl.pi_end = min(c + PV_CHUNK, total);
+        int lo = 0, hi = total_rows;     // 32-ary search: last row with tile0 <= pi
+        while (hi - lo > 32) {
+            const int step = (hi - lo + 31) >> 5;
+            const int probe = lo + lane * step;
+            const bool ok = probe < hi && rowplan[probe].x <= pl.pi;
+            const uint32_t b = __ballot_sync(0xffffffffu, ok);
+            const int k = 31 - __clz(b);
+            lo += k * step;
+            hi = min(hi, lo + step);
+        }
+        const int probe = lo + lane;
+        const bool ok = probe < hi && rowplan[probe].x <= pl.pi;
+        const uint32_t b = __ballot_sync(0xffffffffu, ok);
+        pl.prow = lo + 31 - __clz(b);
+        pl.prp = rowplan[pl.prow];
+    }
+    while (pl.pi >= pl.prp.x + pl.prp.y) { ++pl.prow; pl.prp = rowplan[pl.prow]; }   // rows without tiles are skipped
+    if (lane == 0) {
+        const s2d_video_desc* dp = descs + pl.prp.w;
+        const int q = pl.prow - (int)dp->row0;
+        const int t = pl.prp.z + (pl.pi - pl.prp.x);
+        const int P = dp->P, T = dp->T, L = dp->L;
+        const int64_t rt = (int64_t)q * T + t;
+        PvTile ti;
+        ti.lbl = dp->labels + (int64_t)t * dp->H * dp->W;
+        ti.hout = hits + dp->hits_off + rt * L;
+        ti.uout = uniq + dp->vt_off + rt;
+        *ti.uout = 0;        // the output phase accumulates per-warp partial sums (ordered by the barriers in between)
+        ti.W = dp->W; ti.H = dp->H; ti.L = L;
+        const int32_t* np = dp->npts;
+        ti.n = np ? min(max(np[q], 0), P) : P;
+        ti.valid = 1; ti.pad = P;
+        *rec = ti;
+        const int32_t* tsp = dp->tstart;
+        const int64_t ts = t - (tsp ? tsp[q] : 0);           // frame index inside the stored track window
+        *src = dp->tracks + ((int64_t)q * dp->Ttr + ts) * P * 2;
+    }
+    ++pl.pi;
+    return true;
+}
+
 template <int THREADS, int PPT, int CTAS>
-__global__ void __launch_bounds__(THREADS + 32, CTAS)
+__global__ void __launch_bounds__(THREADS, CTAS)
 point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __restrict__ rowplan,
                        int total_rows, int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
                        int32_t* __restrict__ uniq) {
-    constexpr int STAGE_BYTES = THREADS * PPT * 8;
-    constexpr int TAB_BYTES = pv_tab_bytes(THREADS, PPT, CTAS);
+    constexpr int BUF_BYTES = pv_buf_bytes(THREADS, PPT, CTAS);
     constexpr int NWARPS = THREADS / 32;
-    static_assert(TAB_BYTES >= PV_BM_WORDS * 4, "the fallback bitmap lives in the table");
+    static_assert(BUF_BYTES >= PV_BM_WORDS * 4, "the fallback bitmap lives in the buffer");
     static_assert(THREADS >= S2D_MAX_LABELS, "output phase uses one thread per histogram bin");
     static_assert(PPT % 2 == 0, "points are read two at a time");
-    extern __shared__ __align__(128) uint8_t dsm[];
-    uint8_t* tab = dsm + STAGE_BYTES;
+    extern __shared__ __align__(128) uint8_t buf[];   // tracks of the tile, then its label table
     __shared__ int hist[S2D_MAX_LABELS];
     __shared__ __align__(8) uint2 wred[NWARPS];        // per-warp packed (min, max + 1) of (iy, ix)
     __shared__ uint32_t dummy[32];                     // all ones: target of points outside the band
-    __shared__ __align__(8) uint64_t full, empty, tabbar;
+    __shared__ __align__(8) uint64_t full, tabbar;
     __shared__ PvTile tinfo[2];
+    __shared__ PvPlan plan_s;                          // scheduler state (kept out of the registers)
+    __shared__ const float* nsrc_s;                    // tracks of the planned tile
+    __shared__ int more_s;
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total = ctrl[1];
 
-    if (tid < THREADS)
-        for (int i = tid; i < S2D_MAX_LABELS; i += THREADS) hist[i] = 0;
+    for (int i = tid; i < S2D_MAX_LABELS; i += THREADS) hist[i] = 0;
     if (tid < 32) dummy[tid] = 0xFFFFFFFFu;
     if (tid == 0) {
+        plan_s.pi = plan_s.pi_end = plan_s.prow = 0;
+        plan_s.prp = make_int4(0, 0, 0, 0);
         mbar_init(&full, 1);
-        mbar_init(&empty, NWARPS);
         mbar_init(&tabbar, THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (tid >= THREADS) {
-        // =========================== producer warp ===========================================
-        int pi = 0, pi_end = 0, prow = 0;          // next tile index, end of claimed chunk, its row
-        int4 prp = make_int4(0, 0, 0, 0);          // rowplan[prow]
-        for (int j = 0;; ++j) {
-            const int s = j & 1;
-            if (j >= 1) mbar_wait(&empty, (j - 1) & 1);    // tile j-1 is in registers: stage and tinfo[s] are free
-            bool done = false;
-            if (pi == pi_end) {
-                int c = 0;
-                if (lane == 0) c = atomicAdd(&ctrl[0], PV_CHUNK);
-                c = __shfl_sync(0xffffffffu, c, 0);
-                if (c >= total) {
-                    done = true;
-                } else {
-                    pi = c;
-                    pi_end = min(c + PV_CHUNK, total);
-                    int lo = 0, hi = total_rows;     // 32-ary search: last row with tile0 <= pi
-                    while (hi - lo > 32) {
-                        const int step = (hi - lo + 31) >> 5;
-                        const int probe = lo + lane * step;
-                        const bool ok = probe < hi && rowplan[probe].x <= pi;
-                        const uint32_t b = __ballot_sync(0xffffffffu, ok);
-                        const int k = 31 - __clz(b);
-                        lo += k * step;
-                        hi = min(hi, lo + step);
-                    }
-                    const int probe = lo + lane;
-                    const bool ok = probe < hi && rowplan[probe].x <= pi;
-                    const uint32_t b = __ballot_sync(0xffffffffu, ok);
-                    prow = lo + 31 - __clz(b);
-                    prp = rowplan[prow];
-                }
-            }
-            if (done) {
-                if (lane == 0) { tinfo[s].valid = 0; mbar_arrive(&full); }
-                break;
-            }
-            while (pi >= prp.x + prp.y) { ++prow; prp = rowplan[prow]; }   // rows without tiles are skipped
-            if (lane == 0) {
-                const s2d_video_desc* dp = descs + prp.w;
-                const int q = prow - (int)dp->row0;
-                const int t = prp.z + (pi - prp.x);
-                const int P = dp->P, T = dp->T, L = dp->L;
-                const int64_t rt = (int64_t)q * T + t;
-                PvTile ti;
-                ti.lbl = dp->labels + (int64_t)t * dp->H * dp->W;
-                ti.hout = hits + dp->hits_off + rt * L;
-                ti.uout = uniq + dp->vt_off + rt;
-                *ti.uout = 0;        // consumers accumulate per-warp partial sums (ordered by the mbarrier release/acquire)
-                ti.W = dp->W; ti.H = dp->H; ti.L = L;
-                const int32_t* np = dp->npts;
-                ti.n = np ? min(max(np[q], 0), P) : P;
-                ti.valid = 1; ti.pad = 0;
-                tinfo[s] = ti;
-                const uint32_t bytes = (uint32_t)P * 8u;
-                mbar_expect_tx(&full, bytes);
-                const int32_t* tsp = dp->tstart;
-                const int64_t ts = t - (tsp ? tsp[q] : 0);           // frame index inside the stored track window
-                bulk_g2s(dsm, dp->tracks + ((int64_t)q * dp->Ttr + ts) * P * 2, bytes, &full);
-            }
-            ++pi;
+    // warp 0: plan one tile (state and results live in shared memory)
+    auto plan = [&](PvTile* rec) {
+        PvPlan pl = plan_s;
+        const float* src = nullptr;
+        const bool ok = pv_plan_next(pl, rec, lane, descs, rowplan, total_rows, total, ctrl, hits, uniq, &src);
+        __syncwarp();
+        if (lane == 0) { plan_s = pl; nsrc_s = src; more_s = ok ? 1 : 0; }
+    };
+    if (warp == 0) {
+        plan(&tinfo[0]);
+        __syncwarp();
+        if (lane == 0 && more_s) {
+            const uint32_t bytes = (uint32_t)tinfo[0].pad * 8u;
+            mbar_expect_tx(&full, bytes);
+            bulk_g2s(buf, nsrc_s, bytes, &full);
         }
-        return;
     }
+    __syncthreads();
 
-    // =============================== consumer warps ==========================================
-    const int warp = tid >> 5;
-    const uint32_t tab_s = smem_u32(tab);
+    const uint32_t tab_s = smem_u32(buf);
     const uint32_t dummy_s = smem_u32(&dummy[lane]);
     uint32_t tabphase = 0;
     for (int j = 0;; ++j) {
         const PvTile* ti = &tinfo[j & 1];
+        if (!ti->valid) break;                        // written before the barrier that precedes this read
         mbar_wait(&full, j & 1);
-        if (!ti->valid) break;
         const uint32_t W = ti->W, H = ti->H;
         if (W > 65535u || H > 65535u) __trap();      // packed 16-bit coordinates (documented limit)
         const int n = ti->n;
 
-        // ---- phase A: stage -> registers, round / bounds / pack, bounding box -----------------
+        // ---- phase A: buffer -> registers, round / bounds / pack, bounding box ----------------
         uint32_t pk[PPT];
         uint32_t mn = 0xFFFFFFFFu, mx = 0;
-        const float4* sp = reinterpret_cast<const float4*>(dsm);
+        const float4* sp = reinterpret_cast<const float4*>(buf);
         if (n >= THREADS * PPT) {
 #pragma unroll
             for (int k = 0; k < PPT / 2; ++k) {
@@ -729,8 +747,6 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                 pk[2 * k + 1] = (p0 + 1 < n) ? b : PV_PK_INVALID;
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty);           // this warp no longer reads the stage
 #pragma unroll
         for (int k = 0; k < PPT / 2; ++k) {
             // per-halfword min / max; an invalid point is (0xFFFF, 0xFFFF) for the min and, after the
@@ -743,7 +759,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
             const uint32_t mxx = __reduce_max_sync(0xffffffffu, mx & 0xFFFFu), mxy = __reduce_max_sync(0xffffffffu, mx >> 16);
             if (lane == 0) wred[warp] = make_uint2((mny << 16) | mnx, (mxy << 16) | mxx);
         }
-        consumer_sync(THREADS);                       // S1: per-warp boxes complete; previous tile fully retired
+        __syncthreads();                              // S1: boxes complete, nobody reads the tracks any more
         uint32_t bmn = 0xFFFFFFFFu, bmx = 0;
 #pragma unroll
         for (int w = 0; w < NWARPS; ++w) {
@@ -752,12 +768,13 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
             bmx = __vmaxu2(bmx, v.y);
         }
         const int L = ti->L;
+        bool planned = false;                         // warp 0: next tile's record prepared
         if (bmn != 0xFFFFFFFFu) {                     // at least one point inside the frame
             const uint32_t x0 = bmn & 0xFFFFu, y0 = bmn >> 16;
             const uint32_t bw = (bmx & 0xFFFFu) - x0, bh = (bmx >> 16) - y0;      // max holds coordinate + 1
             uint32_t pitch = bw + 15u;
             pitch += (W - pitch) & 15u;               // pitch = W (mod 16), pitch >= bw + 15
-            const uint32_t R = (uint32_t)TAB_BYTES / pitch;                       // rows per band
+            const uint32_t R = (uint32_t)BUF_BYTES / pitch;                       // rows per band
             const uint8_t* lbl = ti->lbl;
             if (L <= 255 && R * PV_MAX_BANDS >= bh) {
                 // ---- table mode ---------------------------------------------------------------
@@ -770,11 +787,15 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                         const uint32_t ph = (uint32_t)(A + (uint64_t)r * W) & 15u;
                         bytes += (ph + bw + 15u) & ~15u;
                     }
-                    mbar_expect_tx(&tabbar, bytes);                                // one arrival per consumer thread
+                    mbar_expect_tx(&tabbar, bytes);                                // one arrival per thread
                     for (uint32_t r = tid; r < rows; r += THREADS) {
                         const uint64_t g = A + (uint64_t)r * W;
                         const uint32_t ph = (uint32_t)g & 15u;
                         bulk_g2s_addr(tab_s + r * pitch + a15 - ph, g - ph, (ph + bw + 15u) & ~15u, &tabbar);
+                    }
+                    if (warp == 0 && !planned) {      // overlap the plan's dependent loads with the table's flight
+                        plan(&tinfo[(j + 1) & 1]);
+                        planned = true;
                     }
                     mbar_wait(&tabbar, tabphase);
                     tabphase ^= 1u;
@@ -787,12 +808,12 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                     const uint32_t negc = pitch - 65536u;
                     // Groups of G points: all G atomics are issued before the first result is used.
                     // Points outside the band (and invalid ones) hit a per-lane dummy word that is all
-                    // ones, so they read back 0xFF = "not first" without a branch. First points that
-                    // carry the warp's reference label `cur` are counted in a register; the rest
-                    // (object borders, other masks) vote one by one.
-                    constexpr int G = PPT < 8 ? PPT : 8;
-                    uint32_t cur = 0x100u;             // warp-uniform reference label, chosen in group 0
-                    int cnt = 0;
+                    // ones, so they read back 0xFF = "not first" without a branch. Every point then
+                    // votes for the byte it read with one shared-memory reduction (SASS ATOMS.POPC.INC:
+                    // the lanes of a warp that hit the same bin are merged); bin 255 collects the
+                    // points that were not first and is dropped in the output phase (L <= 255 here).
+                    constexpr int G = (PPT < 8 || CTAS >= 5) ? 4 : 8;
+                    const uint32_t hist_s = smem_u32(hist);
 #pragma unroll
                     for (int g = 0; g < PPT; g += G) {
                         uint32_t old[G], sh[G];
@@ -800,46 +821,29 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                         for (int k = 0; k < G; ++k) {
                             const uint32_t e = pk[g + k] - pk0;
                             const uint32_t off = (e >> 16) * negc + e + tabc;      // table + dy * pitch + dx + a15
-                            sh[k] = (off << 3) & 24u;
+                            sh[k] = off << 3;                                      // used modulo 32 (wrapping shifts)
                             const uint32_t addr = (e < lim) ? (off & ~3u) : dummy_s;
-                            asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old[k]) : "r"(addr), "r"(0xFFu << sh[k]));
+                            asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old[k]) : "r"(addr), "r"(__funnelshift_l(0u, 0xFFu, sh[k])));
                         }
-                        if (g == 0) {
-                            const uint32_t l0 = (old[0] >> sh[0]) & 0xFFu;
-                            const uint32_t have = __ballot_sync(0xffffffffu, l0 != 0xFFu);
-                            const uint32_t lsel = __shfl_sync(0xffffffffu, l0, have ? __ffs(have) - 1 : 0);
-                            cur = have ? lsel : 0x100u;
-                        }
-                        uint32_t odd = 0;
 #pragma unroll
                         for (int k = 0; k < G; ++k) {
-                            const uint32_t lab = (old[k] >> sh[k]) & 0xFFu;        // 0xFF: not first / not in band
-                            cnt += (lab == cur) ? 1 : 0;
-                            odd |= (lab != cur && lab != 0xFFu) ? (1u << k) : 0u;
+                            const uint32_t lab = __funnelshift_r(old[k], 0u, sh[k]) & 0xFFu;   // 0xFF: not first / not in band
+                            asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(hist_s + lab * 4u) : "memory");
                         }
-                        if (odd) {
-#pragma unroll
-                            for (int k = 0; k < G; ++k)
-                                if ((odd >> k) & 1u) atomicAdd(&hist[(old[k] >> sh[k]) & 0xFFu], 1);
-                        }
-                    }
-                    if (cur != 0x100u) {               // warp-uniform label: one reduction, one atomic
-                        const int ws = __reduce_add_sync(0xffffffffu, cnt);
-                        if (lane == 0 && ws) atomicAdd(&hist[cur], ws);
                     }
                     if (b0 + R < bh) {                 // the next band's copies overwrite the table
                         fence_proxy_async();
-                        consumer_sync(THREADS);
+                        __syncthreads();
                     }
                 }
             } else {
-                // ---- fallback: bitmap in the table memory + global label gather ----------------
-                uint32_t* bm = reinterpret_cast<uint32_t*>(tab);
+                // ---- fallback: bitmap in the buffer + global label gather ----------------------
+                uint32_t* bm = reinterpret_cast<uint32_t*>(buf);
                 const uint32_t lend = (y0 + bh - 1u) * W + x0 + bw;            // last pixel + 1
                 for (uint32_t base = y0 * W + x0;; base += PV_BM_BITS) {
                     for (int i = tid; i < PV_BM_WORDS / 4; i += THREADS)
                         reinterpret_cast<uint4*>(bm)[i] = make_uint4(0, 0, 0, 0);
-                    consumer_sync(THREADS);
+                    __syncthreads();
 #pragma unroll
                     for (int k = 0; k < PPT; ++k) {
                         const uint32_t p = pk[k];
@@ -847,27 +851,34 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                         if (pv_claim_s(tab_s, lin, base)) atomicAdd(&hist[__ldg(lbl + lin)], 1);
                     }
                     if (lend - base <= (uint32_t)PV_BM_BITS) break;
-                    consumer_sync(THREADS);
+                    __syncthreads();
                 }
             }
         }
-        fence_proxy_async();                          // table atomics before the next tile's bulk copies
-        consumer_sync(THREADS);                       // S2: histogram complete
+        if (warp == 0 && !planned) plan(&tinfo[(j + 1) & 1]);
+        fence_proxy_async();                          // buffer atomics before the next tile's bulk copy
+        __syncthreads();                              // S2: histogram complete, buffer free, next record visible
+        if (tid == 0 && more_s) {                     // the next tile's tracks fly during the output phase
+            const uint32_t bytes = (uint32_t)tinfo[(j + 1) & 1].pad * 8u;
+            mbar_expect_tx(&full, bytes);
+            bulk_g2s(buf, nsrc_s, bytes, &full);
+        }
         if (tid < S2D_MAX_LABELS) {                   // 8 warps: write hits, uniq = sum of the histogram
-            const int h = hist[tid];
+            const int h = (tid == 255 && L <= 255) ? 0 : hist[tid];       // table mode parks non-first points in bin 255
             if (tid < L) ti->hout[tid] = h;
             hist[tid] = 0;
             const int ws = __reduce_add_sync(0xffffffffu, h);
-            if (lane == 0 && ws) atomicAdd(ti->uout, ws);      // *uout was cleared by the producer
+            if (lane == 0 && ws) atomicAdd(ti->uout, ws);      // *uout was cleared when the tile was planned
         }
-        // the next tile's S1 orders these resets before its histogram atomics
+        // the next tile's S1 orders the histogram resets before its votes; tinfo[j & 1] is rewritten
+        // only after that S1 as well (the plan of tile j + 2 runs behind it)
     }
 }
 
 template <int THREADS, int PPT, int CTAS>
 static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, const int4* rowplan,
                          int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq) {
-    const int smem = THREADS * PPT * 8 + pv_tab_bytes(THREADS, PPT, CTAS) + 64;
+    const int smem = pv_buf_bytes(THREADS, PPT, CTAS) + 64;
     auto kfn = point_votes_tab_kernel<THREADS, PPT, CTAS>;
     static bool configured = false;
     if (!configured) {
@@ -876,9 +887,9 @@ static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, 
         configured = true;
     }
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, THREADS + 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, THREADS, smem);
     if (per_sm < 1) per_sm = 1;
-    kfn<<<nsm * per_sm, THREADS + 32, smem, st>>>(descs, rowplan, total_rows, ctrl, hits, uniq);
+    kfn<<<nsm * per_sm, THREADS, smem, st>>>(descs, rowplan, total_rows, ctrl, hits, uniq);
     S2D_CHECK_LAUNCH("point_votes_tab_kernel");
     return 0;
 }
@@ -956,10 +967,15 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
         S2D_CHECK_LAUNCH("pv_scan_kernel");
         const int tr = (int)total_rows;
         if (variant == 0) {      // label-table kernels
-            if (max_P <= 256 * 4) return launch_pv_tab<256, 4, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
-            if (max_P <= 256 * 8) return launch_pv_tab<256, 8, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
-            if (max_P <= 256 * 16) return launch_pv_tab<256, 16, 3>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
-            return launch_pv_tab<256, 32, 2>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+            static const int ctas = getenv("S2D_PV_CTAS") ? atoi(getenv("S2D_PV_CTAS")) : 4;
+            if (max_P <= 256 * 4) return launch_pv_tab<256, 4, 5>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+            if (max_P <= 256 * 8) return launch_pv_tab<256, 8, 5>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+            if (max_P <= 256 * 16) {
+                if (ctas == 5) return launch_pv_tab<256, 16, 5>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+                if (ctas == 3) return launch_pv_tab<256, 16, 3>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+                return launch_pv_tab<256, 16, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+            }
+            return launch_pv_tab<256, 32, 3>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
         }
         if (max_P <= 256 * 4) return launch_pv_tma<256, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);   // 4 CTAs/SM
         if (max_P <= 512 * 4) return launch_pv_tma<512, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
