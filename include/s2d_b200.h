@@ -138,12 +138,19 @@ int s2d_windows(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_TW,
  * lookup with one shared-memory atomic per point; variant 1 de-duplicates in a shared bitmap and
  * gathers labels from global memory; variant 2 (also used when work == NULL or the promises above
  * do not hold) is the one-CTA-per-tile kernel. All variants give identical results.
- * H, W <= 65535; P <= 32768. */
+ * H, W <= 65535; P <= 32768.
+ * label_tmaps (optional, may be NULL): DEVICE copy (64-byte aligned) of the buffer that
+ * s2d_point_votes_tmaps fills on the HOST from a host copy of the descriptors - S2D_PV_TMAP_BYTES
+ * per video: TMA descriptors of the video's label maps, so that variant 0 fetches a tile's table
+ * as a few 2D boxes instead of one bulk copy per row. Videos whose W or label base address is not
+ * a multiple of 16 get no descriptors and keep the row-by-row fetch. */
+#define S2D_PV_TMAP_BYTES 640
 int s2d_point_votes_variant(int variant);   /* process-wide; 0 label table, 1 bitmap, 2 CTA per tile */
 int s2d_point_votes_work_ints(int64_t total_rows, int64_t* out);
+int s2d_point_votes_tmaps(const s2d_video_desc* host_descs, int nvideos, void* host_out);
 int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max_T, int max_Nm, int max_P,
                     int vec4_ok, int64_t total_rows, const int32_t* rowinfo, const int32_t* vidinfo,
-                    int32_t* work, int32_t* hits, int32_t* uniq, void* stream);
+                    int32_t* work, const void* label_tmaps, int32_t* hits, int32_t* uniq, void* stream);
 
 /* K4a. Scores and selection per candidate query: iou = hits/uniq (double), match bit when
  * iou > matching_threshold (cotracker_matching.py:710), one-to-many flag when >= one2x_frames

@@ -15,6 +15,7 @@ S2D_MAX_LABELS = 256
 S2D_MAX_CLUSTERS = 16
 S2D_VIDINFO_WORDS = 8
 S2D_CLINFO_WORDS = 16
+S2D_PV_TMAP_BYTES = 640
 
 
 class VideoDesc(C.Structure):
@@ -46,7 +47,8 @@ SIGNATURES = {
     "s2d_windows": [_P, _I, _L, _I, _L, _L, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "s2d_point_votes_variant": [_I],
     "s2d_point_votes_work_ints": [_L, C.POINTER(C.c_int64)],
-    "s2d_point_votes": [_P, _I, _I, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P],
+    "s2d_point_votes_tmaps": [_P, _I, _P],
+    "s2d_point_votes": [_P, _I, _I, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P],
     "s2d_select": [_P, _I, _I, _L, _P, _P, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P],
     "s2d_group_work_ints": [_L, _I, C.POINTER(C.c_int64)],
     "s2d_group": [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],

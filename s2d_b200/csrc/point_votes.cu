@@ -14,8 +14,10 @@
 // hits[lab] = |P AND mask_lab| = intersection.
 #include "common.cuh"
 
+#include <cuda.h>
 #include <limits.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace s2d {
 
@@ -254,7 +256,9 @@ struct PvTile {             // written by the producer thread, read by everybody
     int32_t* uout;          // &uniq[q,t]
     uint32_t W, H;
     int32_t n, L;
-    int32_t valid, pad;
+    int32_t valid, pad;     // pad: P of the tile in the label-table kernel
+    const uint8_t* tm;      // label-table kernel: the video's TMA descriptors (s2d_point_votes_tmaps) or null
+    uint32_t ybase, pad2;   // t * H: first row of the frame in the descriptors' [T*H][W] view
 };
 
 struct PvOut { int32_t* hout; int32_t* uout; int32_t L, pad; };
@@ -598,6 +602,10 @@ __device__ __forceinline__ void bulk_g2s_addr(uint32_t smem_dst, uint64_t gsrc, 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_box_2d(uint32_t smem_dst, const void* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct PvPlan {              // warp-0 state of the tile scheduler (identical in all its lanes)
@@ -610,7 +618,8 @@ struct PvPlan {              // warp-0 state of the tile scheduler (identical in
 __device__ __forceinline__ bool pv_plan_next(PvPlan& pl, PvTile* rec, int lane, const s2d_video_desc* __restrict__ descs,
                                              const int4* __restrict__ rowplan, int total_rows, int total,
                                              int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
-                                             int32_t* __restrict__ uniq, const float** src) {
+                                             int32_t* __restrict__ uniq, const uint8_t* __restrict__ tmaps,
+                                             const float** src) {
     if (pl.pi == pl.pi_end) {
         int c = 0;
         if (lane == 0) c = atomicAdd(&ctrl[0], PV_CHUNK);
@@ -653,6 +662,10 @@ __device__ __forceinline__ bool pv_plan_next(PvPlan& pl, PvTile* rec, int lane, 
         const int32_t* np = dp->npts;
         ti.n = np ? min(max(np[q], 0), P) : P;
         ti.valid = 1; ti.pad = P;
+        const uint8_t* tm = tmaps ? tmaps + (size_t)pl.prp.w * S2D_PV_TMAP_BYTES : nullptr;
+        if (tm && *reinterpret_cast<const int32_t*>(tm + 4 * 128) == 0) tm = nullptr;     // this video has no descriptors
+        ti.tm = tm;
+        ti.ybase = (uint32_t)t * (uint32_t)dp->H; ti.pad2 = 0;
         *rec = ti;
         const int32_t* tsp = dp->tstart;
         const int64_t ts = t - (tsp ? tsp[q] : 0);           // frame index inside the stored track window
@@ -666,7 +679,7 @@ template <int THREADS, int PPT, int CTAS>
 __global__ void __launch_bounds__(THREADS, CTAS)
 point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __restrict__ rowplan,
                        int total_rows, int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
-                       int32_t* __restrict__ uniq) {
+                       int32_t* __restrict__ uniq, const uint8_t* __restrict__ tmaps) {
     constexpr int BUF_BYTES = pv_buf_bytes(THREADS, PPT, CTAS);
     constexpr int NWARPS = THREADS / 32;
     static_assert(BUF_BYTES >= PV_BM_WORDS * 4, "the fallback bitmap lives in the buffer");
@@ -700,7 +713,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     auto plan = [&](PvTile* rec) {
         PvPlan pl = plan_s;
         const float* src = nullptr;
-        const bool ok = pv_plan_next(pl, rec, lane, descs, rowplan, total_rows, total, ctrl, hits, uniq, &src);
+        const bool ok = pv_plan_next(pl, rec, lane, descs, rowplan, total_rows, total, ctrl, hits, uniq, tmaps, &src);
         __syncwarp();
         if (lane == 0) { plan_s = pl; nsrc_s = src; more_s = ok ? 1 : 0; }
     };
@@ -772,26 +785,50 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         if (bmn != 0xFFFFFFFFu) {                     // at least one point inside the frame
             const uint32_t x0 = bmn & 0xFFFFu, y0 = bmn >> 16;
             const uint32_t bw = (bmx & 0xFFFFu) - x0, bh = (bmx >> 16) - y0;      // max holds coordinate + 1
-            uint32_t pitch = bw + 15u;
-            pitch += (W - pitch) & 15u;               // pitch = W (mod 16), pitch >= bw + 15
-            const uint32_t R = (uint32_t)BUF_BYTES / pitch;                       // rows per band
+            // With TMA descriptors (row pitch and base of the label maps are multiples of 16) the table is
+            // fetched as 2D boxes of 16 rows x 64/128/192/256 pixels, one instruction each; otherwise row by row.
+            // (a box must start on a 16-byte boundary of its row: it starts at x0 & ~15)
+            const uint8_t* tm = (bw + (x0 & 15u) <= 256u) ? ti->tm : nullptr;
+            uint32_t pitch, R;
+            if (tm) {
+                pitch = (bw + (x0 & 15u) + 63u) & ~63u;
+                R = ((uint32_t)BUF_BYTES / pitch) & ~15u;                         // rows per band, whole boxes
+            } else {
+                pitch = bw + 15u;
+                pitch += (W - pitch) & 15u;           // pitch = W (mod 16), pitch >= bw + 15
+                R = (uint32_t)BUF_BYTES / pitch;
+            }
             const uint8_t* lbl = ti->lbl;
             if (L <= 255 && R * PV_MAX_BANDS >= bh) {
                 // ---- table mode ---------------------------------------------------------------
                 for (uint32_t b0 = 0; b0 < bh; b0 += R) {
                     const uint32_t rows = min(R, bh - b0);
-                    const uint64_t A = (uint64_t)(uintptr_t)lbl + (uint64_t)(y0 + b0) * W + x0;
-                    const uint32_t a15 = (uint32_t)A & 15u;
-                    uint32_t bytes = 0;
-                    for (uint32_t r = tid; r < rows; r += THREADS) {
-                        const uint32_t ph = (uint32_t)(A + (uint64_t)r * W) & 15u;
-                        bytes += (ph + bw + 15u) & ~15u;
-                    }
-                    mbar_expect_tx(&tabbar, bytes);                                // one arrival per thread
-                    for (uint32_t r = tid; r < rows; r += THREADS) {
-                        const uint64_t g = A + (uint64_t)r * W;
-                        const uint32_t ph = (uint32_t)g & 15u;
-                        bulk_g2s_addr(tab_s + r * pitch + a15 - ph, g - ph, (ph + bw + 15u) & ~15u, &tabbar);
+                    uint32_t a15 = 0;
+                    if (tm) {
+                        a15 = x0 & 15u;
+                        if (tid == 0) {
+                            const uint32_t nbox = (rows + 15u) >> 4;
+                            mbar_expect_tx(&tabbar, nbox * 16u * pitch);
+                            const uint8_t* map = tm + ((pitch >> 6) - 1u) * 128u;
+                            for (uint32_t i = 0; i < nbox; ++i)
+                                tma_box_2d(tab_s + i * 16u * pitch, map, &tabbar, (int)(x0 & ~15u), (int)(ti->ybase + y0 + b0 + 16u * i));
+                        } else {
+                            mbar_arrive(&tabbar);
+                        }
+                    } else {
+                        const uint64_t A = (uint64_t)(uintptr_t)lbl + (uint64_t)(y0 + b0) * W + x0;
+                        a15 = (uint32_t)A & 15u;
+                        uint32_t bytes = 0;
+                        for (uint32_t r = tid; r < rows; r += THREADS) {
+                            const uint32_t ph = (uint32_t)(A + (uint64_t)r * W) & 15u;
+                            bytes += (ph + bw + 15u) & ~15u;
+                        }
+                        mbar_expect_tx(&tabbar, bytes);                            // one arrival per thread
+                        for (uint32_t r = tid; r < rows; r += THREADS) {
+                            const uint64_t g = A + (uint64_t)r * W;
+                            const uint32_t ph = (uint32_t)g & 15u;
+                            bulk_g2s_addr(tab_s + r * pitch + a15 - ph, g - ph, (ph + bw + 15u) & ~15u, &tabbar);
+                        }
                     }
                     if (warp == 0 && !planned) {      // overlap the plan's dependent loads with the table's flight
                         plan(&tinfo[(j + 1) & 1]);
@@ -877,7 +914,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
 
 template <int THREADS, int PPT, int CTAS>
 static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, const int4* rowplan,
-                         int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq) {
+                         int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq, const uint8_t* tmaps) {
     const int smem = pv_buf_bytes(THREADS, PPT, CTAS) + 64;
     auto kfn = point_votes_tab_kernel<THREADS, PPT, CTAS>;
     static bool configured = false;
@@ -889,7 +926,7 @@ static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, 
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, THREADS, smem);
     if (per_sm < 1) per_sm = 1;
-    kfn<<<nsm * per_sm, THREADS, smem, st>>>(descs, rowplan, total_rows, ctrl, hits, uniq);
+    kfn<<<nsm * per_sm, THREADS, smem, st>>>(descs, rowplan, total_rows, ctrl, hits, uniq, tmaps);
     S2D_CHECK_LAUNCH("point_votes_tab_kernel");
     return 0;
 }
@@ -942,10 +979,58 @@ extern "C" int s2d_point_votes_work_ints(int64_t total_rows, int64_t* out) {
     return 0;
 }
 
+// Host side: TMA descriptors of the videos' label maps for the label-table kernel. Per video
+// S2D_PV_TMAP_BYTES: four CUtensorMap (u8 [T*H][W], boxes of 16 rows x 64/128/192/256 pixels) and a
+// 128-byte trailer whose first int is 1 when the descriptors are usable (W and the base address
+// are multiples of 16, W >= 64), 0 otherwise (that video's tables are then fetched row by row).
+typedef CUresult (*PvEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+extern "C" int s2d_point_votes_tmaps(const s2d_video_desc* host_descs, int nvideos, void* host_out) {
+    S2D_CHECK_ARG(host_descs && host_out && nvideos > 0, "s2d_point_votes_tmaps: bad arguments");
+    static PvEncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            enc = (PvEncodeTiledFn)p;
+    }
+    uint8_t* out = static_cast<uint8_t*>(host_out);
+    memset(out, 0, (size_t)nvideos * S2D_PV_TMAP_BYTES);
+    if (!enc) return 0;                       // no driver entry point: every video falls back to row copies
+    for (int v = 0; v < nvideos; ++v) {
+        const s2d_video_desc& d = host_descs[v];
+        uint8_t* blk = out + (size_t)v * S2D_PV_TMAP_BYTES;
+        if (!d.labels || d.W < 64 || (d.W & 15) || (((uintptr_t)d.labels) & 15) || d.T <= 0 || d.H <= 0) continue;
+        bool ok = true;
+        for (int k = 0; k < 4 && ok; ++k) {
+            if (64 * (k + 1) > d.W) {         // box wider than the frame: reuse the widest one that fits (never selected
+                memcpy(blk + k * 128, blk + (k - 1) * 128, 128);          // for bw <= W, but keep the slot well formed)
+                continue;
+            }
+            CUtensorMap map;
+            cuuint64_t dims[2] = {(cuuint64_t)d.W, (cuuint64_t)d.T * (cuuint64_t)d.H};
+            cuuint64_t strides[1] = {(cuuint64_t)d.W};
+            cuuint32_t box[2] = {(cuuint32_t)(64 * (k + 1)), 16u};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)d.labels, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) ok = false;
+            else memcpy(blk + k * 128, &map, 128);
+        }
+        if (ok) *reinterpret_cast<int32_t*>(blk + 4 * 128) = 1;
+    }
+    return 0;
+}
+
 extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max_T, int max_Nm, int max_P,
                                int vec4_ok, int64_t total_rows, const int32_t* rowinfo,
-                               const int32_t* vidinfo, int32_t* work, int32_t* hits, int32_t* uniq,
-                               void* stream) {
+                               const int32_t* vidinfo, int32_t* work, const void* label_tmaps,
+                               int32_t* hits, int32_t* uniq, void* stream) {
+    S2D_CHECK_ARG((((uintptr_t)label_tmaps) & 63) == 0, "s2d_point_votes: label_tmaps must be 64-byte aligned");
+    const uint8_t* tm = static_cast<const uint8_t*>(label_tmaps);
     S2D_CHECK_ARG(descs && hits && uniq, "s2d_point_votes: null pointer");
     S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_T > 0 && max_Nm > 0 && max_Nm <= 65535,
                   "s2d_point_votes: bad sizes");
@@ -968,14 +1053,14 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
         const int tr = (int)total_rows;
         if (variant == 0) {      // label-table kernels
             static const int ctas = getenv("S2D_PV_CTAS") ? atoi(getenv("S2D_PV_CTAS")) : 4;
-            if (max_P <= 256 * 4) return launch_pv_tab<256, 4, 5>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
-            if (max_P <= 256 * 8) return launch_pv_tab<256, 8, 5>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+            if (max_P <= 256 * 4) return launch_pv_tab<256, 4, 5>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+            if (max_P <= 256 * 8) return launch_pv_tab<256, 8, 5>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
             if (max_P <= 256 * 16) {
-                if (ctas == 5) return launch_pv_tab<256, 16, 5>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
-                if (ctas == 3) return launch_pv_tab<256, 16, 3>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
-                return launch_pv_tab<256, 16, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+                if (ctas == 5) return launch_pv_tab<256, 16, 5>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                if (ctas == 3) return launch_pv_tab<256, 16, 3>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                return launch_pv_tab<256, 16, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
             }
-            return launch_pv_tab<256, 32, 3>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+            return launch_pv_tab<256, 32, 3>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
         }
         if (max_P <= 256 * 4) return launch_pv_tma<256, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);   // 4 CTAs/SM
         if (max_P <= 512 * 4) return launch_pv_tma<512, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (S2D_CLINFO_WORDS, S2D_MAX_CLUSTERS, S2D_MAX_LABELS, S2D_VIDINFO_WORDS, VideoDesc)
+from ._lib import (S2D_CLINFO_WORDS, S2D_MAX_CLUSTERS, S2D_MAX_LABELS, S2D_PV_TMAP_BYTES, S2D_VIDINFO_WORDS, VideoDesc)
 
 
 @dataclass
@@ -152,11 +152,17 @@ class Batch:
             self.ccount = z(vt)
             self.clrow = z(row0 * 4)
             self.majbits, self.rsbits, self.rebits, self.winbits = z(xw), z(xw), z(xw), z(xw)
-        self.pvwork = self.hits = self.uniq = self.mbits = self.one2x = self.nmatch = None
+        self.pvwork = self.pvtmaps = self.hits = self.uniq = self.mbits = self.one2x = self.nmatch = None
         self.grpwork = self.glabel = self.grp_n = self.grp_one2x = None
         if "D" in st:
             _lib.call("s2d_point_votes_work_ints", row0, C.byref(n))
             self.pvwork = z(n.value + 4)
+            # TMA descriptors of the label maps (host-encoded once per batch, S2D_PV_TMA_DESC=0 disables)
+            if os.environ.get("S2D_PV_TMA_DESC", "1") != "0" and all(v.labels is not None for v in videos):
+                hbuf = np.zeros(nv * S2D_PV_TMAP_BYTES, np.uint8)
+                _lib.call("s2d_point_votes_tmaps", descs, nv, hbuf.ctypes.data)
+                self.pvtmaps = torch.from_numpy(hbuf).to(dev)
+                assert self.pvtmaps.data_ptr() % 64 == 0
             self.hits = z(hits)
             self.uniq = z(vt)
             self.mbits = z(mw)
@@ -178,7 +184,7 @@ class Batch:
         number of kernel launches enqueued. `timers`: optional dict name -> list; a pair of CUDA
         events is recorded around every C-ABI call on torch's current stream (bench.py)."""
         st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
-        p = lambda t: t.data_ptr()
+        p = lambda t: t.data_ptr() if t is not None else None
         d, nv = p(self.descs), self.nv
         launches = 0
         stages = self.stages if stages is None else stages
@@ -215,7 +221,7 @@ class Batch:
         if "D" in stages:
             call("point_votes", 3 if self.use_tma else 1, "s2d_point_votes", d, nv, self.max_T, self.max_Nm, self.max_P,
                  self.vec4, self.total_rows, p(self.rowinfo), p(self.vidinfo),
-                 p(self.pvwork) if self.use_tma else None, p(self.hits), p(self.uniq), st)
+                 p(self.pvwork) if self.use_tma else None, p(self.pvtmaps), p(self.hits), p(self.uniq), st)
             call("select", 1, "s2d_select", d, nv, self.max_Nm, self.total_mw, p(self.hits), p(self.uniq),
                  p(self.gid_of), p(self.rowinfo), params.matching_threshold, params.one2x_iou,
                  params.one2x_frames, p(self.mbits), p(self.one2x), p(self.nmatch), p(self.vidinfo), st)
@@ -230,6 +236,7 @@ class Batch:
         st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
         _lib.call("s2d_point_votes", self.descs.data_ptr(), self.nv, self.max_T, self.max_Nm, self.max_P, self.vec4,
                   self.total_rows, None, None, self.pvwork.data_ptr() if self.use_tma else None,
+                  self.pvtmaps.data_ptr() if self.pvtmaps is not None else None,
                   self.hits.data_ptr(), self.uniq.data_ptr(), st)
 
     # ------------------------------------------------------------------ results

@@ -103,13 +103,15 @@ def test_point_votes_shapes_and_bands(P, H, W, pv_variant):
     assert np.array_equal(b.V.cpu().numpy().reshape(Nm, T), ko.visibility_mean(vis))
 
 
-@pytest.mark.parametrize("H,W,P,M,lab255", [(480, 854, 1000, 10, False), (720, 1280, 4096, 20, False),
-                                            (1080, 1920, 2048, 6, False), (97, 131, 512, 5, True),
-                                            (480, 854, 4096, 20, True)])
-def test_point_votes_scene_geometry(H, W, P, M, lab255, pv_variant):
+@pytest.mark.parametrize("H,W,P,M,lab255,off", [(480, 854, 1000, 10, False, 5), (720, 1280, 4096, 20, False, 5),
+                                                (720, 1280, 4096, 20, False, 0), (1080, 1920, 2048, 6, False, 16),
+                                                (480, 864, 1024, 12, False, 0), (97, 131, 512, 5, True, 5),
+                                                (480, 854, 4096, 20, True, 0)])
+def test_point_votes_scene_geometry(H, W, P, M, lab255, off, pv_variant):
     """Object-shaped point clouds (compact bounding boxes: the label-table kernel's main path, one
     or several bands), widths that are not a multiple of 16, a label map that does not start on a
-    16-byte boundary, and label id 255 in use (the table kernel must take its bitmap fallback)."""
+    16-byte boundary (off = 5: tables fetched row by row; off = 0 / 16 with W a multiple of 16: tables
+    fetched as 2D TMA boxes), and label id 255 in use (the table kernel must take its bitmap fallback)."""
     from s2d_b200.pipeline import Batch, VideoInput
     from s2d_b200.synth import make_scene
     sc = make_scene(31 + H, 5, H, W, M, P, specials=True, dup_rate=0.05)
@@ -120,7 +122,6 @@ def test_point_votes_scene_geometry(H, W, P, M, lab255, pv_variant):
         maxlab = 255
     d = _dev()
     raw = torch.zeros(labels.size + 64, dtype=torch.uint8, device=d)
-    off = 5                                                    # misaligned label map
     raw[off:off + labels.size] = torch.from_numpy(labels.reshape(-1)).to(d)
     lab_dev = raw[off:off + labels.size].view(labels.shape)
     vid = VideoInput(labels=lab_dev, tracks=torch.from_numpy(sc.tracks).to(d), vis=torch.from_numpy(sc.vis).to(d),

@@ -46,7 +46,8 @@ def main():
 
                 def votes():
                     _lib.call("s2d_point_votes", b.descs.data_ptr(), 1, b.max_T, b.max_Nm, b.max_P, b.vec4, b.total_rows,
-                              b.rowinfo.data_ptr(), b.vidinfo.data_ptr(), b.pvwork.data_ptr(), b.hits.data_ptr(),
+                              b.rowinfo.data_ptr(), b.vidinfo.data_ptr(), b.pvwork.data_ptr(),
+                              b.pvtmaps.data_ptr() if b.pvtmaps is not None else None, b.hits.data_ptr(),
                               b.uniq.data_ptr(), st)
                 for _ in range(2):
                     votes()
