@@ -259,6 +259,7 @@ struct PvTile {             // written by the producer thread, read by everybody
     int32_t valid, pad;     // pad: P of the tile in the label-table kernel
     const uint8_t* tm;      // label-table kernel: the video's TMA descriptors (s2d_point_votes_tmaps) or null
     uint32_t ybase, pad2;   // t * H: first row of the frame in the descriptors' [T*H][W] view
+    const float* src;       // label-table kernel: tracks[q, t] of the tile
 };
 
 struct PvOut { int32_t* hout; int32_t* uout; int32_t L, pad; };
@@ -666,31 +667,36 @@ __device__ __forceinline__ bool pv_plan_next(PvPlan& pl, PvTile* rec, int lane, 
         if (tm && *reinterpret_cast<const int32_t*>(tm + 4 * 128) == 0) tm = nullptr;     // this video has no descriptors
         ti.tm = tm;
         ti.ybase = (uint32_t)t * (uint32_t)dp->H; ti.pad2 = 0;
-        *rec = ti;
         const int32_t* tsp = dp->tstart;
         const int64_t ts = t - (tsp ? tsp[q] : 0);           // frame index inside the stored track window
-        *src = dp->tracks + ((int64_t)q * dp->Ttr + ts) * P * 2;
+        ti.src = dp->tracks + ((int64_t)q * dp->Ttr + ts) * P * 2;
+        *rec = ti;
+        *src = ti.src;
     }
     ++pl.pi;
     return true;
 }
 
-template <int THREADS, int PPT, int CTAS>
+// PF = true: the tracks never touch shared memory. Each thread pulls its PPT points of the NEXT tile
+// into registers with 128-bit streaming loads right after the current tile's S1, so they fly while the
+// current tile waits for its table and votes; the buffer is then the table only (bigger bands), and the
+// serial chain of a tile shrinks to phase A -> table -> votes. Costs PPT * 2 registers.
+template <int THREADS, int PPT, int CTAS, bool PF>
 __global__ void __launch_bounds__(THREADS, CTAS)
 point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __restrict__ rowplan,
                        int total_rows, int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
                        int32_t* __restrict__ uniq, const uint8_t* __restrict__ tmaps) {
-    constexpr int BUF_BYTES = pv_buf_bytes(THREADS, PPT, CTAS);
+    constexpr int BUF_BYTES = PF ? pv_buf_bytes(THREADS, 0, CTAS) : pv_buf_bytes(THREADS, PPT, CTAS);
     constexpr int NWARPS = THREADS / 32;
     static_assert(BUF_BYTES >= PV_BM_WORDS * 4, "the fallback bitmap lives in the buffer");
-    static_assert(THREADS >= S2D_MAX_LABELS, "output phase uses one thread per histogram bin");
+    static_assert(S2D_MAX_LABELS % THREADS == 0 || THREADS % S2D_MAX_LABELS == 0, "output phase: whole warps per pass");
     static_assert(PPT % 2 == 0, "points are read two at a time");
     extern __shared__ __align__(128) uint8_t buf[];   // tracks of the tile, then its label table
     __shared__ int hist[S2D_MAX_LABELS];
     __shared__ __align__(8) uint2 wred[NWARPS];        // per-warp packed (min, max + 1) of (iy, ix)
     __shared__ uint32_t dummy[32];                     // all ones: target of points outside the band
     __shared__ __align__(8) uint64_t full, tabbar;
-    __shared__ PvTile tinfo[2];
+    __shared__ PvTile tinfo[3];                        // PF: ring of 3 (current, next being loaded, being planned); else 2
     __shared__ PvPlan plan_s;                          // scheduler state (kept out of the registers)
     __shared__ const float* nsrc_s;                    // tracks of the planned tile
     __shared__ int more_s;
@@ -717,24 +723,42 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         __syncwarp();
         if (lane == 0) { plan_s = pl; nsrc_s = src; more_s = ok ? 1 : 0; }
     };
+    int4 raw[PF ? PPT / 2 : 1];                        // PF: the tile's points, two per register quad
+    auto load_raw = [&](const PvTile* t) {
+        const int4* gp = reinterpret_cast<const int4*>(t->src);
+        const int np2 = t->pad >> 1;                   // 16-byte pairs of points in the tile
+#pragma unroll
+        for (int k = 0; k < (PF ? PPT / 2 : 1); ++k) {
+            const int idx = k * THREADS + tid;
+            raw[k] = make_int4(0, 0, 0, 0);
+            if (idx < np2) raw[k] = ld_stream(gp + idx);
+        }
+    };
     if (warp == 0) {
         plan(&tinfo[0]);
         __syncwarp();
-        if (lane == 0 && more_s) {
+        if (PF) {
+            plan(&tinfo[1]);
+        } else if (lane == 0 && more_s) {
             const uint32_t bytes = (uint32_t)tinfo[0].pad * 8u;
             mbar_expect_tx(&full, bytes);
             bulk_g2s(buf, nsrc_s, bytes, &full);
         }
     }
     __syncthreads();
+    if (PF && tinfo[0].valid) load_raw(&tinfo[0]);
 
     const uint32_t tab_s = smem_u32(buf);
     const uint32_t dummy_s = smem_u32(&dummy[lane]);
     uint32_t tabphase = 0;
+    int scur = 0, snxt = 1, spl = PF ? 2 : 1;         // slots of tile j, tile j + 1, and of the tile planned during tile j
     for (int j = 0;; ++j) {
-        const PvTile* ti = &tinfo[j & 1];
+        const PvTile* ti = &tinfo[scur];
         if (!ti->valid) break;                        // written before the barrier that precedes this read
-        mbar_wait(&full, j & 1);
+        if (!PF) {                                    // one warp polls the mbarrier, the rest park at the hardware barrier
+            if (warp == 0) mbar_wait(&full, j & 1);
+            __syncthreads();
+        }
         const uint32_t W = ti->W, H = ti->H;
         if (W > 65535u || H > 65535u) __trap();      // packed 16-bit coordinates (documented limit)
         const int n = ti->n;
@@ -743,17 +767,21 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         uint32_t pk[PPT];
         uint32_t mn = 0xFFFFFFFFu, mx = 0;
         const float4* sp = reinterpret_cast<const float4*>(buf);
+        auto point_pair = [&](int k) -> float4 {
+            if (PF) return make_float4(__int_as_float(raw[k].x), __int_as_float(raw[k].y), __int_as_float(raw[k].z), __int_as_float(raw[k].w));
+            return sp[k * THREADS + tid];
+        };
         if (n >= THREADS * PPT) {
 #pragma unroll
             for (int k = 0; k < PPT / 2; ++k) {
-                const float4 v = sp[k * THREADS + tid];
+                const float4 v = point_pair(k);
                 pk[2 * k] = pv_pack(v.x, v.y, W, H);
                 pk[2 * k + 1] = pv_pack(v.z, v.w, W, H);
             }
         } else {
 #pragma unroll
             for (int k = 0; k < PPT / 2; ++k) {
-                const float4 v = sp[k * THREADS + tid];
+                const float4 v = point_pair(k);
                 const int p0 = 2 * (k * THREADS + tid);
                 const uint32_t a = pv_pack(v.x, v.y, W, H), b = pv_pack(v.z, v.w, W, H);
                 pk[2 * k] = (p0 < n) ? a : PV_PK_INVALID;
@@ -773,6 +801,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
             if (lane == 0) wred[warp] = make_uint2((mny << 16) | mnx, (mxy << 16) | mxx);
         }
         __syncthreads();                              // S1: boxes complete, nobody reads the tracks any more
+        if (PF && tinfo[snxt].valid) load_raw(&tinfo[snxt]);       // planned during the previous tile
         uint32_t bmn = 0xFFFFFFFFu, bmx = 0;
 #pragma unroll
         for (int w = 0; w < NWARPS; ++w) {
@@ -831,10 +860,11 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                         }
                     }
                     if (warp == 0 && !planned) {      // overlap the plan's dependent loads with the table's flight
-                        plan(&tinfo[(j + 1) & 1]);
+                        plan(&tinfo[spl]);
                         planned = true;
                     }
-                    mbar_wait(&tabbar, tabphase);
+                    if (warp == 0) mbar_wait(&tabbar, tabphase);
+                    __syncthreads();
                     tabphase ^= 1u;
 
                     // phase B: e = (dy << 16) + dx for points of this band, >= lim otherwise (rows above
@@ -892,31 +922,34 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                 }
             }
         }
-        if (warp == 0 && !planned) plan(&tinfo[(j + 1) & 1]);
+        if (warp == 0 && !planned) plan(&tinfo[spl]);
         fence_proxy_async();                          // buffer atomics before the next tile's bulk copy
         __syncthreads();                              // S2: histogram complete, buffer free, next record visible
-        if (tid == 0 && more_s) {                     // the next tile's tracks fly during the output phase
-            const uint32_t bytes = (uint32_t)tinfo[(j + 1) & 1].pad * 8u;
+        if (!PF && tid == 0 && more_s) {              // the next tile's tracks fly during the output phase
+            const uint32_t bytes = (uint32_t)tinfo[snxt].pad * 8u;
             mbar_expect_tx(&full, bytes);
             bulk_g2s(buf, nsrc_s, bytes, &full);
         }
-        if (tid < S2D_MAX_LABELS) {                   // 8 warps: write hits, uniq = sum of the histogram
-            const int h = (tid == 255 && L <= 255) ? 0 : hist[tid];       // table mode parks non-first points in bin 255
-            if (tid < L) ti->hout[tid] = h;
-            hist[tid] = 0;
+#pragma unroll
+        for (int b = tid; b < S2D_MAX_LABELS; b += THREADS) {     // write hits, uniq = sum of the histogram
+            const int h = (b == 255 && L <= 255) ? 0 : hist[b];           // table mode parks non-first points in bin 255
+            if (b < L) ti->hout[b] = h;
+            hist[b] = 0;
             const int ws = __reduce_add_sync(0xffffffffu, h);
             if (lane == 0 && ws) atomicAdd(ti->uout, ws);      // *uout was cleared when the tile was planned
         }
-        // the next tile's S1 orders the histogram resets before its votes; tinfo[j & 1] is rewritten
-        // only after that S1 as well (the plan of tile j + 2 runs behind it)
+        // the next tile's S1 orders the histogram resets before its votes; this tile's record is
+        // rewritten only after that S1 as well (the next plan runs behind it)
+        if (PF) { const int t0 = scur; scur = snxt; snxt = spl; spl = t0; }
+        else { scur ^= 1; snxt ^= 1; spl = snxt; }
     }
 }
 
-template <int THREADS, int PPT, int CTAS>
+template <int THREADS, int PPT, int CTAS, bool PF>
 static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, const int4* rowplan,
                          int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq, const uint8_t* tmaps) {
-    const int smem = pv_buf_bytes(THREADS, PPT, CTAS) + 64;
-    auto kfn = point_votes_tab_kernel<THREADS, PPT, CTAS>;
+    const int smem = (PF ? pv_buf_bytes(THREADS, 0, CTAS) : pv_buf_bytes(THREADS, PPT, CTAS)) + 64;
+    auto kfn = point_votes_tab_kernel<THREADS, PPT, CTAS, PF>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1052,15 +1085,22 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
         S2D_CHECK_LAUNCH("pv_scan_kernel");
         const int tr = (int)total_rows;
         if (variant == 0) {      // label-table kernels
-            static const int ctas = getenv("S2D_PV_CTAS") ? atoi(getenv("S2D_PV_CTAS")) : 4;
-            if (max_P <= 256 * 4) return launch_pv_tab<256, 4, 5>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-            if (max_P <= 256 * 8) return launch_pv_tab<256, 8, 5>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+            static const int ctas = getenv("S2D_PV_CTAS") ? atoi(getenv("S2D_PV_CTAS")) : 6;
+            static const int pf = getenv("S2D_PV_PF") ? atoi(getenv("S2D_PV_PF")) : 0;
+            if (max_P <= 256 * 4) return launch_pv_tab<256, 4, 5, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+            if (max_P <= 256 * 8) return launch_pv_tab<256, 8, 5, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
             if (max_P <= 256 * 16) {
-                if (ctas == 5) return launch_pv_tab<256, 16, 5>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-                if (ctas == 3) return launch_pv_tab<256, 16, 3>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-                return launch_pv_tab<256, 16, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                if (pf) {
+                    if (ctas == 2) return launch_pv_tab<256, 16, 2, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                    if (ctas == 4) return launch_pv_tab<256, 16, 4, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                    return launch_pv_tab<256, 16, 3, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                }
+                if (ctas == 3) return launch_pv_tab<256, 16, 3, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                if (ctas == 5) return launch_pv_tab<128, 32, 5, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                if (ctas == 6) return launch_pv_tab<128, 32, 6, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                return launch_pv_tab<256, 16, 4, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
             }
-            return launch_pv_tab<256, 32, 3>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+            return launch_pv_tab<256, 32, 3, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
         }
         if (max_P <= 256 * 4) return launch_pv_tma<256, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);   // 4 CTAs/SM
         if (max_P <= 512 * 4) return launch_pv_tma<512, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
