@@ -664,7 +664,7 @@ __device__ __forceinline__ bool pv_plan_next(PvPlan& pl, PvTile* rec, int lane, 
         ti.n = np ? min(max(np[q], 0), P) : P;
         ti.valid = 1; ti.pad = P;
         const uint8_t* tm = tmaps ? tmaps + (size_t)pl.prp.w * S2D_PV_TMAP_BYTES : nullptr;
-        if (tm && *reinterpret_cast<const int32_t*>(tm + 4 * 128) == 0) tm = nullptr;     // this video has no descriptors
+        if (tm && *reinterpret_cast<const int32_t*>(tm + S2D_PV_TMAPS * 128) == 0) tm = nullptr;     // this video has no descriptors
         ti.tm = tm;
         ti.ybase = (uint32_t)t * (uint32_t)dp->H; ti.pad2 = 0;
         const int32_t* tsp = dp->tstart;
@@ -820,7 +820,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
             const uint8_t* tm = (bw + (x0 & 15u) <= 256u) ? ti->tm : nullptr;
             uint32_t pitch, R;
             if (tm) {
-                pitch = (bw + (x0 & 15u) + 63u) & ~63u;
+                pitch = (bw + (x0 & 15u) + 15u) & ~15u;
                 R = ((uint32_t)BUF_BYTES / pitch) & ~15u;                         // rows per band, whole boxes
             } else {
                 pitch = bw + 15u;
@@ -838,7 +838,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                         if (tid == 0) {
                             const uint32_t nbox = (rows + 15u) >> 4;
                             mbar_expect_tx(&tabbar, nbox * 16u * pitch);
-                            const uint8_t* map = tm + ((pitch >> 6) - 1u) * 128u;
+                            const uint8_t* map = tm + ((pitch >> 4) - 1u) * 128u;
                             for (uint32_t i = 0; i < nbox; ++i)
                                 tma_box_2d(tab_s + i * 16u * pitch, map, &tabbar, (int)(x0 & ~15u), (int)(ti->ybase + y0 + b0 + 16u * i));
                         } else {
@@ -1013,9 +1013,9 @@ extern "C" int s2d_point_votes_work_ints(int64_t total_rows, int64_t* out) {
 }
 
 // Host side: TMA descriptors of the videos' label maps for the label-table kernel. Per video
-// S2D_PV_TMAP_BYTES: four CUtensorMap (u8 [T*H][W], boxes of 16 rows x 64/128/192/256 pixels) and a
-// 128-byte trailer whose first int is 1 when the descriptors are usable (W and the base address
-// are multiples of 16, W >= 64), 0 otherwise (that video's tables are then fetched row by row).
+// S2D_PV_TMAP_BYTES: S2D_PV_TMAPS CUtensorMap (u8 [T*H][W], boxes of 16 rows x 16, 32, ... 256 pixels)
+// and a 128-byte trailer whose first int is 1 when the descriptors are usable (W and the base
+// address are multiples of 16, W >= 16), 0 otherwise (that video's tables are fetched row by row).
 typedef CUresult (*PvEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1035,17 +1035,17 @@ extern "C" int s2d_point_votes_tmaps(const s2d_video_desc* host_descs, int nvide
     for (int v = 0; v < nvideos; ++v) {
         const s2d_video_desc& d = host_descs[v];
         uint8_t* blk = out + (size_t)v * S2D_PV_TMAP_BYTES;
-        if (!d.labels || d.W < 64 || (d.W & 15) || (((uintptr_t)d.labels) & 15) || d.T <= 0 || d.H <= 0) continue;
+        if (!d.labels || d.W < 16 || (d.W & 15) || (((uintptr_t)d.labels) & 15) || d.T <= 0 || d.H <= 0) continue;
         bool ok = true;
-        for (int k = 0; k < 4 && ok; ++k) {
-            if (64 * (k + 1) > d.W) {         // box wider than the frame: reuse the widest one that fits (never selected
-                memcpy(blk + k * 128, blk + (k - 1) * 128, 128);          // for bw <= W, but keep the slot well formed)
+        for (int k = 0; k < S2D_PV_TMAPS && ok; ++k) {
+            if (16 * (k + 1) > d.W) {         // box wider than the frame: never selected (bw <= W); keep the slot well formed
+                memcpy(blk + k * 128, blk + (k - 1) * 128, 128);
                 continue;
             }
             CUtensorMap map;
             cuuint64_t dims[2] = {(cuuint64_t)d.W, (cuuint64_t)d.T * (cuuint64_t)d.H};
             cuuint64_t strides[1] = {(cuuint64_t)d.W};
-            cuuint32_t box[2] = {(cuuint32_t)(64 * (k + 1)), 16u};
+            cuuint32_t box[2] = {(cuuint32_t)(16 * (k + 1)), 16u};
             cuuint32_t estr[2] = {1, 1};
             CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)d.labels, dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1053,7 +1053,7 @@ extern "C" int s2d_point_votes_tmaps(const s2d_video_desc* host_descs, int nvide
             if (r != CUDA_SUCCESS) ok = false;
             else memcpy(blk + k * 128, &map, 128);
         }
-        if (ok) *reinterpret_cast<int32_t*>(blk + 4 * 128) = 1;
+        if (ok) *reinterpret_cast<int32_t*>(blk + S2D_PV_TMAPS * 128) = 1;
     }
     return 0;
 }
