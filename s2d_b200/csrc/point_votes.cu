@@ -622,15 +622,18 @@ __device__ __forceinline__ bool pv_plan_next(PvPlan& pl, PvTile* rec, int lane, 
                                              int32_t* __restrict__ uniq, const uint8_t* __restrict__ tmaps,
                                              const float** src) {
     if (pl.pi == pl.pi_end) {
+        // consecutive tiles per claim: up to PV_CHUNK (same query, neighbouring frames: label maps stay hot
+        // in L2), fewer when the launch is small so that every CTA gets work
+        const int chunk = max(1, min(PV_CHUNK, total / (int)(gridDim.x * 2u)));
         int c = 0;
-        if (lane == 0) c = atomicAdd(&ctrl[0], PV_CHUNK);
+        if (lane == 0) c = atomicAdd(&ctrl[0], chunk);
         c = __shfl_sync(0xffffffffu, c, 0);
         if (c >= total) {
             if (lane == 0) rec->valid = 0;
             return false;
         }
         pl.pi = c;
-        pl.pi_end = min(c + PV_CHUNK, total);
+        pl.pi_end = min(c + chunk, total);
         int lo = 0, hi = total_rows;     // 32-ary search: last row with tile0 <= pi
         while (hi - lo > 32) {
             const int step = (hi - lo + 31) >> 5;
@@ -1087,8 +1090,8 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
         if (variant == 0) {      // label-table kernels
             static const int ctas = getenv("S2D_PV_CTAS") ? atoi(getenv("S2D_PV_CTAS")) : 6;
             static const int pf = getenv("S2D_PV_PF") ? atoi(getenv("S2D_PV_PF")) : 0;
-            if (max_P <= 256 * 4) return launch_pv_tab<256, 4, 5, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-            if (max_P <= 256 * 8) return launch_pv_tab<256, 8, 5, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+            if (max_P <= 128 * 8) return launch_pv_tab<128, 8, 6, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+            if (max_P <= 128 * 16) return launch_pv_tab<128, 16, 6, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
             if (max_P <= 256 * 16) {
                 if (pf) {
                     if (ctas == 2) return launch_pv_tab<256, 16, 2, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
