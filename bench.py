@@ -254,10 +254,19 @@ def main():
     k2_ms = stage_ms["point_votes"]
     achieved = alg_bytes / (k2_ms / 1000.0) / 1e9
     vr_bytes = sum(d.Nm * d.T * d.P + 8 * d.Nm * d.T for d in batch.host_descs)
-    pv_name = ("point_votes_tma_kernel (persistent, cp.async.bulk ring)" if batch.use_tma and batch.vec4 and P <= 8192
+    pv_name = ("point_votes_tab_kernel (persistent; tile's tracks by cp.async.bulk, bbox of the label map by TMA "
+               "boxes into the same smem buffer, one shared atomic per point)" if batch.use_tma and batch.vec4 and P <= 8192
                else "point_votes_kernel (one CTA per tile)")
+    # DRAM traffic of the same launch from the committed `ncu --set full` capture (profiles/), if it
+    # was taken on this workload: dram__bytes_read.sum + dram__bytes_write.sum
+    traffic = None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "k2_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("workload") == args.workload and int(tj.get("videos", -1)) == nvid and tj.get("point_order") == args.point_order:
+            traffic = float(tj["dram_bytes_per_launch"])
     roofline = {"kernel": pv_name, "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k2_ms, "tiles_per_launch": tiles,
                 "share_of_step": k2_ms / (ms / args.steps),
                 "vis_reduce": {"achieved": vr_bytes / (stage_ms["vis_reduce"] / 1000.0) / 1e9,

@@ -153,6 +153,21 @@ int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max_T, int max
                     int vec4_ok, int64_t total_rows, const int32_t* rowinfo, const int32_t* vidinfo,
                     int32_t* work, const void* label_tmaps, int32_t* hits, int32_t* uniq, void* stream);
 
+/* K3d. Appearance events of visibility curves V f32 [N][T] (device): moving average of odd length
+ * smoothing_window (reflect padding), `>= thresh`, morphological opening with window
+ * min_run_length (erosion then dilation as reflect-padded min / max pooling; for even windows each
+ * pooling shortens the signal by one sample, like the reference), then the 0->1 / 1->0 transitions
+ * of the opened signal compacted per row with warp ballots: nstart[row], nend[row] and the first
+ * max_events frame indices of each kind in starts / ends [N][max_events]. opened (optional,
+ * u8 [N][T], first T2 columns written) receives the opened signal. Replaces
+ * extract_appearance_events (cotracker_occlusions.py:166-223 == cotracker_matching.py:212-269);
+ * bit-exact for smoothing_window == 1 (the default), float32 fma accumulation otherwise.
+ * s2d_boolean_visibility: out[i] = V[i] >= threshold (cotracker_occlusions.py:226-240). */
+int s2d_appearance_events(const float* V, int N, int T, int smoothing_window, float thresh,
+                          int min_run_length, int max_events, int32_t* nstart, int32_t* nend,
+                          int32_t* starts, int32_t* ends, uint8_t* opened, void* stream);
+int s2d_boolean_visibility(const float* V, int64_t n, float threshold, uint8_t* out, void* stream);
+
 /* K4a. Scores and selection per candidate query: iou = hits/uniq (double), match bit when
  * iou > matching_threshold (cotracker_matching.py:710), one-to-many flag when >= one2x_frames
  * frames hold more than one mask with iou > one2x_iou (cotracker_matching.py:1082-1111).
