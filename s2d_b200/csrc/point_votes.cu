@@ -902,9 +902,16 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                     // points that were not first and is dropped in the output phase (L <= 255 here).
                     constexpr int G = (PPT < 8 || CTAS >= 5) ? 4 : 8;
                     const uint32_t hist_s = smem_u32(hist);
+                    const bool banded = bh > R;        // several bands: most groups of a pass are outside its band
 #pragma unroll
                     for (int g = 0; g < PPT; g += G) {
                         uint32_t old[G], sh[G];
+                        if (banded) {                  // points are close to raster order: skip groups with no point in the band
+                            bool any = false;
+#pragma unroll
+                            for (int k = 0; k < G; ++k) any |= (pk[g + k] - pk0) < lim;
+                            if (!__any_sync(0xffffffffu, any)) continue;
+                        }
 #pragma unroll
                         for (int k = 0; k < G; ++k) {
                             const uint32_t e = pk[g + k] - pk0;

@@ -153,3 +153,35 @@ def color_frames_to_labels(rgb_frames: np.ndarray):
     if int(ncol_h.max()) > 255:
         raise ValueError("s2d_b200 supports at most 255 masks per frame")
     return labels, ncol_h
+
+
+def appearance_events(vis: torch.Tensor, smoothing_window: int = 1, thresh: float = 0.95, min_run_length: int = 4):
+    """K3d through the C ABI: {row: list(zip(starts, ends))} exactly as the reference builds it."""
+    from s2d_b200 import _lib
+    dev = device()
+    v = vis.to(dev, torch.float32).contiguous()
+    n, T = v.shape
+    p1, p2 = (int(smoothing_window) - 1) // 2, (int(min_run_length) - 1) // 2
+    if p1 >= T or p2 >= T or p2 >= T + 2 * p2 - int(min_run_length) + 1:
+        raise RuntimeError("Padding size should be less than the corresponding input dimension")   # what torch raises
+    cap = T // 2 + 2                                # a row cannot hold more transitions of one kind
+    ns = torch.empty(n, dtype=torch.int32, device=dev)
+    ne = torch.empty(n, dtype=torch.int32, device=dev)
+    st = torch.empty((n, cap), dtype=torch.int32, device=dev)
+    en = torch.empty((n, cap), dtype=torch.int32, device=dev)
+    _lib.call("s2d_appearance_events", v.data_ptr(), n, T, int(smoothing_window), float(np.float32(thresh)),
+              int(min_run_length), cap, ns.data_ptr(), ne.data_ptr(), st.data_ptr(), en.data_ptr(), None,
+              torch.cuda.current_stream(dev).cuda_stream)
+    ns, ne, st, en = ns.cpu().numpy(), ne.cpu().numpy(), st.cpu().numpy(), en.cpu().numpy()
+    return {i: list(zip(st[i, :ns[i]].tolist(), en[i, :ne[i]].tolist())) for i in range(n)}
+
+
+def boolean_visibility(vis: torch.Tensor, threshold: float = 0.3) -> torch.Tensor:
+    from s2d_b200 import _lib
+    dev = device()
+    v = vis.to(dev, torch.float32).contiguous()
+    out = torch.empty(v.shape, dtype=torch.uint8, device=dev)
+    if v.numel():
+        _lib.call("s2d_boolean_visibility", v.data_ptr(), v.numel(), float(np.float32(threshold)), out.data_ptr(),
+                  torch.cuda.current_stream(dev).cuda_stream)
+    return out.to(torch.bool).to(vis.device)

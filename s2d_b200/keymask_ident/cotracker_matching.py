@@ -142,20 +142,15 @@ def compute_point_mask_intersection(pointmask: torch.Tensor, mask: torch.Tensor,
 
 
 def extract_appearance_events(vis: torch.Tensor, smoothing_window: int = 1, thresh: float = 0.95, min_run_length: int = 4):
-    """Exported by the reference but never called on the keymask path (cotracker_matching.py:212-269):
-    moving average, threshold, morphological opening, (appear, disappear) transitions per row."""
-    import torch.nn.functional as F
-    n = vis.shape[0]
-    pad = (smoothing_window - 1) // 2
-    kern = torch.ones(1, 1, smoothing_window, device=vis.device) / smoothing_window
-    smooth = F.conv1d(F.pad(vis.unsqueeze(1), (pad, pad), mode="reflect"), kern).squeeze(1)
-    b = (smooth >= thresh).to(vis.dtype)
-    k, p2 = min_run_length, (min_run_length - 1) // 2
-    er = 1.0 - F.max_pool1d(F.pad((1.0 - b).unsqueeze(1), (p2, p2), mode="reflect"), kernel_size=k, stride=1).squeeze(1)
-    op = F.max_pool1d(F.pad(er.unsqueeze(1), (p2, p2), mode="reflect"), kernel_size=k, stride=1).squeeze(1)
-    d = op[:, 1:] - op[:, :-1]
-    return {i: list(zip(((d[i] == 1).nonzero(as_tuple=False).squeeze(1) + 1).tolist(),
-                        ((d[i] == -1).nonzero(as_tuple=False).squeeze(1) + 1).tolist())) for i in range(n)}
+    """{row: [(appear_frame, disappear_frame), ...]} of (N, T) visibility curves; exported by the
+    reference but never called on the keymask path (cotracker_matching.py:212-269); K3d
+    appearance_events_kernel."""
+    return _engine.appearance_events(vis, smoothing_window, thresh, min_run_length)
+
+
+def boolean_visibility(vis: torch.Tensor, threshold: float = 0.3) -> torch.Tensor:
+    """vis >= threshold on the GPU (cotracker_matching.py:272-286)."""
+    return _engine.boolean_visibility(vis, threshold)
 
 
 def crop_bool_tensor(bool_arr: np.ndarray):

@@ -52,7 +52,14 @@ def get_segmentation_mask(masks: torch.Tensor, query_frame_idx: int, object_id: 
 
 
 def boolean_visibility(vis: torch.Tensor, threshold: float = 0.3) -> torch.Tensor:
-    return vis >= threshold
+    """vis >= threshold on the GPU (cotracker_occlusions.py:226-240)."""
+    return _engine.boolean_visibility(vis, threshold)
+
+
+def extract_appearance_events(vis: torch.Tensor, smoothing_window: int = 1, thresh: float = 0.95, min_run_length: int = 4):
+    """{row: [(appear_frame, disappear_frame), ...]} of (N, T) visibility curves
+    (cotracker_occlusions.py:166-223); K3d appearance_events_kernel."""
+    return _engine.appearance_events(vis, smoothing_window, thresh, min_run_length)
 
 
 def extract_object_visibility_data(video_path, masks_path, video_output_dir, visibility_maps_base_output_dir, debug=False):

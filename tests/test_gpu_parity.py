@@ -402,3 +402,25 @@ def test_windowed_track_storage(P):
             h, u = ko.point_votes(full[q], labels, int(v0[q]), int(v1[q]), nbins=5)
             assert np.array_equal(uniq[q, inside], u) and np.array_equal(hits[q, inside], h), q
         assert (uniq[q, ~inside] == -5).all() and (hits[q, ~inside] == -5).all(), q
+
+
+def test_appearance_events_vs_reference_golden():
+    """K3d (appearance_events_kernel, boolean_visibility_kernel) through the drop-in functions of both
+    modules against vectors produced by the unmodified reference (oracle/make_golden_events.py)."""
+    import os
+    from s2d_b200.keymask_ident import cotracker_matching as cm, cotracker_occlusions as co
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "events.npz"))
+    for name in g["names"]:
+        V = torch.from_numpy(g[f"{name}__V"])
+        sw, th, k = g[f"{name}__params"]
+        for mod in (co, cm):
+            ev = mod.extract_appearance_events(V, smoothing_window=int(sw), thresh=float(th), min_run_length=int(k))
+            npairs, pairs = g[f"{name}__npairs"], g[f"{name}__pairs"]
+            assert [len(ev[i]) for i in range(V.shape[0])] == npairs.tolist(), name
+            flat = [p for i in range(V.shape[0]) for p in ev[i]]
+            assert np.array_equal(np.asarray(flat, np.int32).reshape(-1, 2), pairs), name
+            assert np.array_equal(mod.boolean_visibility(V, threshold=float(th)).numpy(), g[f"{name}__bool"]), name
+        ev_o, _ = ko.appearance_events(g[f"{name}__V"], int(sw), float(th), int(k))
+        assert ev_o == ev, name
+    with pytest.raises(RuntimeError):
+        co.extract_appearance_events(torch.zeros(2, 1), min_run_length=4)      # torch: padding >= input size

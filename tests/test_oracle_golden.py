@@ -77,3 +77,18 @@ def test_dense_port_matches_reference_pairs(golden_case):
     V = dense_port.visibility_rows(torch.from_numpy(vis.astype(bool))).numpy()
     ref = np.asarray([r["visibility"] for r in g["visibility_rows"]], np.float32)
     assert np.array_equal(V, ref)
+
+
+def test_appearance_events_oracle_vs_reference_golden():
+    """numpy restatement of extract_appearance_events against vectors produced by the unmodified
+    reference function (oracle/make_golden_events.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "events.npz"))
+    for name in g["names"]:
+        V = g[f"{name}__V"]
+        sw, th, k = g[f"{name}__params"]
+        ev, _ = ko.appearance_events(V, int(sw), float(th), int(k))
+        npairs, pairs = g[f"{name}__npairs"], g[f"{name}__pairs"]
+        assert [len(ev[i]) for i in range(V.shape[0])] == npairs.tolist(), name
+        flat = [p for i in range(V.shape[0]) for p in ev[i]]
+        assert np.array_equal(np.asarray(flat, np.int32).reshape(-1, 2), pairs), name
