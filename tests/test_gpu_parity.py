@@ -424,3 +424,26 @@ def test_appearance_events_vs_reference_golden():
         assert ev_o == ev, name
     with pytest.raises(RuntimeError):
         co.extract_appearance_events(torch.zeros(2, 1), min_run_length=4)      # torch: padding >= input size
+
+
+@pytest.mark.parametrize("n1,n2,H,W", [(5, 7, 33, 47), (40, 130, 64, 80), (130, 70, 96, 128), (1, 1, 8, 8)])
+def test_mask_iou_consumers_vs_reference_formulas(n1, n2, H, W):
+    """f3: mask_iou_matrix / BatchIoU on the K1 kernels against the reference's own torch formulas
+    (mask2former_video/engine/train_loop.py:378-388, cutler/tools/get_self_training_ann.py:80-89) on CPU."""
+    from s2d_b200.mask_iou import BatchIoU, mask_iou_matrix
+    rng = np.random.default_rng(n1 * 1000 + n2)
+    x = torch.from_numpy((rng.random((n1, H, W)) < 0.3).astype(np.float32))
+    y = torch.from_numpy((rng.random((n2, H, W)) < 0.4).astype(np.float32))
+    y[0] = 0                                                   # empty mask: 0/0 -> nan like the reference
+    xf, yf = x.reshape(n1, -1), y.reshape(n2, -1)
+    inter = xf @ yf.t()
+    sx, sy = xf.sum(1)[:, None].expand(n1, n2), yf.sum(1)[None, :].expand(n1, n2)
+    for mode, want in (("iou", inter / (sx + sy - inter)), ("ioy", inter / sy)):
+        got = mask_iou_matrix(x, y, mode=mode)
+        assert got.dtype == torch.float32 and torch.equal(torch.isnan(got), torch.isnan(want))
+        assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(want)), mode
+    p1, p2 = torch.from_numpy(rng.random((n1, H, W)).astype(np.float32)), torch.from_numpy(rng.random((n2, H, W)).astype(np.float32))
+    m1, m2 = (p1 > 0.5), (p2 > 0.5)
+    a, b = m1[:, None].expand(-1, n2, -1, -1), m2[None].expand(n1, -1, -1, -1)
+    want = torch.sum(a * (a == b), dim=[-1, -2]).to(torch.float) / torch.sum(a + b, dim=[-1, -2])
+    assert torch.equal(BatchIoU(p1, p2), want)
