@@ -168,6 +168,18 @@ int s2d_appearance_events(const float* V, int N, int T, int smoothing_window, fl
                           int32_t* starts, int32_t* ends, uint8_t* opened, void* stream);
 int s2d_boolean_visibility(const float* V, int64_t n, float threshold, uint8_t* out, void* stream);
 
+/* f2. COCO run-length encoding of N binary masks (u8 [N][H][W] row-major, non-zero = set) with area
+ * and bounding box: what annotations.py:94-106 and convert_results_to_annotations.py:70-81 obtain from
+ * pycocotools (maskApi.c rleEncode / rleArea / rleToBbox). counts [N][max_runs] receives the run
+ * lengths in COLUMN-major order starting with a run of zeros (possibly of length 0); nruns[n] is the
+ * true number of runs - when it exceeds max_runs only the first max_runs were written and the caller
+ * repeats the call with a larger bound. area[n] = set pixels; bbox[n] = (xmin, ymin, xmax, ymax)
+ * inclusive, (INT_MAX, INT_MAX, -1, -1) for an empty mask. work: s2d_rle_work_ints() int32. The
+ * base-48 string packing of the counts (rleToString) is a host-side pass over the short count list. */
+int s2d_rle_work_ints(int N, int H, int W, int max_runs, int64_t* out);
+int s2d_rle_encode(const uint8_t* masks, int N, int H, int W, int max_runs, int32_t* work,
+                   int32_t* counts, int32_t* nruns, int32_t* area, int32_t* bbox, void* stream);
+
 /* K4a. Scores and selection per candidate query: iou = hits/uniq (double), match bit when
  * iou > matching_threshold (cotracker_matching.py:710), one-to-many flag when >= one2x_frames
  * frames hold more than one mask with iou > one2x_iou (cotracker_matching.py:1082-1111).

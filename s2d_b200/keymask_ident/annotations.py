@@ -1,31 +1,29 @@
 """Drop-in for keymask_ident/annotations.py (stage E): single-video YTVIS json from the
-`cluster_*/group_*/frame{f}_mask{m}.png` tree. The reference calls pycocotools for the RLE;
-pycocotools is used when importable, otherwise the same COCO RLE format is produced by the
-restatement in `coco_rle` below (maskApi.c rleEncode / rleToString / rleArea / rleToBbox).
-Parity at the RLE boundary is unpinned in the build container (pycocotools is not installed)."""
+`cluster_*/group_*/frame{f}_mask{m}.png` tree. The reference calls pycocotools per keymask
+(mask_util.encode / area / toBbox, annotations.py:94-106); here all keymasks of a video are encoded
+in one batch on the GPU (s2d_rle_encode: column-major run lengths, area, bounding box) and only the
+base-48 string packing of the short count lists (maskApi.c rleToString) runs on the host.
+pycocotools is not installable in the build container, so parity at the RLE boundary is pinned by
+the published algorithm and by decode round trips only (tests/test_dropin_gpu.py)."""
 from __future__ import annotations
 
+import ctypes as C
 import json
 import os
 import re
 
 import numpy as np
+import torch
 from PIL import Image
+
+try:
+    from . import _engine
+except ImportError:
+    import _engine
 
 
 class coco_rle:
-    @staticmethod
-    def counts(mask: np.ndarray):
-        """column-major run lengths starting with a run of zeros."""
-        flat = np.asarray(mask, dtype=np.uint8).reshape(-1, order="F")
-        if flat.size == 0:
-            return [0]
-        change = np.nonzero(flat[1:] != flat[:-1])[0] + 1
-        edges = np.concatenate(([0], change, [flat.size]))
-        runs = np.diff(edges).tolist()
-        if flat[0] != 0:
-            runs = [0] + runs
-        return runs
+    """COCO compressed-RLE strings (maskApi.c rleToString / rleFrString) and the GPU batch encoder."""
 
     @staticmethod
     def to_string(cnts):
@@ -63,31 +61,42 @@ class coco_rle:
         return cnts
 
     @staticmethod
-    def encode(mask: np.ndarray):
-        h, w = mask.shape[:2]
-        return {"size": [int(h), int(w)], "counts": coco_rle.to_string(coco_rle.counts(mask.reshape(h, w)))}
-
-    @staticmethod
-    def area(mask: np.ndarray):
-        return int(np.count_nonzero(mask))
-
-    @staticmethod
-    def bbox(mask: np.ndarray):
-        m = np.asarray(mask).reshape(mask.shape[0], mask.shape[1]) != 0
-        if not m.any():
-            return [0.0, 0.0, 0.0, 0.0]
-        ys, xs = np.nonzero(m.any(axis=1))[0], np.nonzero(m.any(axis=0))[0]
-        return [float(xs[0]), float(ys[0]), float(xs[-1] - xs[0] + 1), float(ys[-1] - ys[0] + 1)]
-
-
-def _encode(binary_mask):
-    try:
-        from pycocotools import mask as mask_util
-        rle = mask_util.encode(np.array(binary_mask[..., None], order="F", dtype="uint8"))[0]
-        rle["counts"] = rle["counts"].decode("ascii")
-        return rle, int(mask_util.area(rle)), mask_util.toBbox(rle).tolist()
-    except ImportError:
-        return coco_rle.encode(binary_mask), coco_rle.area(binary_mask), coco_rle.bbox(binary_mask)
+    def encode_batch(masks):
+        """masks [N,H,W] (bool / uint8, numpy or torch) -> list of (rle dict, area int, bbox [x,y,w,h] floats),
+        what mask_util.encode / area / toBbox return per mask."""
+        from s2d_b200 import _lib
+        dev = _engine.device()
+        m = torch.as_tensor(np.asarray(masks)) if not torch.is_tensor(masks) else masks
+        m = (m != 0).to(dev, torch.uint8).contiguous()
+        n, h, w = m.shape
+        if n == 0:
+            return []
+        st = torch.cuda.current_stream(dev).cuda_stream
+        max_runs = min(h * w + 1, 8 * w + 64)
+        while True:
+            need = C.c_int64()
+            _lib.call("s2d_rle_work_ints", n, h, w, max_runs, C.byref(need))
+            work = torch.empty(need.value, dtype=torch.int32, device=dev)
+            counts = torch.empty((n, max_runs), dtype=torch.int32, device=dev)
+            nruns = torch.empty(n, dtype=torch.int32, device=dev)
+            area = torch.empty(n, dtype=torch.int32, device=dev)
+            bbox = torch.empty((n, 4), dtype=torch.int32, device=dev)
+            _lib.call("s2d_rle_encode", m.data_ptr(), n, h, w, max_runs, work.data_ptr(), counts.data_ptr(),
+                      nruns.data_ptr(), area.data_ptr(), bbox.data_ptr(), st)
+            nr = nruns.cpu().numpy()
+            if int(nr.max()) <= max_runs:
+                break
+            max_runs = int(nr.max())                   # a mask with more runs than the first guess: once more
+        cn, ar, bb = counts.cpu().numpy(), area.cpu().numpy(), bbox.cpu().numpy()
+        out = []
+        for i in range(n):
+            rle = {"size": [int(h), int(w)], "counts": coco_rle.to_string(cn[i, :nr[i]].tolist())}
+            if ar[i] == 0:
+                box = [0.0, 0.0, 0.0, 0.0]
+            else:
+                box = [float(bb[i, 0]), float(bb[i, 1]), float(bb[i, 2] - bb[i, 0] + 1), float(bb[i, 3] - bb[i, 1] + 1)]
+            out.append((rle, int(ar[i]), box))
+        return out
 
 
 def write_annotation_for_video(video_path, cluster_masks_path, annotation_output_path, visibility_data):
@@ -108,6 +117,7 @@ def write_annotation_for_video(video_path, cluster_masks_path, annotation_output
     with open(os.path.join(cluster_masks_path, "video_one2x_data.json")) as f:
         one2x_data = json.load(f)
     annotations, ann_id, n = [], 1, len(video_files)
+    pending = []
     for cname in cluster_dirs:
         cdir = os.path.join(cluster_masks_path, cname)
         groups = sorted(d for d in os.listdir(cdir) if os.path.isdir(os.path.join(cdir, d)) and d.startswith("group_"))
@@ -127,12 +137,20 @@ def write_annotation_for_video(video_path, cluster_masks_path, annotation_output
                 if not m or int(m.group(1)) >= n:
                     continue
                 binary = np.array(Image.open(os.path.join(gdir, mf)).convert("L")) > 0
-                segs[int(m.group(1))], areas[int(m.group(1))], boxes[int(m.group(1))] = _encode(binary)
+                pending.append((segs, areas, boxes, int(m.group(1)), binary))     # encoded in one GPU batch below
             annotations.append({"video_id": 1, "iscrowd": 0, "height": height, "width": width, "length": n,
                                 "segmentations": segs, "bboxes": boxes, "areas": areas, "category_id": 1,
                                 "id": ann_id, "one2x": round(float(one2x_data[cname][gname]["avg_one2x"]), 2),
                                 "visibility_ranges": ranges})
             ann_id += 1
+    # later files of a group overwrite earlier ones on the same frame, like the reference's loop
+    by_shape = {}
+    for item in pending:
+        by_shape.setdefault(item[4].shape, []).append(item)
+    for items in by_shape.values():
+        enc = coco_rle.encode_batch(np.stack([it[4] for it in items]))
+        for (segs, areas, boxes, fidx, _), (rle, area, box) in zip(items, enc):
+            segs[fidx], areas[fidx], boxes[fidx] = rle, area, box
     os.makedirs(annotation_output_path, exist_ok=True)
     with open(os.path.join(annotation_output_path, f"{video_name}.json"), "w") as f:
         json.dump({"videos": [video], "annotations": annotations,

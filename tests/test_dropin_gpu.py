@@ -152,3 +152,79 @@ def test_dropin_helpers_on_gpu():
     assert ivw.get_visible_ranges(maj) == [(1, 2), (5, 5), (7, 9)]
     assert ivw.get_visible_ranges(torch.zeros(7)) == []
     assert ivw.get_visible_ranges(torch.ones(40)) == [(0, 39)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W", [(1, 1), (31, 33), (64, 96), (97, 131), (480, 854), (720, 1280)])
+def test_rle_encode_gpu_vs_restatement(H, W):
+    """f2: s2d_rle_encode (column-major runs, area, bbox) against the numpy restatement of maskApi.c and a
+    decode round trip; masks that start set, empty / full masks, ragged sizes."""
+    import numpy as np
+    from oracle import coco_rle as cr
+    from s2d_b200.keymask_ident.annotations import coco_rle
+    rng = np.random.default_rng(H * 7 + W)
+    yy, xx = np.mgrid[0:H, 0:W]
+    masks = [np.zeros((H, W), bool), np.ones((H, W), bool), rng.random((H, W)) < 0.5,
+             ((xx - W / 2) ** 2 / max(1, (W / 3) ** 2) + (yy - H / 2) ** 2 / max(1, (H / 4) ** 2)) <= 1.0,
+             (xx + yy) % 7 < 3]
+    m0 = np.zeros((H, W), bool); m0[0, 0] = True; masks.append(m0)
+    m1 = np.zeros((H, W), bool); m1[-1, -1] = True; masks.append(m1)
+    enc = coco_rle.encode_batch(np.stack(masks))
+    for m, (rle, area, box) in zip(masks, enc):
+        assert rle["size"] == [H, W]
+        c = coco_rle.from_string(rle["counts"])
+        assert c == cr.counts(m)
+        assert np.array_equal(cr.decode(c, H, W), m.astype(np.uint8))
+        assert area == cr.area(m) == int(m.sum()) and box == cr.bbox(m)
+
+
+@pytest.mark.gpu
+def test_write_annotation_for_video_roundtrip(tmp_path):
+    """stage E drop-in on a small cluster/group tree: YTVIS schema of the reference (annotations.py:28-140),
+    segmentations decode back to the PNG masks, areas / boxes match."""
+    import json
+    import numpy as np
+    from PIL import Image
+    from oracle import coco_rle as cr
+    from s2d_b200.keymask_ident import annotations as ann
+    H, W, T = 48, 70, 5
+    vdir = tmp_path / "ytvis2021" / "train" / "JPEGImages" / "vidA"
+    vdir.mkdir(parents=True)
+    for t in range(T):
+        Image.fromarray(np.zeros((H, W, 3), np.uint8)).save(vdir / f"{t:05d}.jpg")
+    cdir = tmp_path / "seg" / "vidA"
+    rng = np.random.default_rng(0)
+    truth = {}
+    for cname, groups in (("cluster_0", ("group_0", "group_1")), ("cluster_1", ("group_0",))):
+        for g in groups:
+            (cdir / cname / g).mkdir(parents=True)
+            for t in rng.choice(T, size=3, replace=False):
+                m = np.zeros((H, W), np.uint8)
+                y0, x0 = rng.integers(0, H - 10), rng.integers(0, W - 10)
+                m[y0:y0 + rng.integers(2, 10), x0:x0 + rng.integers(2, 10)] = 255
+                Image.fromarray(m).save(cdir / cname / g / f"frame{t}_mask{int(rng.integers(1, 5))}.png")
+                truth[(cname, g, int(t))] = m > 0
+        Image.fromarray(np.zeros((H, W), np.uint8)).save(cdir / cname / f"{cname.replace('_', '')}_frame0_mask1.png")
+    one2x = {"cluster_0": {"avg_one2x_cluster": 0.1, "group_0": {"avg_one2x": 0.126, "one2x_counts": 3, "noisy": False},
+                           "group_1": {"avg_one2x": 0.0, "one2x_counts": 3, "noisy": False}},
+             "cluster_1": {"avg_one2x_cluster": 0.0, "group_0": {"avg_one2x": 1.0, "one2x_counts": 3, "noisy": True}}}
+    (cdir / "video_one2x_data.json").write_text(json.dumps(one2x))
+    vis = {"video_name": "vidA", "clusters": [{"cluster_id": 0, "ranges": [[0, 2]]}, {"cluster_id": 1, "ranges": [[3, 4]]}]}
+    out = tmp_path / "ann"
+    ann.write_annotation_for_video(str(vdir), str(cdir), str(out), vis)
+    d = json.loads((out / "vidA.json").read_text())
+    assert d["videos"][0]["height"] == H and d["videos"][0]["width"] == W and d["videos"][0]["length"] == T
+    assert d["categories"] == [{"supercategory": "object", "id": 1, "name": "fg"}]
+    assert [a["id"] for a in d["annotations"]] == [1, 2, 3]
+    order = [("cluster_0", "group_0"), ("cluster_0", "group_1"), ("cluster_1", "group_0")]
+    for a, (cname, g) in zip(d["annotations"], order):
+        assert a["one2x"] == round(one2x[cname][g]["avg_one2x"], 2)
+        assert a["visibility_ranges"] == vis["clusters"][int(cname[-1])]["ranges"]
+        for t in range(T):
+            m = truth.get((cname, g, t))
+            if m is None:
+                assert a["segmentations"][t] is None and a["bboxes"][t] is None and a["areas"][t] is None
+            else:
+                seg = a["segmentations"][t]
+                assert np.array_equal(cr.decode(ann.coco_rle.from_string(seg["counts"]), H, W), m.astype(np.uint8))
+                assert a["areas"][t] == int(m.sum()) and a["bboxes"][t] == cr.bbox(m)

@@ -92,3 +92,23 @@ def test_appearance_events_oracle_vs_reference_golden():
         assert [len(ev[i]) for i in range(V.shape[0])] == npairs.tolist(), name
         flat = [p for i in range(V.shape[0]) for p in ev[i]]
         assert np.array_equal(np.asarray(flat, np.int32).reshape(-1, 2), pairs), name
+
+
+def test_coco_rle_restatement_known_answers_and_roundtrip():
+    """oracle/coco_rle.py against hand-derived COCO answers (column-major runs, leading zero run) and the
+    product's string codec (rleToString / rleFrString) as a round trip."""
+    from oracle import coco_rle as cr
+    from s2d_b200.keymask_ident.annotations import coco_rle as codec
+    m = np.array([[0, 1, 1], [0, 1, 0]], np.uint8)             # columns: 00 | 11 | 10
+    assert cr.counts(m) == [2, 3, 1] and cr.area(m) == 3 and cr.bbox(m) == [1.0, 0.0, 2.0, 2.0]
+    m1 = np.array([[1, 0], [1, 1]], np.uint8)                  # starts set: leading zero-length run
+    assert cr.counts(m1) == [0, 2, 1, 1]
+    assert cr.counts(np.zeros((3, 4), np.uint8)) == [12] and cr.bbox(np.zeros((3, 4))) == [0.0] * 4
+    rng = np.random.default_rng(3)
+    for h, w in [(1, 1), (5, 7), (33, 64), (120, 97)]:
+        mm = (rng.random((h, w)) < 0.4).astype(np.uint8)
+        c = cr.counts(mm)
+        assert sum(c) == h * w and np.array_equal(cr.decode(c, h, w), mm)
+        assert codec.from_string(codec.to_string(c)) == c
+    big = [0, 5, 100000, 3, 70000, 1, 1, 40]                   # multi-character counts and negative deltas
+    assert codec.from_string(codec.to_string(big)) == big
