@@ -206,6 +206,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
     if world > 1:
+        # NCCL prints its version banner on STDOUT (NCCL_DEBUG=VERSION/WARN in this image): send its log to
+        # stderr so that stdout holds the one JSON line the driver parses
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     nvid, T, H, W, M, P, desc = WORKLOADS[args.workload]
