@@ -208,7 +208,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int BN>
 __global__ void __launch_bounds__(GR_GROUPS * (GM_BLOCK_M + BN) + 32, 1)
 gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npix, int kblocks_total,
-                   int kblocks_per_split, int nfr_max, int Rp, int32_t* __restrict__ part) {
+                   int kblocks_per_split, int nfr_max, int Rp, int mt, int32_t* __restrict__ part) {
     constexpr int STAGES = GR_STAGES;
     constexpr int PRODUCERS = GM_BLOCK_M + BN;
     constexpr int A_BYTES = GM_BLOCK_M * GM_BLOCK_K;
@@ -225,7 +225,16 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
 
     const int R = F * L;
     const int tid = threadIdx.x % PRODUCERS, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // tid: index inside the group
-    const int m0 = blockIdx.x * GM_BLOCK_M, n0 = blockIdx.y * BN;
+    // G is symmetric: only the tiles that touch the upper triangle are computed (blockIdx.x walks them
+    // column block by column block; column block nj holds the row blocks 0 .. min(mt - 1, nj * BN / 128 + BN / 128 - 1)),
+    // gram_reduce_kernel mirrors them into the lower triangle.
+    int mi = blockIdx.x, nj = 0;
+    for (;;) {
+        const int rows_here = min(mt, (nj + 1) * (BN / GM_BLOCK_M));
+        if (mi < rows_here) break;
+        mi -= rows_here; ++nj;
+    }
+    const int m0 = mi * GM_BLOCK_M, n0 = nj * BN;
     const int kb0 = blockIdx.z * kblocks_per_split;
     const int nkb = min(kblocks_total, kb0 + kblocks_per_split) - kb0;
     // frames whose labels the two operand tiles need
@@ -377,16 +386,23 @@ __global__ void gram_reduce_kernel(const int32_t* __restrict__ part, int splits,
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)R * R) return;
     const int r = (int)(i / R), c = (int)(i - (int64_t)r * R);
+    const int rr = min(r, c), cc = max(r, c);          // only upper-triangle tiles were computed
     int acc = 0;
-    for (int s = 0; s < splits; ++s) acc += part[((int64_t)s * R + r) * Rp + c];
+    for (int s = 0; s < splits; ++s) acc += part[((int64_t)s * R + rr) * Rp + cc];
     G[i] = acc;
+}
+
+static int gram_tiles(int mt, int nt, int BN) {        // tiles that touch the upper triangle (see gram_labels_kernel)
+    int n = 0;
+    for (int nj = 0; nj < nt; ++nj) { const int rows_here = (nj + 1) * (BN / GM_BLOCK_M); n += rows_here < mt ? rows_here : mt; }
+    return n;
 }
 
 static void gram_plan(int R, int BN, int64_t npix, int* mt, int* nt, int* kblocks, int* per, int* splits, int* Rp) {
     *mt = (R + GM_BLOCK_M - 1) / GM_BLOCK_M;
     *nt = (R + BN - 1) / BN;
     *kblocks = (int)((npix + GM_BLOCK_K - 1) / GM_BLOCK_K);
-    int sp = 148 / (*mt * *nt);              // one wave of CTAs (1 CTA per SM)
+    int sp = 148 / gram_tiles(*mt, *nt, BN);  // one wave of CTAs (1 CTA per SM)
     if (sp > *kblocks) sp = *kblocks;
     if (sp < 1) sp = 1;
     *per = (*kblocks + sp - 1) / sp;
@@ -405,8 +421,8 @@ static int launch_gram(const uint8_t* labels, int F, int L, int64_t npix, int32_
     if (e != cudaSuccess) { set_error("gram_labels_kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return -2; }
     int mt, nt, kblocks, per, splits, Rp;
     gram_plan(R, BN, npix, &mt, &nt, &kblocks, &per, &splits, &Rp);
-    dim3 grid(mt, nt, splits);
-    kfn<<<grid, GR_GROUPS * (GM_BLOCK_M + BN) + 32, smem, st>>>(labels, F, L, npix, kblocks, per, nfr_max, Rp, work);
+    dim3 grid(gram_tiles(mt, nt, BN), 1, splits);
+    kfn<<<grid, GR_GROUPS * (GM_BLOCK_M + BN) + 32, smem, st>>>(labels, F, L, npix, kblocks, per, nfr_max, Rp, mt, work);
     S2D_CHECK_LAUNCH("gram_labels_kernel");
     gram_reduce_kernel<<<(unsigned)(((int64_t)R * R + 255) / 256), 256, 0, st>>>(work, splits, R, Rp, G);
     S2D_CHECK_LAUNCH("gram_reduce_kernel");
