@@ -24,10 +24,14 @@ def main():
     if os.path.exists(p):
         peak = float(json.load(open(p))["hbm_gbs"])
     T, H, W = 64, 480, 854
+    grid = [(M, P, Tw) for M in (10, 20, 50, 100) for P in (1024, 4096, 16384) for Tw in (8, 16, 32, 64)]
+    if len(sys.argv) > 1:        # one custom point: python tools/sweep.py T H W M P Tw   (e.g. the SA-V-shaped C3 tile: 48 1080 1920 30 8192 32)
+        T, H, W = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+        grid = [(int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6]))]
     rows = []
-    for M in (10, 20, 50, 100):
-        for P in (1024, 4096, 16384):
-            for Tw in (8, 16, 32, 64):
+    for M, P, Tw in grid:
+        for _once in (0,):
+            for _once2 in (0,):
                 if M * T * Tw * P * 8 > 40e9:
                     continue
                 sc = make_scene_device(7 + M, T, H, W, M, P, dev)
