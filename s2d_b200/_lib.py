@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libs2d_b200.so")
+LIB_PATH = os.environ.get("S2D_B200_LIB") or os.path.join(_HERE, "libs2d_b200.so")   # override: debug builds (make check)
 
 S2D_MAX_LABELS = 256
 S2D_MAX_CLUSTERS = 16

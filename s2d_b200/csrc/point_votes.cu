@@ -859,6 +859,9 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                             const uint32_t nbox = (rows + 15u) >> 4;
                             mbar_expect_tx(&tabbar, nbox * 16u * pitch);
                             const uint8_t* map = tm + ((pitch >> 4) - 1u) * 128u;
+#ifdef S2D_PV_BOUNDS_CHECK
+                            if (nbox * 16u * pitch > (uint32_t)BUF_BYTES || (pitch & 15u) || pitch > 256u) __trap();
+#endif
                             for (uint32_t i = 0; i < nbox; ++i)
                                 tma_box_2d(tab_s + i * 16u * pitch, map, &tabbar, (int)(x0 & ~15u), (int)(ti->ybase + y0 + b0 + 16u * i), l2_policy_evict_last());
                         } else {
@@ -877,6 +880,12 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                         for (uint32_t r = tid; r < rows; r += THREADS) {
                             const uint64_t g = A + (uint64_t)r * W;
                             const uint32_t ph = (uint32_t)g & 15u;
+#ifdef S2D_PV_BOUNDS_CHECK
+                            {
+                                const uint32_t d0 = r * pitch + a15 - ph, len = (ph + bw + 15u) & ~15u;
+                                if ((d0 & 15u) || d0 + len > (uint32_t)BUF_BYTES + 64u || ((g - ph) & 15u)) __trap();
+                            }
+#endif
                             bulk_g2s_addr(tab_s + r * pitch + a15 - ph, g - ph, (ph + bw + 15u) & ~15u, &tabbar, pol_labels);
                         }
                     }
@@ -918,6 +927,9 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                             const uint32_t off = (e >> 16) * negc + e + tabc;      // table + dy * pitch + dx + a15
                             sh[k] = off << 3;                                      // used modulo 32 (wrapping shifts)
                             const uint32_t addr = (e < lim) ? (off & ~3u) : dummy_s;
+#ifdef S2D_PV_BOUNDS_CHECK      // debug build (make check): every claimed byte lies inside the fetched table
+                            if (e < lim && (off - tab_s >= (uint32_t)BUF_BYTES || off - tabc >= rows * pitch)) __trap();
+#endif
                             asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old[k]) : "r"(addr), "r"(__funnelshift_l(0u, 0xFFu, sh[k])));
                         }
 #pragma unroll
