@@ -14,8 +14,9 @@ namespace s2d {
 // select: one warp per candidate query
 // ------------------------------------------------------------------------------------------
 constexpr int SEL_WARPS = 4;
+constexpr int SEL_MAX_T = 1024;          // frames per video (s2d_windows has the same limit)
 
-__global__ void __launch_bounds__(SEL_WARPS * 32)
+__global__ void __launch_bounds__(SEL_WARPS * 32, 10)
 select_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __restrict__ hits,
               const int32_t* __restrict__ uniq, const int32_t* __restrict__ gid_of,
               const int32_t* __restrict__ rowinfo, double match_thr, double one2x_iou,
@@ -34,28 +35,54 @@ select_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __restric
     }
     uint32_t* mrow = mbits + d.mbits_off + (int64_t)q * d.NW;
     int warn = 0, nm = 0, maxg = -1;
-    for (int t = ri.z; t <= ri.w; ++t) {
-        const int64_t rt = (int64_t)q * d.T + t;
-        const int U = uniq[d.vt_off + rt];
-        const int32_t* h = hits + d.hits_off + rt * d.L;
-        const int32_t* g = gid_of + (d.frame0 + t) * S2D_MAX_LABELS;
-        int c25 = 0;
-        for (int l = lane; l < d.L; l += 32) {
-            const int gid = g[l];
-            if (gid < 0) continue;
-            const int I = h[l];
-            // intersection / union as python floats; 0.0 when union == 0 (matching.py:659-662)
-            const double iou = (U == 0) ? 0.0 : (double)I / (double)U;
-            if (iou > match_thr) {
-                atomicOr(&mrow[gid >> 5], 1u << (gid & 31));
-                ++nm;
-                maxg = max(maxg, gid);
+    // The (frame, label) cells of the query's window are one contiguous run of hits[q]: the lanes walk
+    // it 32 cells at a time with every load independent (a loop over frames with a warp reduction per
+    // frame is a chain of global-memory latencies). Cells with iou > one2x_iou are rare: they bump a
+    // per-frame counter in shared memory, and the frames with more than one are counted at the end.
+    __shared__ int c25s[SEL_WARPS][SEL_MAX_T];
+    int* c25 = c25s[threadIdx.x >> 5];
+    const int L = d.L;
+    for (int t0 = max(ri.z, 0); t0 <= min(ri.w, d.T - 1); t0 += SEL_MAX_T) {      // one segment unless the window is huge
+        const int t1 = min(min(ri.w, d.T - 1), t0 + SEL_MAX_T - 1);
+        for (int t = t0 + lane; t <= t1; t += 32) c25[t - t0] = 0;
+        __syncwarp();
+        const int ncell = (t1 - t0 + 1) * L;
+        const int32_t* h0 = hits + d.hits_off + ((int64_t)q * d.T + t0) * L;
+        const int32_t* u0 = uniq + d.vt_off + (int64_t)q * d.T + t0;
+        const int32_t* g0 = gid_of + (d.frame0 + t0) * S2D_MAX_LABELS;
+        int tt = lane / L, l = lane - tt * L;              // cell j = tt * L + l, advanced by 32 per step without dividing
+#pragma unroll 8
+        for (int j = lane; j < ncell; j += 32) {
+            const int gid = g0[tt * S2D_MAX_LABELS + l];
+            const int I = h0[j], U = u0[tt];              // unconditional: the three loads of all unrolled steps fly together
+            if (gid >= 0) {
+                // iou = intersection / union as python floats, 0.0 when union == 0 (matching.py:659-662).
+                // The comparison iou > thr is decided without the division whenever I - thr * U is clearly
+                // away from zero (one FMA; a gap of 1e-12 * U is thousands of ulps of the quotient), and by
+                // the reference's own expression otherwise.
+                const double fI = (double)I, fU = (double)U, tol = 1e-12 * fU;
+                const double dm = fma(-match_thr, fU, fI), d2 = fma(-one2x_iou, fU, fI);
+                bool m1, m2;
+                if (U == 0) { m1 = 0.0 > match_thr; m2 = 0.0 > one2x_iou; }
+                else {
+                    m1 = dm > tol ? true : (dm < -tol ? false : (fI / fU > match_thr));
+                    m2 = d2 > tol ? true : (d2 < -tol ? false : (fI / fU > one2x_iou));
+                }
+                if (m1) {
+                    atomicOr(&mrow[gid >> 5], 1u << (gid & 31));
+                    ++nm;
+                    maxg = max(maxg, gid);
+                }
+                if (m2) atomicAdd(&c25[tt], 1);
             }
-            if (iou > one2x_iou) ++c25;
+            l += 32;
+            while (l >= L) { l -= L; ++tt; }
         }
-        c25 = warp_sum(c25);
-        if (c25 > 1) ++warn;
+        __syncwarp();
+        for (int t = t0 + lane; t <= t1; t += 32) warn += c25[t - t0] > 1 ? 1 : 0;
+        __syncwarp();
     }
+    warn = warp_sum(warn);
     nm = warp_sum(nm);
     maxg = __reduce_max_sync(0xffffffffu, maxg);
     if (lane == 0) {
