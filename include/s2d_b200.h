@@ -132,7 +132,7 @@ int s2d_windows(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_TW,
  * rowinfo == NULL votes every (q,t); vidinfo == NULL ignores the stage-B status.
  * vec4_ok != 0 promises P even and 16-byte aligned tracks for every video (128-bit loads).
  * work: int32 scratch of s2d_point_votes_work_ints(total_rows) elements, 16-byte aligned; with it
- * (and vec4_ok, P <= 8192) a persistent kernel runs: a device-side plan lists the (row, frame)
+ * (and vec4_ok, P <= 16384; 8192 for variant 1) a persistent kernel runs: a device-side plan lists the (row, frame)
  * tiles and 2-4 CTAs per SM stream them through cp.async.bulk. Variant 0 (default) pulls the
  * tile's bounding box of the label map into shared memory and resolves de-duplication and label
  * lookup with one shared-memory atomic per point; variant 1 de-duplicates in a shared bitmap and

@@ -587,8 +587,8 @@ constexpr int PV_MAX_BANDS = 6;
 constexpr uint32_t PV_PK_INVALID = 0xFFFFFFFFu;
 
 __host__ __device__ constexpr int pv_buf_bytes(int threads, int ppt, int ctas) {
-    // 228 KB per SM, 1 KB reserved per CTA, ~1.5 KB static shared memory, 64 B slack behind the table
-    const int cap = ((233472 / ctas - 1024 - 1536 - 64) / 128) * 128;
+    // 228 KB per SM, 1 KB reserved per CTA, <= 2 KB static shared memory, 64 B slack behind the table
+    const int cap = ((233472 / ctas - 1024 - 2048 - 64) / 128) * 128;
     return cap < threads * ppt * 8 ? threads * ppt * 8 : cap;
 }
 
@@ -1111,7 +1111,7 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
     cudaStream_t st = (cudaStream_t)stream;
     const bool v4 = vec4_ok != 0;
     const int variant = g_pv_variant;
-    if (variant != 2 && v4 && work && max_P <= 8192 && total_rows > 0 && total_rows <= 2147483647LL) {
+    if (variant != 2 && v4 && work && max_P <= (variant == 0 ? 16384 : 8192) && total_rows > 0 && total_rows <= 2147483647LL) {
         // persistent TMA path
         S2D_CHECK_ARG((((uintptr_t)work) & 15) == 0, "s2d_point_votes: work must be 16-byte aligned");
         int dev = 0, nsm = 148;
@@ -1140,7 +1140,8 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
                 if (ctas == 6) return launch_pv_tab<128, 32, 6, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
                 return launch_pv_tab<256, 16, 4, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
             }
-            return launch_pv_tab<256, 32, 3, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+            if (max_P <= 256 * 32) return launch_pv_tab<256, 32, 3, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+            return launch_pv_tab<512, 32, 1, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);     // 128 KB tiles: one CTA per SM
         }
         if (max_P <= 256 * 4) return launch_pv_tma<256, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);   // 4 CTAs/SM
         if (max_P <= 512 * 4) return launch_pv_tma<512, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);

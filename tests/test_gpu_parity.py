@@ -106,6 +106,7 @@ def test_point_votes_shapes_and_bands(P, H, W, pv_variant):
 @pytest.mark.parametrize("H,W,P,M,lab255,off", [(480, 854, 1000, 10, False, 5), (720, 1280, 4096, 20, False, 5),
                                                 (720, 1280, 4096, 20, False, 0), (1080, 1920, 2048, 6, False, 16),
                                                 (480, 864, 1024, 12, False, 0), (97, 131, 512, 5, True, 5),
+                                                (720, 1280, 16384, 4, False, 0), (480, 854, 12000, 6, False, 5),
                                                 (480, 854, 4096, 20, True, 0)])
 def test_point_votes_scene_geometry(H, W, P, M, lab255, off, pv_variant):
     """Object-shaped point clouds (compact bounding boxes: the label-table kernel's main path, one
