@@ -144,7 +144,7 @@ int s2d_windows(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_TW,
  * per video: TMA descriptors of the video's label maps, so that variant 0 fetches a tile's table
  * as a few 2D boxes instead of one bulk copy per row. Videos whose W or label base address is not
  * a multiple of 16 get no descriptors and keep the row-by-row fetch. */
-#define S2D_PV_TMAPS 16                            /* box widths 16, 32, ... 256 pixels, 16 rows each */
+#define S2D_PV_TMAPS 32                            /* box widths 16, 32, ... 512 pixels, 16 rows each */
 #define S2D_PV_TMAP_BYTES (S2D_PV_TMAPS * 128 + 128)
 int s2d_point_votes_variant(int variant);   /* process-wide; 0 label table, 1 bitmap, 2 CTA per tile */
 int s2d_point_votes_work_ints(int64_t total_rows, int64_t* out);

@@ -15,7 +15,7 @@ S2D_MAX_LABELS = 256
 S2D_MAX_CLUSTERS = 16
 S2D_VIDINFO_WORDS = 8
 S2D_CLINFO_WORDS = 16
-S2D_PV_TMAP_BYTES = 16 * 128 + 128
+S2D_PV_TMAP_BYTES = 32 * 128 + 128
 
 
 class VideoDesc(C.Structure):

@@ -835,9 +835,9 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
             const uint32_t x0 = bmn & 0xFFFFu, y0 = bmn >> 16;
             const uint32_t bw = (bmx & 0xFFFFu) - x0, bh = (bmx >> 16) - y0;      // max holds coordinate + 1
             // With TMA descriptors (row pitch and base of the label maps are multiples of 16) the table is
-            // fetched as 2D boxes of 16 rows x 64/128/192/256 pixels, one instruction each; otherwise row by row.
+            // fetched as 2D boxes of 16 rows x 16..512 pixels, one instruction each; otherwise row by row.
             // (a box must start on a 16-byte boundary of its row: it starts at x0 & ~15)
-            const uint8_t* tm = (bw + (x0 & 15u) <= 256u) ? ti->tm : nullptr;
+            const uint8_t* tm = (bw + (x0 & 15u) <= 16u * S2D_PV_TMAPS) ? ti->tm : nullptr;
             uint32_t pitch, R;
             if (tm) {
                 pitch = (bw + (x0 & 15u) + 15u) & ~15u;
@@ -860,10 +860,10 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                             mbar_expect_tx(&tabbar, nbox * 16u * pitch);
                             const uint8_t* map = tm + ((pitch >> 4) - 1u) * 128u;
 #ifdef S2D_PV_BOUNDS_CHECK
-                            if (nbox * 16u * pitch > (uint32_t)BUF_BYTES || (pitch & 15u) || pitch > 256u) __trap();
+                            if (nbox * 16u * pitch > (uint32_t)BUF_BYTES || (pitch & 15u) || pitch > 16u * S2D_PV_TMAPS) __trap();
 #endif
                             for (uint32_t i = 0; i < nbox; ++i)
-                                tma_box_2d(tab_s + i * 16u * pitch, map, &tabbar, (int)(x0 & ~15u), (int)(ti->ybase + y0 + b0 + 16u * i), l2_policy_evict_last());
+                                tma_box_2d(tab_s + i * 16u * pitch, map, &tabbar, (int)((x0 & ~15u) >> 1), (int)(ti->ybase + y0 + b0 + 16u * i), l2_policy_evict_last());
                         } else {
                             mbar_arrive(&tabbar);
                         }
@@ -1053,7 +1053,7 @@ extern "C" int s2d_point_votes_work_ints(int64_t total_rows, int64_t* out) {
 }
 
 // Host side: TMA descriptors of the videos' label maps for the label-table kernel. Per video
-// S2D_PV_TMAP_BYTES: S2D_PV_TMAPS CUtensorMap (u8 [T*H][W], boxes of 16 rows x 16, 32, ... 256 pixels)
+// S2D_PV_TMAP_BYTES: S2D_PV_TMAPS CUtensorMap (boxes of 16 rows x 16, 32, ... 512 pixels of the [T*H][W] u8 map)
 // and a 128-byte trailer whose first int is 1 when the descriptors are usable (W and the base
 // address are multiples of 16, W >= 16), 0 otherwise (that video's tables are fetched row by row).
 typedef CUresult (*PvEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1082,12 +1082,14 @@ extern "C" int s2d_point_votes_tmaps(const s2d_video_desc* host_descs, int nvide
                 memcpy(blk + k * 128, blk + (k - 1) * 128, 128);
                 continue;
             }
+            // the u8 map is described as u16 [T*H][W/2]: a box dimension is limited to 256 ELEMENTS, so
+            // 16-bit elements give boxes of up to 512 pixels (same bytes, coordinates in pixel pairs)
             CUtensorMap map;
-            cuuint64_t dims[2] = {(cuuint64_t)d.W, (cuuint64_t)d.T * (cuuint64_t)d.H};
+            cuuint64_t dims[2] = {(cuuint64_t)d.W / 2, (cuuint64_t)d.T * (cuuint64_t)d.H};
             cuuint64_t strides[1] = {(cuuint64_t)d.W};
-            cuuint32_t box[2] = {(cuuint32_t)(16 * (k + 1)), 16u};
+            cuuint32_t box[2] = {(cuuint32_t)(8 * (k + 1)), 16u};
             cuuint32_t estr[2] = {1, 1};
-            CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)d.labels, dims, strides, box, estr,
+            CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, (void*)d.labels, dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) ok = false;
