@@ -92,6 +92,27 @@ def main():
     np.savez_compressed(path, **store)
     print("wrote", path, {n: int(store[f"{n}__npairs"].sum()) for n in names})
 
+    # convex-hull grid scorers (cotracker_matching.py:506-637): random point rasters inside a blob vs a mask
+    rng = np.random.default_rng(5)
+    pg = {}
+    shapes = [(48, 64, 25), (96, 128, 25), (120, 97, 50), (64, 64, 10)]
+    for i, (H, W, gs) in enumerate(shapes):
+        yy, xx = np.mgrid[0:H, 0:W]
+        blob = ((xx - W * 0.45) / (W * 0.3)) ** 2 + ((yy - H * 0.5) / (H * 0.35)) ** 2 <= 1.0
+        ys, xs = np.nonzero(blob)
+        sel = rng.choice(len(ys), size=min(len(ys), 40 + 30 * i), replace=False)
+        pm = np.zeros((H, W), np.uint8)
+        pm[ys[sel], xs[sel]] = 1
+        mask = (np.roll(blob, (3, -4), axis=(0, 1))).astype(np.uint8)
+        ext = mat.extend_pointgrid(torch.from_numpy(pm).bool(), gs).numpy()
+        iou = mat.compute_point_mask_iou(torch.from_numpy(pm), torch.from_numpy(mask), gs)
+        pg[f"pm{i}"], pg[f"mask{i}"], pg[f"grid{i}"], pg[f"ext{i}"], pg[f"iou{i}"] = pm, mask, gs, ext, np.float64(iou)
+    pg["n"] = len(shapes)
+    pg["grid7"] = mat.get_points_on_a_grid(7, (48, 64)).numpy()
+    path = os.path.join(ROOT, "tests", "golden", "pointgrid.npz")
+    np.savez_compressed(path, **pg)
+    print("wrote", path, [float(pg[f"iou{i}"]) for i in range(len(shapes))])
+
 
 if __name__ == "__main__":
     main()

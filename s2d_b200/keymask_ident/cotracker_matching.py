@@ -153,6 +153,204 @@ def boolean_visibility(vis: torch.Tensor, threshold: float = 0.3) -> torch.Tenso
     return _engine.boolean_visibility(vis, threshold)
 
 
+def get_points_on_a_grid(size: int, extent, center=None, device=torch.device("cpu")):
+    """(1, size*size, 2) grid of (x, y) points covering an (H, W) extent with a margin of W/64, row-major
+    (cotracker_matching.py:506-562, CoTracker's query grid)."""
+    if size == 1:
+        return torch.tensor([extent[1] / 2, extent[0] / 2], device=device)[None, None]
+    if center is None:
+        center = [extent[0] / 2, extent[1] / 2]
+    margin = extent[1] / 64
+    ys = torch.linspace(margin - extent[0] / 2 + center[0], extent[0] / 2 + center[0] - margin, size, device=device)
+    xs = torch.linspace(margin - extent[1] / 2 + center[1], extent[1] / 2 + center[1] - margin, size, device=device)
+    gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+    return torch.stack([gx, gy], dim=-1).reshape(1, -1, 2)
+
+
+def extend_pointgrid(pointmask: torch.Tensor, grid_size: int) -> torch.Tensor:
+    """Point raster OR the grid points that fall outside the convex hull of the points
+    (cotracker_matching.py:565-609; exported, never called by the driver). Hull and polygon fill stay
+    OpenCV's, as in the reference; the grid density follows points-per-hull-area."""
+    H, W = pointmask.shape
+    pts = torch.nonzero(pointmask, as_tuple=False).cpu().numpy()
+    if pts.shape[0] < 3:
+        warnings.warn("Not enough points to compute a convex hull. At least 3 points are required.")
+        return pointmask
+    hull = cv2.convexHull(pts.astype(np.int32))
+    filled = np.zeros((H, W), dtype=np.uint8)
+    cv2.fillPoly(filled, [hull], color=255)
+    filled = torch.from_numpy(filled).to(pointmask.device).bool()
+    new_size = torch.sqrt((torch.sum(pointmask) / torch.sum(filled)) * H * W).item()
+    if not torch.isfinite(torch.Tensor([new_size])) or new_size <= 0:
+        new_size = grid_size
+    new_size = min(new_size, grid_size * 1.5)
+    grid = get_points_on_a_grid(size=int(new_size), extent=(H, W), device=pointmask.device)
+    gx, gy = grid[0, :, 0].round().long(), grid[0, :, 1].round().long()
+    outside = ~filled[gy.cpu(), gx.cpu()].bool()
+    ext = torch.zeros_like(pointmask, dtype=torch.uint8)
+    ext[gy[outside], gx[outside]] = 1
+    return pointmask | ext
+
+
+def compute_point_mask_iou(pointmask: torch.Tensor, mask: torch.Tensor, grid_size: int) -> float:
+    """|P and M'| / |P or M'| with M' = mask restricted to the hull-extended point grid
+    (cotracker_matching.py:612-637); the counts come from the bit-packed overlap kernel (K1)."""
+    pm = pointmask.bool().to(mask.device)
+    ext = extend_pointgrid(pm, grid_size)
+    m = mask.bool() * ext
+    dev = _engine.device()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    a = pm.to(dev, torch.uint8).contiguous().reshape(1, -1)
+    b = m.to(dev, torch.uint8).contiguous().reshape(1, -1)
+    npix = a.shape[1]
+    nw = (npix + 31) // 32
+    ba = torch.empty(nw, dtype=torch.int32, device=dev)
+    bb = torch.empty(nw, dtype=torch.int32, device=dev)
+    I = torch.empty(1, dtype=torch.int32, device=dev)
+    A = torch.empty(1, dtype=torch.int32, device=dev)
+    B = torch.empty(1, dtype=torch.int32, device=dev)
+    _lib.call("s2d_pack_bits", a.data_ptr(), 1, npix, ba.data_ptr(), st)
+    _lib.call("s2d_pack_bits", b.data_ptr(), 1, npix, bb.data_ptr(), st)
+    _lib.call("s2d_overlap_bits", ba.data_ptr(), 1, bb.data_ptr(), 1, nw, I.data_ptr(), A.data_ptr(), B.data_ptr(), st)
+    inter = int(I.item())
+    union = int(A.item()) + int(B.item()) - inter
+    return 0.0 if union == 0 else inter / union
+
+
+def extract_mask_matches(segm_mask, pred_tracks, all_video_masks, frame_id, v_range, grid_size, globalid_lookup,
+                         clusterid_lookup, cluster_id, matching_threshold):
+    """Single-query form of stage D's inner loop (cotracker_matching.py:665-719): the query's tracked points
+    voted into every frame of v_range by K2, iou = |P and mask| / |P| as python floats, matches where
+    iou > matching_threshold. Returns (matches, all_comparisons) with the reference's dict keys. The driver
+    path (temporal_correspondence_match) runs the same kernel batched over all queries instead."""
+    T = all_video_masks.shape[0]
+    assert pred_tracks.shape[1] == T, f"Track masks shape {pred_tracks.shape[1]} does not match video masks shape {T}"
+    lab = all_video_masks[..., 0]
+    if tuple(lab.shape[1:]) != tuple(segm_mask.shape[:2]):      # targets are nearest-resized to the query mask's size
+        lab = torch.nn.functional.interpolate(lab[:, None].float(), size=tuple(segm_mask.shape[:2]), mode="nearest")[:, 0].long()
+    labels_dev = _engine.labels_u8_device(lab[..., None])
+    dev = labels_dev.device
+    qf, ql, _area = _engine.enumerate_objects(labels_dev)
+    tr = pred_tracks[0].to(dev, torch.float32)
+    P = int(tr.shape[1])
+    Pp = P + (P % 2)
+    tracks = torch.zeros((1, T, Pp, 2), dtype=torch.float32, device=dev)
+    tracks[0, :, :P] = tr
+    b = Batch([VideoInput(labels=labels_dev, tracks=tracks, npts=torch.tensor([P], dtype=torch.int32, device=dev),
+                          max_label=int(lab.max()))], stages="D")
+    b.votes_all()
+    torch.cuda.synchronize(dev)
+    L = b.host_descs[0].L
+    hits = b.hits.cpu().numpy().reshape(T, L)
+    uniq = b.uniq.cpu().numpy().reshape(T)
+    matches, all_comparisons = [], []
+    for f in range(v_range[0], v_range[1] + 1):
+        for oid in (int(l) for l in ql[qf == f]):
+            inter, union = int(hits[f, oid]), int(uniq[f])
+            iou = 0.0 if union == 0 else inter / union
+            rec = {"frame_id": f, "mask_id": oid,
+                   "overall_mask_id": get_overall_maskid(globalid_lookup, f, oid),
+                   "cluster_mask_id": get_cluster_maskid(clusterid_lookup, cluster_id, f, oid), "iou": iou}
+            all_comparisons.append(rec)
+            if iou > matching_threshold:
+                matches.append(dict(rec))
+    return matches, all_comparisons
+
+
+def temporal_correspondance_clustering(matches_data, frameid_maskid_to_overall_maskid_lookup, debug):
+    """Per visibility cluster: 0/1 match matrix over overall mask ids, bounding-box crop, Hamming DBSCAN with the
+    reference's eps / min_samples table (on the GPU: s2d_hamming_dbscan), zero rows -> -1, groups keyed by label
+    (cotracker_matching.py:764-840). (-1, -1) when a cluster's crop is empty."""
+    import ctypes as C
+    max_id = max([m["overall_mask_id"] for md in matches_data for m in md["matches"]], default=-1)
+    cluster_ids = sorted(set(m["cluster_id"] for m in matches_data))
+    out = []
+    for cid in cluster_ids:
+        mat = np.zeros((max_id + 1, max_id + 1), dtype=np.float32)
+        for md in (m for m in matches_data if int(m["cluster_id"]) == cid):
+            r = md["overall_mask_id"]
+            for m in md["matches"]:
+                c = m["overall_mask_id"]
+                if r >= mat.shape[0] or c >= mat.shape[1]:
+                    warnings.warn("Overall mask ID exceeds matrix dimensions. Skipping this match.")
+                    continue
+                mat[r, c] = 1
+        mat, (row_off, _col_off) = crop_bool_tensor(mat)
+        if mat.shape[0] == 0 or mat.shape[1] == 0:
+            return -1, -1
+        n, d = mat.shape
+        eps, ms = (0.05, 5) if d > 50 else ((0.1, 3) if d < 10 else (0.1, 5))
+        dev = _engine.device()
+        stride = (d + 31) // 32
+        pad = np.zeros((n, stride * 32), bool)
+        pad[:, :d] = mat != 0
+        words = np.packbits(pad.reshape(n, stride, 32), axis=-1, bitorder="little").view(np.uint32).reshape(n, stride)
+        bits = torch.from_numpy(words.view(np.int32).copy()).to(dev)
+        nw = C.c_int64()
+        _lib.call("s2d_dbscan_work_ints", n, 1, C.byref(nw))
+        work = torch.empty(nw.value + 2, dtype=torch.int32, device=dev)
+        lab_d = torch.empty(n, dtype=torch.int32, device=dev)
+        _lib.call("s2d_hamming_dbscan", bits.data_ptr(), n, stride, d, eps, ms, work.data_ptr(), lab_d.data_ptr(),
+                  torch.cuda.current_stream(dev).cuda_stream)
+        labels = lab_d.cpu().numpy().astype(np.int64)
+        labels[mat.sum(axis=1) == 0] = -1
+        print(f"Clustering labels for cluster {cid}: {labels}") if debug else None
+        groups = {}
+        for i, l in enumerate(labels.tolist()):
+            if l != -1:
+                groups.setdefault(l, []).append(get_frameid_maskid_from_overall_maskid(frameid_maskid_to_overall_maskid_lookup, i + row_off))
+        out.append({"cluster_id": cid, "visibility_to_temporal_factor": len(set(labels[labels != -1].tolist())),
+                    "overall_mask_ids_per_label": groups})
+    return cluster_ids, out
+
+
+def calculate_cluster_coverage(cluster_masks, mask_groupings):
+    """Fraction of each visibility cluster's candidate masks that ended up in a temporal group, and overall
+    (cotracker_matching.py:843-872); cluster folders are zipped with the groupings positionally, as there."""
+    matched_all = total_all = 0
+    per_cluster = []
+    for c_masks, grouping in zip(cluster_masks, mask_groupings):
+        if len(c_masks) == 0:
+            print("No cluster masks found for this cluster.")
+            continue
+        have = [(int(m["frame_id"]), int(m["mask_id"])) for m in c_masks]
+        grouped = [fm for fms in grouping["overall_mask_ids_per_label"].values() for fm in fms]
+        matched = sum(1 for fm in grouped if fm in have)
+        cov = matched / len(have) if len(have) > 0 else 0
+        print(f"Cluster coverage: {cov:.2%} ({matched}/{len(have)}) for cluster masks {c_masks[0]['vis_cluster_id']}")
+        per_cluster.append(cov)
+        matched_all += matched
+        total_all += len(have)
+    overall = matched_all / total_all if total_all > 0 else 0
+    print(f"Overall coverage {overall:.2%} ({matched_all}/{total_all})")
+    return overall, per_cluster
+
+
+def gather_and_save_one2x_data(matches_data, mask_groupings, visibility_group_mask_path):
+    """Average one-to-many flags per visibility cluster and per temporal group, written as
+    cluster_{c}/one2x_data_cluster{c}.json and video_one2x_data.json (cotracker_matching.py:875-921)."""
+    per_cluster = {}
+    for md in matches_data:
+        per_cluster.setdefault(f"cluster_{md['cluster_id']}", []).append(md["one2x"])
+    video = {}
+    for g in mask_groupings:
+        cid = g["cluster_id"]
+        od = {"avg_one2x_cluster": np.mean(per_cluster.get(f"cluster_{cid}", []))}
+        for label, fms in g["overall_mask_ids_per_label"].items():
+            ent = []
+            for (f, m) in fms:
+                e = next((md["one2x"] for md in matches_data if md["frame_id"] == f and md["mask_id"] == m), None)
+                if e is not None:
+                    ent.append(e)
+            avg = np.sum(ent) / len(ent) if ent else 0
+            od[f"group_{label}"] = {"avg_one2x": avg, "one2x_counts": len(ent), "noisy": bool(avg > 0.5)}
+        with open(os.path.join(visibility_group_mask_path, f"cluster_{cid}", f"one2x_data_cluster{cid}.json"), "w") as f:
+            json.dump(od, f, indent=4)
+        video[f"cluster_{cid}"] = od
+    with open(os.path.join(visibility_group_mask_path, "video_one2x_data.json"), "w") as f:
+        json.dump(video, f, indent=4)
+
+
 def crop_bool_tensor(bool_arr: np.ndarray):
     if bool_arr.ndim != 2:
         raise ValueError("Input must be a 2D boolean array.")

@@ -228,3 +228,65 @@ def test_write_annotation_for_video_roundtrip(tmp_path):
                 seg = a["segmentations"][t]
                 assert np.array_equal(cr.decode(ann.coco_rle.from_string(seg["counts"]), H, W), m.astype(np.uint8))
                 assert a["areas"][t] == int(m.sum()) and a["bboxes"][t] == cr.bbox(m)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["basic", "one2x", "medium", "dups"])
+def test_exported_stage_d_helpers_match_reference_golden(case, tmp_path):
+    """The single-call helpers the reference exports next to temporal_correspondence_match
+    (extract_mask_matches, temporal_correspondance_clustering, calculate_cluster_coverage,
+    gather_and_save_one2x_data; cotracker_matching.py:665-921) against the intermediates the unmodified
+    reference produced for the golden videos."""
+    import json
+    import numpy as np
+    from s2d_b200.keymask_ident import cotracker_matching as cm
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    g = json.load(open(os.path.join(gdir, f"{case}.json")))
+    z = np.load(os.path.join(gdir, f"{case}.npz"))
+    assert g["status"] == 1
+    labels, tracks = z["labels"], z["tracks"]
+    T, H, W = labels.shape
+    masks = torch.from_numpy(labels.astype(np.int64))[..., None]
+    glookup = cm.contruct_frameid_maskid_lookup(masks)
+    ncl = max(q["cluster_id"] for q in g["queries"]) + 1
+    cluster_masks = [[{"frame_id": q["frame_id"], "mask_id": q["mask_id"], "vis_cluster_id": c}
+                      for q in g["queries"] if q["cluster_id"] == c] for c in range(ncl)]
+    clookup = cm.contruct_frameid_maskid_cluster_lookup(cluster_masks)
+    matches_data = []
+    for q in g["queries"]:
+        gid = q["overall_mask_id"]
+        seg = torch.from_numpy((labels[q["frame_id"]] == q["mask_id"]).astype(np.uint8) * 255)
+        m, comps = cm.extract_mask_matches(seg, torch.from_numpy(tracks[gid])[None], masks, q["frame_id"], tuple(q["v_range"]),
+                                           q["grid_size"], glookup, clookup, q["cluster_id"], g["matching_threshold"])
+        assert [x["overall_mask_id"] for x in m] == q["matches"], (case, gid)
+        assert [[c["frame_id"], c["mask_id"], c["overall_mask_id"]] for c in comps] == [c[:3] for c in q["comps"]]
+        assert [c["iou"] for c in comps] == [c[5] for c in q["comps"]]                  # python floats: exact
+        matches_data.append({"cluster_id": q["cluster_id"], "frame_id": q["frame_id"], "mask_id": q["mask_id"],
+                             "overall_mask_id": gid, "one2x": q["one2x"], "matches": m})
+    cids, groupings = cm.temporal_correspondance_clustering(matches_data, glookup, False)
+    assert cids == [x["cluster_id"] for x in g["groupings"]]
+    for got, want in zip(groupings, g["groupings"]):
+        assert got["visibility_to_temporal_factor"] == want["factor"]
+        assert {str(k): [list(fm) for fm in v] for k, v in got["overall_mask_ids_per_label"].items()} == want["groups"]
+    cov, ccov = cm.calculate_cluster_coverage(cluster_masks, groupings)
+    assert f"Video Coverage: {cov:.2f}\n" == g["video_coverage_txt"]
+    for c, v in zip(cids, ccov):
+        assert g["cluster_coverage_txt"][f"cluster_{c}"].startswith(f"Cluster {c} Coverage: {v:.2f}\n")
+    for c in cids:
+        os.makedirs(tmp_path / f"cluster_{c}")
+    cm.gather_and_save_one2x_data(matches_data, groupings, str(tmp_path))
+    assert json.load(open(tmp_path / "video_one2x_data.json")) == g["one2x"]
+
+
+@pytest.mark.gpu
+def test_point_grid_helpers_vs_reference_golden():
+    """get_points_on_a_grid / extend_pointgrid / compute_point_mask_iou (cotracker_matching.py:506-637, exported,
+    never called by the driver) against outputs of the unmodified reference (oracle/make_golden_events.py)."""
+    import numpy as np
+    from s2d_b200.keymask_ident import cotracker_matching as cm
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pointgrid.npz"))
+    for i in range(int(g["n"])):
+        pm, mk, gs = torch.from_numpy(g[f"pm{i}"]), torch.from_numpy(g[f"mask{i}"]), int(g[f"grid{i}"])
+        assert np.array_equal(cm.extend_pointgrid(pm.bool(), gs).numpy(), g[f"ext{i}"])
+        assert cm.compute_point_mask_iou(pm, mk, gs) == float(g[f"iou{i}"])
+    assert torch.equal(cm.get_points_on_a_grid(7, (48, 64)), torch.from_numpy(g["grid7"]))
