@@ -180,6 +180,13 @@ int s2d_rle_work_ints(int N, int H, int W, int max_runs, int64_t* out);
 int s2d_rle_encode(const uint8_t* masks, int N, int H, int W, int max_runs, int32_t* work,
                    int32_t* counts, int32_t* nruns, int32_t* area, int32_t* bbox, void* stream);
 
+/* Area and bounding box of N run-length encodings without decoding them (maskApi.c rleArea /
+ * rleToBbox, as convert_results_to_annotations.py:70-81 calls them per predicted segmentation).
+ * counts: the RLEs' run lengths back to back (device int32), offsets [N+1] (device int64) the start
+ * of each, heights [N] the mask heights. area[n] = sum of the odd runs, bbox[n] = (x, y, w, h). */
+int s2d_rle_area_bbox(const int32_t* counts, const int64_t* offsets, int N, const int32_t* heights,
+                      int32_t* area, int32_t* bbox, void* stream);
+
 /* K4a. Scores and selection per candidate query: iou = hits/uniq (double), match bit when
  * iou > matching_threshold (cotracker_matching.py:710), one-to-many flag when >= one2x_frames
  * frames hold more than one mask with iou > one2x_iou (cotracker_matching.py:1082-1111).

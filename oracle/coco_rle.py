@@ -44,3 +44,34 @@ def decode(cnts, h: int, w: int) -> np.ndarray:
         p += c
         v ^= 1
     return flat.reshape((h, w), order="F")
+
+
+def rle_area(cnts) -> int:
+    """rleArea on the counts."""
+    return int(sum(cnts[1::2]))
+
+
+def rle_to_bbox(cnts, h: int):
+    """rleToBbox, loop for loop (maskApi.c): boundaries of the first 2*floor(n/2) runs."""
+    m = (len(cnts) // 2) * 2
+    if m == 0:
+        return [0.0, 0.0, 0.0, 0.0]
+    xs = ys = None
+    xe = ye = 0
+    cc, xp = 0, 0
+    full = False
+    for j in range(m):
+        cc += int(cnts[j])
+        t = cc - (j % 2)
+        y = t % h
+        x = (t - y) // h
+        if j % 2 == 0:
+            xp = x
+        elif xp < x:
+            full = True
+        xs = x if xs is None else min(xs, x)
+        ys = y if ys is None else min(ys, y)
+        xe, ye = max(xe, x), max(ye, y)
+    if full:
+        ys, ye = 0, h - 1
+    return [float(xs), float(ys), float(xe - xs + 1), float(ye - ys + 1)]

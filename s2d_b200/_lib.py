@@ -53,6 +53,7 @@ SIGNATURES = {
     "s2d_boolean_visibility": [_P, _L, _F, _P, _P],
     "s2d_rle_work_ints": [_I, _I, _I, _I, C.POINTER(C.c_int64)],
     "s2d_rle_encode": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "s2d_rle_area_bbox": [_P, _P, _I, _P, _P, _P, _P],
     "s2d_select": [_P, _I, _I, _L, _P, _P, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P],
     "s2d_group_work_ints": [_L, _I, C.POINTER(C.c_int64)],
     "s2d_group": [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],

@@ -165,3 +165,71 @@ extern "C" int s2d_rle_encode(const uint8_t* masks, int N, int H, int W, int max
     S2D_CHECK_LAUNCH("rle_runs_kernel");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// RLE -> area and bounding box (maskApi.c rleArea / rleToBbox; convert_results_to_annotations.py:
+// 70-81 recomputes both for every predicted segmentation). One warp per RLE: the lanes walk the
+// counts 32 at a time with a warp-wide inclusive scan carrying the running pixel position.
+// rleToBbox semantics are kept to the letter: with cc the inclusive prefix of the first
+// m = 2 * floor(n / 2) counts, boundary j sits at t = cc - (j & 1) (first pixel of a set run for
+// even j, last pixel for odd j), x = t / h, y = t % h; a set run that crosses into another column
+// makes the box span all rows; an RLE without a complete set run gives (0, 0, 0, 0).
+// ------------------------------------------------------------------------------------------
+namespace s2d {
+
+__global__ void __launch_bounds__(128)
+rle_area_bbox_kernel(const int32_t* __restrict__ counts, const int64_t* __restrict__ offsets, int N, const int32_t* __restrict__ hs,
+                     int32_t* __restrict__ area, int32_t* __restrict__ bbox) {
+    const int n = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const int32_t* c = counts + offsets[n];
+    const int nr = (int)(offsets[n + 1] - offsets[n]);
+    const int m = (nr / 2) * 2;
+    const unsigned h = (unsigned)hs[n];
+    unsigned carry = 0, a = 0;
+    unsigned xs = 0xFFFFFFFFu, ys = 0xFFFFFFFFu, xe = 0, ye = 0;
+    unsigned xp_carry = 0;                        // x of the latest even boundary seen so far
+    bool full_rows = false;
+    for (int base = 0; base < m; base += 32) {
+        const int j = base + lane;
+        const unsigned v = j < m ? (unsigned)c[j] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        const unsigned cc = carry + incl;
+        const unsigned t = cc - (unsigned)(j & 1);
+        const unsigned y = t % h, x = (t - y) / h;
+        // x of the preceding even boundary: the previous lane's (or the previous chunk's last even one)
+        unsigned xprev = __shfl_up_sync(0xffffffffu, x, 1);
+        if (lane == 0) xprev = xp_carry;
+        if (j < m) {
+            if (j & 1) { a += v; if (xprev < x) full_rows = true; }
+            xs = min(xs, x); xe = max(xe, x); ys = min(ys, y); ye = max(ye, y);
+        }
+        carry = __shfl_sync(0xffffffffu, cc, 31);
+        xp_carry = __shfl_sync(0xffffffffu, x, 30);          // lane 30 holds an even j (base is a multiple of 32)
+    }
+    a = __reduce_add_sync(0xffffffffu, a);
+    xs = __reduce_min_sync(0xffffffffu, xs); ys = __reduce_min_sync(0xffffffffu, ys);
+    xe = __reduce_max_sync(0xffffffffu, xe); ye = __reduce_max_sync(0xffffffffu, ye);
+    full_rows = __any_sync(0xffffffffu, full_rows);
+    if (lane == 0) {
+        area[n] = (int32_t)a;
+        int32_t* bb = bbox + 4 * n;
+        if (m == 0) { bb[0] = bb[1] = bb[2] = bb[3] = 0; }
+        else {
+            if (full_rows) { ys = 0; ye = h - 1; }
+            bb[0] = (int32_t)xs; bb[1] = (int32_t)ys; bb[2] = (int32_t)(xe - xs + 1); bb[3] = (int32_t)(ye - ys + 1);
+        }
+    }
+}
+
+}  // namespace s2d
+
+extern "C" int s2d_rle_area_bbox(const int32_t* counts, const int64_t* offsets, int N, const int32_t* heights,
+                                 int32_t* area, int32_t* bbox, void* stream) {
+    S2D_CHECK_ARG(counts && offsets && heights && area && bbox && N > 0, "s2d_rle_area_bbox: bad arguments");
+    rle_area_bbox_kernel<<<(N + 3) / 4, 128, 0, (cudaStream_t)stream>>>(counts, offsets, N, heights, area, bbox);
+    S2D_CHECK_LAUNCH("rle_area_bbox_kernel");
+    return 0;
+}

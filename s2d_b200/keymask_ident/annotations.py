@@ -99,6 +99,33 @@ class coco_rle:
         return out
 
 
+def rle_area_bbox_batch(rles):
+    """[(area int, bbox [x, y, w, h] floats)] of COCO RLE dicts ({"size": [h, w], "counts": str | bytes | list})
+    without decoding the masks: mask_util.area / toBbox for a whole list in one GPU launch (s2d_rle_area_bbox)."""
+    from s2d_b200 import _lib
+    if not rles:
+        return []
+    dev = _engine.device()
+    lists = []
+    for r in rles:
+        c = r["counts"]
+        if isinstance(c, bytes):
+            c = c.decode("ascii")
+        lists.append(coco_rle.from_string(c) if isinstance(c, str) else [int(x) for x in c])
+    offs = np.zeros(len(lists) + 1, np.int64)
+    offs[1:] = np.cumsum([len(x) for x in lists])
+    flat = np.concatenate([np.asarray(x, np.int64) for x in lists] + [np.zeros(1, np.int64)]).astype(np.int32)
+    counts = torch.from_numpy(flat).to(dev)
+    offsets = torch.from_numpy(offs).to(dev)
+    hs = torch.tensor([int(r["size"][0]) for r in rles], dtype=torch.int32, device=dev)
+    area = torch.empty(len(rles), dtype=torch.int32, device=dev)
+    bbox = torch.empty((len(rles), 4), dtype=torch.int32, device=dev)
+    _lib.call("s2d_rle_area_bbox", counts.data_ptr(), offsets.data_ptr(), len(rles), hs.data_ptr(), area.data_ptr(),
+              bbox.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    a, b = area.cpu().numpy(), bbox.cpu().numpy()
+    return [(int(a[i]), [float(v) for v in b[i]]) for i in range(len(rles))]
+
+
 def write_annotation_for_video(video_path, cluster_masks_path, annotation_output_path, visibility_data):
     """Same contract as the reference (annotations.py:8-140)."""
     video_name = os.path.basename(video_path)

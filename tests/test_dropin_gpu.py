@@ -290,3 +290,43 @@ def test_point_grid_helpers_vs_reference_golden():
         assert np.array_equal(cm.extend_pointgrid(pm.bool(), gs).numpy(), g[f"ext{i}"])
         assert cm.compute_point_mask_iou(pm, mk, gs) == float(g[f"iou{i}"])
     assert torch.equal(cm.get_points_on_a_grid(7, (48, 64)), torch.from_numpy(g["grid7"]))
+
+
+@pytest.mark.gpu
+def test_rle_area_bbox_and_results_conversion(tmp_path):
+    """s2d_rle_area_bbox against the loop-for-loop restatement of maskApi.c rleArea / rleToBbox, and the
+    convert_results_to_annotations drop-in end to end (schema of convert_results_to_annotations.py:38-95)."""
+    import json
+    import numpy as np
+    from oracle import coco_rle as cr
+    from s2d_b200.keymask_ident import annotations as ann
+    from s2d_b200.keymask_ident.convert_results_to_annotations import convert_results_to_annotation
+    rng = np.random.default_rng(4)
+    rles, want = [], []
+    for (h, w) in [(1, 1), (7, 5), (33, 64), (97, 131), (480, 854)]:
+        yy, xx = np.mgrid[0:h, 0:w]
+        for m in (np.zeros((h, w), bool), np.ones((h, w), bool), rng.random((h, w)) < 0.3,
+                  (xx > w // 3) & (xx < 2 * w // 3 + 1) & (yy >= h // 4) & (yy <= 3 * h // 4), (xx + 2 * yy) % 11 < 4):
+            c = cr.counts(m)
+            rles.append({"size": [h, w], "counts": ann.coco_rle.to_string(c)})
+            want.append((cr.rle_area(c), cr.rle_to_bbox(c, h)))
+            if m.any():
+                assert cr.rle_to_bbox(c, h) == cr.bbox(m) and cr.rle_area(c) == int(m.sum())
+    rles.append({"size": [4, 4], "counts": [3, 5, 8]})                 # a run that wraps over columns: all rows
+    want.append((5, cr.rle_to_bbox([3, 5, 8], 4)))
+    assert ann.rle_area_bbox_batch(rles) == want
+    # end to end
+    gt = {"info": {"d": 1}, "licenses": [], "videos": [{"id": 7, "length": 3, "height": 33, "width": 64, "file_names": ["v7/0.jpg"]}]}
+    merged = {"categories": [{"id": 1, "name": "fg"}]}
+    seg = [rles[10], None, rles[12]]
+    results = [{"video_id": 7, "score": 0.9, "category_id": 1, "segmentations": seg},
+               {"video_id": 7, "score": 0.1, "category_id": 1, "segmentations": seg}]
+    for name, obj in (("gt", gt), ("merged", merged), ("res", results)):
+        (tmp_path / f"{name}.json").write_text(json.dumps(obj))
+    convert_results_to_annotation(str(tmp_path / "merged.json"), str(tmp_path / "gt.json"), str(tmp_path / "res.json"), 0.75,
+                                  str(tmp_path / "out"), "conv")
+    d = json.loads((tmp_path / "out" / "conv.json").read_text())
+    assert d["videos"] == gt["videos"] and d["categories"] == merged["categories"] and len(d["annotations"]) == 1
+    a = d["annotations"][0]
+    assert a["id"] == 1 and a["length"] == 3 and a["segmentations"] == seg
+    assert a["areas"] == [want[10][0], None, want[12][0]] and a["bboxes"] == [want[10][1], None, want[12][1]]
