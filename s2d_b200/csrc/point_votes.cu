@@ -710,12 +710,12 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     constexpr int NWARPS = THREADS / 32;
     static_assert(BUF_BYTES >= PV_BM_WORDS * 4, "the fallback bitmap lives in the buffer");
     static_assert(S2D_MAX_LABELS % THREADS == 0 || THREADS % S2D_MAX_LABELS == 0, "output phase: whole warps per pass");
-    static_assert(PPT % 2 == 0, "points are read two at a time");
+    static_assert(PPT % 4 == 0, "points are read two at a time, in two halves");
     extern __shared__ __align__(128) uint8_t buf[];   // tracks of the tile, then its label table
     __shared__ int hist[S2D_MAX_LABELS];
     __shared__ __align__(8) uint2 wred[NWARPS];        // per-warp packed (min, max + 1) of (iy, ix)
     __shared__ uint32_t dummy[32];                     // all ones: target of points outside the band
-    __shared__ __align__(8) uint64_t full, tabbar;
+    __shared__ __align__(8) uint64_t full, full2, tabbar;   // tracks arrive in two halves: phase A starts on the first
     __shared__ PvTile tinfo[3];                        // PF: ring of 3 (current, next being loaded, being planned); else 2
     __shared__ PvPlan plan_s;                          // scheduler state (kept out of the registers)
     __shared__ const float* nsrc_s;                    // tracks of the planned tile
@@ -730,6 +730,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         plan_s.pi = plan_s.pi_end = plan_s.prow = 0;
         plan_s.prp = make_int4(0, 0, 0, 0);
         mbar_init(&full, 1);
+        mbar_init(&full2, 1);
         mbar_init(&tabbar, THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -754,15 +755,23 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
             if (idx < np2) raw[k] = ld_stream(gp + idx);
         }
     };
+    // tracks of the planned tile -> buffer, as two bulk copies on two mbarriers (the halves of the k loop of phase A)
+    auto issue_tracks = [&](int P) {
+        const uint32_t bytes = (uint32_t)P * 8u;
+        const uint32_t b1 = min(bytes, (uint32_t)(THREADS * PPT * 4));
+        const uint64_t pol = l2_policy_evict_first();
+        mbar_expect_tx(&full, b1);
+        bulk_g2s_hint(buf, nsrc_s, b1, &full, pol);
+        mbar_expect_tx(&full2, bytes - b1);
+        if (bytes > b1) bulk_g2s_hint(buf + b1, reinterpret_cast<const uint8_t*>(nsrc_s) + b1, bytes - b1, &full2, pol);
+    };
     if (warp == 0) {
         plan(&tinfo[0]);
         __syncwarp();
         if (PF) {
             plan(&tinfo[1]);
         } else if (lane == 0 && more_s) {
-            const uint32_t bytes = (uint32_t)tinfo[0].pad * 8u;
-            mbar_expect_tx(&full, bytes);
-            bulk_g2s_hint(buf, nsrc_s, bytes, &full, l2_policy_evict_first());
+            issue_tracks(tinfo[0].pad);
         }
     }
     __syncthreads();
@@ -791,21 +800,28 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
             if (PF) return make_float4(__int_as_float(raw[k].x), __int_as_float(raw[k].y), __int_as_float(raw[k].z), __int_as_float(raw[k].w));
             return sp[k * THREADS + tid];
         };
-        if (n >= THREADS * PPT) {
 #pragma unroll
-            for (int k = 0; k < PPT / 2; ++k) {
-                const float4 v = point_pair(k);
-                pk[2 * k] = pv_pack(v.x, v.y, W, H);
-                pk[2 * k + 1] = pv_pack(v.z, v.w, W, H);
+        for (int half = 0; half < 2; ++half) {
+            if (half == 1 && !PF) {                   // second half of the tracks
+                if (warp == 0) mbar_wait(&full2, j & 1);
+                __syncthreads();
             }
-        } else {
+            if (n >= THREADS * PPT) {
 #pragma unroll
-            for (int k = 0; k < PPT / 2; ++k) {
-                const float4 v = point_pair(k);
-                const int p0 = 2 * (k * THREADS + tid);
-                const uint32_t a = pv_pack(v.x, v.y, W, H), b = pv_pack(v.z, v.w, W, H);
-                pk[2 * k] = (p0 < n) ? a : PV_PK_INVALID;
-                pk[2 * k + 1] = (p0 + 1 < n) ? b : PV_PK_INVALID;
+                for (int k = half * (PPT / 4); k < (half + 1) * (PPT / 4); ++k) {
+                    const float4 v = point_pair(k);
+                    pk[2 * k] = pv_pack(v.x, v.y, W, H);
+                    pk[2 * k + 1] = pv_pack(v.z, v.w, W, H);
+                }
+            } else {
+#pragma unroll
+                for (int k = half * (PPT / 4); k < (half + 1) * (PPT / 4); ++k) {
+                    const float4 v = point_pair(k);
+                    const int p0 = 2 * (k * THREADS + tid);
+                    const uint32_t a = pv_pack(v.x, v.y, W, H), b = pv_pack(v.z, v.w, W, H);
+                    pk[2 * k] = (p0 < n) ? a : PV_PK_INVALID;
+                    pk[2 * k + 1] = (p0 + 1 < n) ? b : PV_PK_INVALID;
+                }
             }
         }
 #pragma unroll
@@ -966,9 +982,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         fence_proxy_async();                          // buffer atomics before the next tile's bulk copy
         __syncthreads();                              // S2: histogram complete, buffer free, next record visible
         if (!PF && tid == 0 && more_s) {              // the next tile's tracks fly during the output phase
-            const uint32_t bytes = (uint32_t)tinfo[snxt].pad * 8u;
-            mbar_expect_tx(&full, bytes);
-            bulk_g2s_hint(buf, nsrc_s, bytes, &full, l2_policy_evict_first());
+            issue_tracks(tinfo[snxt].pad);
         }
 #pragma unroll
         for (int b = tid; b < S2D_MAX_LABELS; b += THREADS) {     // write hits, uniq = sum of the histogram
