@@ -64,6 +64,17 @@ __device__ __forceinline__ uint32_t pv_claim_s(uint32_t bm_saddr, uint32_t lin, 
     return bit & ~old;
 }
 
+// same for a bitmap of 2^LOGW words (the label-table kernel's fallback sizes its bitmap to its buffer)
+template <int LOGW>
+__device__ __forceinline__ uint32_t pv_claim_t(uint32_t bm_saddr, uint32_t lin, uint32_t base) {
+    const uint32_t kk = lin - base;
+    const uint32_t w4 = ((kk ^ (kk >> 5)) & ((1u << LOGW) - 1u)) << 2;
+    const uint32_t bit = shl_clamp(1u, kk >> LOGW);
+    uint32_t old;
+    asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(bm_saddr + w4), "r"(bit) : "memory");
+    return bit & ~old;
+}
+
 // expand the low 4 bits of m into a byte mask (bit i -> byte i = 0xFF)
 __device__ __forceinline__ uint32_t nib2bytes(uint32_t m) {
     return (((m & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
@@ -708,7 +719,11 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                        int32_t* __restrict__ uniq, const uint8_t* __restrict__ tmaps) {
     constexpr int BUF_BYTES = PF ? pv_buf_bytes(THREADS, 0, CTAS) : pv_buf_bytes(THREADS, PPT, CTAS);
     constexpr int NWARPS = THREADS / 32;
-    static_assert(BUF_BYTES >= PV_BM_WORDS * 4, "the fallback bitmap lives in the buffer");
+    // the fallback bitmap lives in the buffer: the largest power of two of words that fits (at most 2^13 = 32 KB)
+    constexpr int FB_LOGW = BUF_BYTES >= 32768 ? 13 : (BUF_BYTES >= 16384 ? 12 : 11);
+    constexpr int FB_WORDS = 1 << FB_LOGW;
+    constexpr uint32_t FB_BITS = (uint32_t)FB_WORDS * 32u;
+    static_assert(BUF_BYTES >= FB_WORDS * 4, "the fallback bitmap lives in the buffer");
     static_assert(S2D_MAX_LABELS % THREADS == 0 || THREADS % S2D_MAX_LABELS == 0, "output phase: whole warps per pass");
     static_assert(PPT % 4 == 0, "points are read two at a time, in two halves");
     extern __shared__ __align__(128) uint8_t buf[];   // tracks of the tile, then its label table
@@ -963,17 +978,17 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                 // ---- fallback: bitmap in the buffer + global label gather ----------------------
                 uint32_t* bm = reinterpret_cast<uint32_t*>(buf);
                 const uint32_t lend = (y0 + bh - 1u) * W + x0 + bw;            // last pixel + 1
-                for (uint32_t base = y0 * W + x0;; base += PV_BM_BITS) {
-                    for (int i = tid; i < PV_BM_WORDS / 4; i += THREADS)
+                for (uint32_t base = y0 * W + x0;; base += FB_BITS) {
+                    for (int i = tid; i < FB_WORDS / 4; i += THREADS)
                         reinterpret_cast<uint4*>(bm)[i] = make_uint4(0, 0, 0, 0);
                     __syncthreads();
 #pragma unroll
                     for (int k = 0; k < PPT; ++k) {
                         const uint32_t p = pk[k];
                         const uint32_t lin = (p == PV_PK_INVALID) ? PV_INVALID : (p >> 16) * W + (p & 0xFFFFu);
-                        if (pv_claim_s(tab_s, lin, base)) atomicAdd(&hist[__ldg(lbl + lin)], 1);
+                        if (pv_claim_t<FB_LOGW>(tab_s, lin, base)) atomicAdd(&hist[__ldg(lbl + lin)], 1);
                     }
-                    if (lend - base <= (uint32_t)PV_BM_BITS) break;
+                    if (lend - base <= FB_BITS) break;
                     __syncthreads();
                 }
             }
