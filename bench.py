@@ -182,6 +182,9 @@ def main():
     ap.add_argument("--videos", type=int, default=0, help="override videos per GPU (profiling runs)")
     ap.add_argument("--point-order", default="raster", choices=["raster", "random"],
                     help="order of a query's points: raster (CoTracker-like grid order) or random (worst case)")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the step as one CUDA graph (launch-bound small workloads such as c1); per-stage "
+                         "times then come from one extra un-timed pass")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-k1", action="store_true")
@@ -221,8 +224,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    if args.graph:
+        batch.capture(params)
     for _ in range(args.warmup):
-        batch.run(params)
+        batch.replay() if args.graph else batch.run(params)
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -232,10 +237,18 @@ def main():
     e0.record()
     launches = 0
     for _ in range(args.steps):
-        launches += batch.run(params, timers=timers)
+        if args.graph:
+            batch.replay()
+            launches += batch.kernel_launches_per_run
+        else:
+            launches += batch.run(params, timers=timers)
     e1.record()
     barrier()
     clk = clocks.stop()
+    if args.graph:                       # per-stage times of the same work, outside the timed region
+        for _ in range(3):
+            batch.run(params, timers=timers)
+        torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -319,7 +332,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": f"{args.workload}: {desc}", "videos_per_gpu": nvid, "frames_per_video": T,
                            "resolution": [H, W], "masks_per_frame": M, "tracks_per_query": P,
-                           "queries_per_video": int(batch.host_descs[0].Nm), "point_order": args.point_order, "partition": f"by video, {world} GPU(s)",
+                           "queries_per_video": int(batch.host_descs[0].Nm), "point_order": args.point_order, "cuda_graph": bool(args.graph), "partition": f"by video, {world} GPU(s)",
                            "cache": "inputs per step (tracks+flags+labels) >> 126 MB L2, no flush needed",
                            "input_bytes_per_step_per_gpu": int(sum(v.tracks.numel() * 4 + v.vis.numel() + v.labels.numel() for v in vids))},
                 "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,

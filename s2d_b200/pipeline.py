@@ -231,6 +231,22 @@ class Batch:
         self.kernel_launches_per_run = launches
         return launches
 
+    def capture(self, params: Params = Params(), stages: Optional[str] = None):
+        """Record the whole path of this batch once as a CUDA graph; replay() then costs one launch
+        instead of ~20 (small batches - a single short video - are launch-bound). The C-ABI calls only
+        enqueue kernels and memsets on the current stream, so they capture as they are; the first,
+        un-captured run() configures the kernels' attributes."""
+        self.run(params, stages=stages)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run(params, stages=stages)
+        self._graph = g
+        return g
+
+    def replay(self):
+        self._graph.replay()
+
     def votes_all(self, stream=None):
         """K2 over every (query, frame) of every video, ignoring candidates/status (tests, bench)."""
         st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream

@@ -448,3 +448,23 @@ def test_mask_iou_consumers_vs_reference_formulas(n1, n2, H, W):
     a, b = m1[:, None].expand(-1, n2, -1, -1), m2[None].expand(n1, -1, -1, -1)
     want = torch.sum(a * (a == b), dim=[-1, -2]).to(torch.float) / torch.sum(a + b, dim=[-1, -2])
     assert torch.equal(BatchIoU(p1, p2), want)
+
+
+def test_cuda_graph_replay_matches_direct_run(golden_case):
+    """Batch.capture / replay: the whole path recorded once as a CUDA graph gives the same result tables."""
+    from s2d_b200.pipeline import Batch, Params
+    name, g, labels, tracks, vis = golden_case
+    par = Params(g["visibility_threshold"], g["matching_threshold"])
+    b1 = Batch([_video(labels, tracks, vis)])
+    b1.run(par)
+    torch.cuda.synchronize()
+    want = b1.fetch_summary()
+    b2 = Batch([_video(labels, tracks, vis)])
+    b2.capture(par)
+    for _ in range(3):
+        b2.replay()
+    torch.cuda.synchronize()
+    got = b2.fetch_summary()
+    for k in want:
+        assert np.array_equal(want[k], got[k]), (name, k)
+    assert torch.equal(b1.hits, b2.hits) and torch.equal(b1.uniq, b2.uniq)
