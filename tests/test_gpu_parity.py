@@ -467,4 +467,5 @@ def test_cuda_graph_replay_matches_direct_run(golden_case):
     got = b2.fetch_summary()
     for k in want:
         assert np.array_equal(want[k], got[k]), (name, k)
-    assert torch.equal(b1.hits, b2.hits) and torch.equal(b1.uniq, b2.uniq)
+    # (hits / uniq are only written for the voted tiles, the rest of those buffers is uninitialised: the result
+    # tables above are what depends on them)
