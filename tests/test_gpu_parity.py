@@ -469,3 +469,39 @@ def test_cuda_graph_replay_matches_direct_run(golden_case):
         assert np.array_equal(want[k], got[k]), (name, k)
     # (hits / uniq are only written for the voted tiles, the rest of those buffers is uninitialised: the result
     # tables above are what depends on them)
+
+
+@pytest.mark.parametrize("seed,T,H,W,M,P,kw", [
+    (11, 16, 120, 160, 5, 256, dict(specials=True)),
+    (12, 20, 96, 128, 8, 130, dict(dup_rate=0.2)),
+    (13, 14, 200, 320, 12, 512, dict(specials=True, noise=1.5)),
+    (14, 30, 64, 80, 4, 64, dict(occlude=False)),
+    (15, 12, 240, 426, 6, 1000, dict(full_cover_frames=(3, 4), specials=True)),
+    (16, 18, 144, 256, 10, 300, dict(noise=0.0)),
+])
+def test_random_scenes_full_pipeline_vs_oracle(seed, T, H, W, M, P, kw):
+    """Seeded scenes of different shapes (odd point counts, duplicates, NaN/inf/half-integer coordinates,
+    frames without background, no occlusion): the whole device pipeline - whatever status the video ends with -
+    against the CPU oracle restatement of the reference (itself pinned to the reference's goldens)."""
+    from s2d_b200.pipeline import Params, discover_keymasks
+    from s2d_b200.synth import make_scene
+    sc = make_scene(seed, T=T, H=H, W=W, M=M, P=P, **kw)
+    for mt in (0.5, 0.35):
+        res = discover_keymasks([_video(sc.labels, sc.tracks, sc.vis, max_label=M)], Params(matching_threshold=mt))[0]
+        ref = ko.discover(sc.labels, sc.tracks, sc.vis, matching_threshold=mt)
+        assert res["status"] == ref["status"], (seed, mt)
+        assert np.array_equal(res["V"], ref["V"], equal_nan=True)
+        assert np.array_equal(res["labels1"], ref["labels1"])
+        assert json_eq(res["clusters"], ref["clusters"])
+        if ref["status"] != 1:
+            continue
+        assert len(res["queries"]) == len(ref["queries"])
+        for a, b in zip(res["queries"], ref["queries"]):
+            assert (a["cluster_id"], a["frame_id"], a["mask_id"], a["one2x"]) == (b["cluster_id"], b["frame_id"], b["mask_id"], b["one2x"])
+            assert a["matches"] == b["matches"]
+            assert [c[:5] for c in a["comps"]] == [c[:5] for c in b["comps"]]
+        ga = [(g["cluster_id"], g["visibility_to_temporal_factor"], g["overall_mask_ids_per_label"]) for g in res["groupings"]]
+        gb = [(g["cluster_id"], g["visibility_to_temporal_factor"], g["overall_mask_ids_per_label"]) for g in ref["groupings"]]
+        assert ga == gb
+        assert res["video_coverage"] == ref["video_coverage"] and res["cluster_coverages"] == ref["cluster_coverages"]
+        assert res["one2x"] == ref["one2x"]
