@@ -390,9 +390,10 @@ def run_k1(vids, batch, L):
     diag = G.reshape(R, R).diagonal().cpu().numpy()
     ops = 2.0 * R * R * H * W
     tops = ops / (ms * 1e-3) / 1e12
-    return {"kernel": "gram_labels_kernel: one-hot operands synthesised in smem, tcgen05.mma kind::i8, int32 in TMEM; "
-                      "only the tiles touching the upper triangle of the symmetric overlap matrix are executed "
-                      "(2/3 of the MMAs at this shape), `achieved` counts the algorithmic 2*R^2*pixels ops",
+    return {"kernel": "gram_labels2_kernel: one-hot operands synthesised in smem, two tcgen05.mma kind::i8 M128xN256 groups "
+                      "per k-block into 512 int32 TMEM columns; only the 256x256 blocks on or above the diagonal of the "
+                      "symmetric overlap matrix are executed (2/3 of the MMAs at this shape), `achieved` counts the "
+                      "algorithmic 2*R^2*pixels ops",
             "rows": R, "pixels": H * W, "ms_per_video": ms, "achieved": tops, "unit": "TOP/s",
             "peak": peak, "peak_source": "measured here: torch._int_mm 8192^3 (cuBLASLt int8)", "frac": tops / peak,
             "frac_of_nominal_4500": tops / 4500.0, "hbm_bytes_per_video": int(T * H * W),

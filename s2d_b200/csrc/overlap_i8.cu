@@ -381,6 +381,180 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
     if (warp == 0) tmem_dealloc<BN>(tmem);
 }
 
+// ------------------------------------------------------------------------------------------
+// Two m-tiles per CTA. The operand producers pace the kernel above (ncu: tensor pipe 39 % active): a
+// k-block costs 128 + 256 rows of synthesis for one M128 x N256 MMA group. Here a CTA owns a 256 x 256
+// output block: it synthesises 256 A rows + 256 B rows per k-block and issues TWO MMA groups (rows 0-127
+// and 128-255 of the A tile against the same B tile) into the two halves of the 512 TMEM columns - a third
+// less synthesis per MMA. One producer group of 512 threads (one per operand row), three 64 KB stages.
+// ------------------------------------------------------------------------------------------
+constexpr int G2_AM = 256;               // A rows per CTA (two M = 128 instruction tiles)
+constexpr int G2_BN = 256;
+constexpr int G2_STAGES = 3;
+constexpr int G2_PRODUCERS = G2_AM + G2_BN;
+
+__global__ void __launch_bounds__(G2_PRODUCERS + 32, 1)
+gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npix, int kblocks_total,
+                    int kblocks_per_split, int nfr_max, int Rp, int32_t* __restrict__ part) {
+    constexpr int STAGES = G2_STAGES;
+    constexpr int PRODUCERS = G2_PRODUCERS;
+    constexpr int A_BYTES = G2_AM * GM_BLOCK_K;
+    constexpr int B_BYTES = G2_BN * GM_BLOCK_K;
+    extern __shared__ __align__(1024) uint8_t gsm_raw[];
+    uint8_t* gsm = gsm_raw + ((1024u - (s_u32(gsm_raw) & 1023u)) & 1023u);
+    uint8_t* sOps = gsm;                                         // STAGES x (A tile | B tile)
+    uint8_t* sLab = gsm + STAGES * (A_BYTES + B_BYTES);          // (GR_PF + 1) label slots x nfr_max x 128 B
+    uint8_t* sDesc = sLab + (GR_PF + 1) * nfr_max * 128;         // 2 slots x nfr_max x 8 chunk descriptors
+    __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], accum_full;
+    __shared__ uint32_t tmem_base;
+
+    const int R = F * L;
+    const int tid = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // symmetric: block column nj holds the block rows 0 .. nj (256 x 256 blocks)
+    int mi = blockIdx.x, nj = 0;
+    while (mi > nj) { mi -= nj + 1; ++nj; }
+    const int m0 = mi * G2_AM, n0 = nj * G2_BN;
+    const int kb0 = blockIdx.z * kblocks_per_split;
+    const int nkb = min(kblocks_total, kb0 + kblocks_per_split) - kb0;
+    const int fa0 = m0 / L, fa1 = min(R - 1, m0 + G2_AM - 1) / L;
+    const int fb0 = min(n0, R - 1) / L, fb1 = min(R - 1, n0 + G2_BN - 1) / L;
+    const int nfa = fa1 - fa0 + 1, nfb = fb1 - fb0 + 1;
+    const int slot_bytes = nfr_max * 128;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], PRODUCERS / 32); bar_init(&empty[s], 1); }
+        bar_init(&accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc<512>(&tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base;
+
+    if (nkb > 0) {
+        if (tid < PRODUCERS) {
+            // ---- operand producers: one thread per operand row, every k-block ----
+            const bool isA = tid < G2_AM;
+            const int rl = isA ? tid : tid - G2_AM;
+            const int r = (isA ? m0 : n0) + rl;
+            const bool rvalid = r < R;
+            const int f = rvalid ? r / L : 0;
+            const uint32_t sp = rvalid ? (uint32_t)(r - f * L) * 0x01010101u : 0xFEFEFEFEu;   // 0xFE never matches (L <= 254)
+            const int lab_off = (isA ? (f - fa0) : nfa + (f - fb0)) * 128;
+            const int row_off = (isA ? 0 : A_BYTES) + rl * 128;
+            const int r7 = rl & 7;
+
+            auto issue_labels = [&](int i) {        // label bytes of k-block i -> ring slot i % (GR_PF + 1)
+                if (i < nkb) {
+                    uint8_t* slot = sLab + (i % (GR_PF + 1)) * slot_bytes;
+                    const int64_t px0 = (int64_t)(kb0 + i) * GM_BLOCK_K;
+                    for (int j = tid; j < (nfa + nfb) * 8; j += PRODUCERS) {
+                        const int fr = j >> 3, c = j & 7;
+                        const int ff = fr < nfa ? fa0 + fr : fb0 + (fr - nfa);
+                        const int64_t px = px0 + 16 * c;
+                        if (px < npix) cp_async16(slot + fr * 128 + 16 * c, labels + (int64_t)ff * npix + px);
+                        else *reinterpret_cast<uint4*>(slot + fr * 128 + 16 * c) = make_uint4(~0u, ~0u, ~0u, ~0u);   // 0xFF: no label
+                    }
+                }
+                cp_async_commit();
+            };
+            auto make_desc = [&](int i) {           // per 16-pixel chunk: its single label, 0xFF when mixed
+                if (i < nkb) {
+                    const uint8_t* slot = sLab + (i % (GR_PF + 1)) * slot_bytes;
+                    for (int j = tid; j < (nfa + nfb) * 8; j += PRODUCERS) {
+                        const uint4 w = *reinterpret_cast<const uint4*>(slot + j * 16);
+                        const bool uni = (w.x == w.y) & (w.y == w.z) & (w.z == w.w) & (w.x == __byte_perm(w.x, 0, 0x0000));
+                        sDesc[(i & 1) * nfr_max * 8 + j] = uni ? (uint8_t)(w.x & 255u) : (uint8_t)0xFF;
+                    }
+                }
+            };
+            for (int j = 0; j < GR_PF; ++j) issue_labels(j);
+            cp_async_wait<GR_PF - 1>();
+            asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");
+            make_desc(0);
+            const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+            const uint4 zeros = make_uint4(0, 0, 0, 0);
+            const uint32_t mylab = sp & 255u;
+            const int desc_off = (isA ? (f - fa0) : nfa + (f - fb0)) * 8;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                cp_async_wait<GR_PF - 2>();          // this thread's copies of k-blocks <= i+1 have landed
+                asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");   // everybody's; desc(i) visible; k-block i-1 consumed
+                issue_labels(i + GR_PF);             // refills the slot k-block i-1 used
+                make_desc(i + 1);
+                if (i >= STAGES) bar_wait(&empty[s], ((i / STAGES) - 1) & 1);
+                const uint8_t* lab = sLab + (i % (GR_PF + 1)) * slot_bytes + lab_off;
+                uint8_t* dst = sOps + s * (A_BYTES + B_BYTES) + row_off;
+                const uint2 d8 = *reinterpret_cast<const uint2*>(sDesc + (i & 1) * nfr_max * 8 + desc_off);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t u = ((c < 4 ? d8.x : d8.y) >> (8 * (c & 3))) & 255u;
+                    uint4* out = reinterpret_cast<uint4*>(dst + ((c ^ r7) << 4));
+                    if (u != 0xFFu) {
+                        *out = (u == mylab && rvalid) ? ones : zeros;
+                    } else {                          // mixed chunk (object border): compare the 16 pixels
+                        const uint4 w = *reinterpret_cast<const uint4*>(lab + 16 * c);
+                        uint4 o;
+                        o.x = __vcmpeq4(w.x, sp) & 0x01010101u;
+                        o.y = __vcmpeq4(w.y, sp) & 0x01010101u;
+                        o.z = __vcmpeq4(w.z, sp) & 0x01010101u;
+                        o.w = __vcmpeq4(w.w, sp) & 0x01010101u;
+                        *out = o;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (MMA) reads
+                __syncwarp();
+                if (lane == 0) bar_arrive(&full[s]);                           // one arrival per producer warp
+            }
+            // ---- epilogue: warps 0-3 own the four TMEM lane quarters; two accumulators (A rows 0-127 and 128-255) ----
+            if (warp < 4) {
+                bar_wait(&accum_full, 0);
+                tc_fence_after();
+#pragma unroll 1
+                for (int acc = 0; acc < 2; ++acc) {
+                    const int row = m0 + acc * GM_BLOCK_M + warp * 32 + lane;
+                    int32_t* prow = part + ((int64_t)blockIdx.z * R + row) * Rp;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < G2_BN; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + acc * G2_BN + c0, v);
+                        if (row < R) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const int col = n0 + c0 + j;
+                                if (col < Rp) *reinterpret_cast<uint4*>(prow + col) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+        } else if (lane == 0) {
+            // ---- MMA issuer: two M = 128 groups per k-block against the same B tile ----
+            constexpr uint32_t idesc = umma_idesc_i8(G2_BN);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                bar_wait(&full[s], (i / STAGES) & 1);
+                tc_fence_after();
+                const uint64_t ad0 = umma_desc(s_u32(sOps + s * (A_BYTES + B_BYTES)));
+                const uint64_t ad1 = umma_desc(s_u32(sOps + s * (A_BYTES + B_BYTES) + GM_BLOCK_M * GM_BLOCK_K));
+                const uint64_t bd = umma_desc(s_u32(sOps + s * (A_BYTES + B_BYTES) + A_BYTES));
+#pragma unroll
+                for (int k = 0; k < GM_BLOCK_K / GM_UMMA_K; ++k) {
+                    const uint64_t ko = (uint64_t)(k * GM_UMMA_K >> 4);
+                    umma_i8(tmem, ad0 + ko, bd + ko, idesc, (i | k) != 0);
+                    umma_i8(tmem + G2_BN, ad1 + ko, bd + ko, idesc, (i | k) != 0);
+                }
+                tc_commit(&empty[s]);
+            }
+            tc_commit(&accum_full);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 // G[r][c] = sum over splits of part[s][r][c]  (row pitch Rp in part, R in G)
 __global__ void gram_reduce_kernel(const int32_t* __restrict__ part, int splits, int R, int Rp, int32_t* __restrict__ G) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -408,6 +582,42 @@ static void gram_plan(int R, int BN, int64_t npix, int* mt, int* nt, int* kblock
     *per = (*kblocks + sp - 1) / sp;
     *splits = (*kblocks + *per - 1) / *per;
     *Rp = *nt * BN;                          // every column an epilogue may store exists
+}
+
+static void gram2_plan(int R, int64_t npix, int* ntiles, int* nt, int* kblocks, int* per, int* splits, int* Rp) {
+    *nt = (R + G2_BN - 1) / G2_BN;
+    *ntiles = *nt * (*nt + 1) / 2;            // 256 x 256 blocks on or above the diagonal
+    *kblocks = (int)((npix + GM_BLOCK_K - 1) / GM_BLOCK_K);
+    int sp = 148 / *ntiles;                  // one wave of CTAs (1 CTA per SM)
+    if (sp > *kblocks) sp = *kblocks;
+    if (sp < 1) sp = 1;
+    *per = (*kblocks + sp - 1) / sp;
+    *splits = (*kblocks + *per - 1) / *per;
+    *Rp = *nt * G2_BN;
+}
+
+static bool gram_use_v2(int R) {
+    static const int forced = getenv("S2D_GRAM_V2") ? atoi(getenv("S2D_GRAM_V2")) : -1;
+    if (forced >= 0) return forced != 0 && R > 128;
+    return R > 256;
+}
+
+static int launch_gram2(const uint8_t* labels, int F, int L, int64_t npix, int32_t* work, int32_t* G, cudaStream_t st) {
+    const int R = F * L;
+    const int per_tile = G2_AM / L + 2;
+    const int nfr_max = 2 * (F < per_tile ? F : per_tile);
+    const int smem = G2_STAGES * (G2_AM + G2_BN) * GM_BLOCK_K + (GR_PF + 1) * nfr_max * 128 + 2 * nfr_max * 8 + 1024;
+    if (smem > 227 * 1024) { set_error("s2d_overlap_gram_labels: nlab=%d is too small for the label ring (needs %d B of shared memory)", L, smem); return -1; }
+    cudaError_t e = cudaFuncSetAttribute(gram_labels2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("gram_labels2_kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return -2; }
+    int ntiles, nt, kblocks, per, splits, Rp;
+    gram2_plan(R, npix, &ntiles, &nt, &kblocks, &per, &splits, &Rp);
+    dim3 grid(ntiles, 1, splits);
+    gram_labels2_kernel<<<grid, G2_PRODUCERS + 32, smem, st>>>(labels, F, L, npix, kblocks, per, nfr_max, Rp, work);
+    S2D_CHECK_LAUNCH("gram_labels2_kernel");
+    gram_reduce_kernel<<<(unsigned)(((int64_t)R * R + 255) / 256), 256, 0, st>>>(work, splits, R, Rp, G);
+    S2D_CHECK_LAUNCH("gram_reduce_kernel");
+    return 0;
 }
 
 template <int BN>
@@ -504,7 +714,14 @@ extern "C" int s2d_overlap_gram_work_ints(int nframes, int nlab, int64_t npix, i
     const int R = nframes * nlab, BN = R <= 128 ? 128 : 256;
     int mt, nt, kblocks, per, splits, Rp;
     gram_plan(R, BN, npix, &mt, &nt, &kblocks, &per, &splits, &Rp);
-    *out = (int64_t)splits * R * Rp + 4;
+    int64_t need = (int64_t)splits * R * Rp + 4;
+    if (R > 128) {                            // the two-m-tile kernel uses more, shorter splits
+        int ntiles;
+        gram2_plan(R, npix, &ntiles, &nt, &kblocks, &per, &splits, &Rp);
+        const int64_t need2 = (int64_t)splits * R * Rp + 4;
+        if (need2 > need) need = need2;
+    }
+    *out = need;
     return 0;
 }
 
@@ -517,5 +734,6 @@ extern "C" int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int n
     cudaStream_t st = (cudaStream_t)stream;
     const int R = nframes * nlab;
     if (R <= 128) return launch_gram<128>(labels, nframes, nlab, npix, work, G, st);
+    if (gram_use_v2(R)) return launch_gram2(labels, nframes, nlab, npix, work, G, st);
     return launch_gram<256>(labels, nframes, nlab, npix, work, G, st);
 }

@@ -277,7 +277,8 @@ def test_overlap_i8_tensor_core_vs_oracle(Na, Nb, H, W):
     assert np.array_equal(I.cpu().numpy().reshape(Na, Nb), rI)
 
 
-@pytest.mark.parametrize("F,L,H,W", [(3, 4, 16, 32), (6, 21, 48, 64), (36, 21, 96, 128), (13, 30, 120, 160)])
+@pytest.mark.parametrize("F,L,H,W", [(3, 4, 16, 32), (6, 21, 48, 64), (36, 21, 96, 128), (13, 30, 120, 160),
+                                     (10, 21, 17, 48), (50, 25, 64, 96), (12, 22, 19, 80)])
 def test_gram_labels_tensor_core_vs_oracle(F, L, H, W):
     """one-hot Gram matrix synthesised on-chip + tcgen05 kind::i8 == numpy one-hot contraction."""
     from s2d_b200 import _lib
