@@ -18,6 +18,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 namespace s2d {
 
 constexpr int GM_BLOCK_M = 128;
@@ -395,7 +397,8 @@ constexpr int G2_PRODUCERS = G2_AM + G2_BN;
 
 __global__ void __launch_bounds__(G2_PRODUCERS + 32, 1)
 gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npix, int kblocks_total,
-                    int kblocks_per_split, int nfr_max, int Rp, int32_t* __restrict__ part) {
+                    int nt, int s_off, int s_diag, int per_off, int per_diag, int nfr_max, int Rp,
+                    int32_t* __restrict__ part) {
     constexpr int STAGES = G2_STAGES;
     constexpr int PRODUCERS = G2_PRODUCERS;
     constexpr int A_BYTES = G2_AM * GM_BLOCK_K;
@@ -410,15 +413,24 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
 
     const int R = F * L;
     const int tid = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // symmetric: block column nj holds the block rows 0 .. nj (256 x 256 blocks)
-    int mi = blockIdx.x, nj = 0;
-    while (mi > nj) { mi -= nj + 1; ++nj; }
+    // symmetric: block column nj holds the block rows 0 .. nj (256 x 256 blocks). A diagonal block's A rows ARE its
+    // B rows: it synthesises the B tile only and points both A descriptors into it - half the producer work - so it
+    // gets fewer, longer pixel splits than an off-diagonal block (s_diag vs s_off) and all CTAs finish together.
+    int x = blockIdx.x, mi = 0, nj = 0;
+    for (;;) {
+        const int cnt = (mi == nj) ? s_diag : s_off;
+        if (x < cnt) break;
+        x -= cnt;
+        if (++mi > nj) { mi = 0; ++nj; }
+    }
+    const bool diag = mi == nj;
+    const int split = x, kblocks_per_split = diag ? per_diag : per_off;
     const int m0 = mi * G2_AM, n0 = nj * G2_BN;
-    const int kb0 = blockIdx.z * kblocks_per_split;
-    const int nkb = min(kblocks_total, kb0 + kblocks_per_split) - kb0;
+    const int kb0 = split * kblocks_per_split;
+    const int nkb = max(min(kblocks_total, kb0 + kblocks_per_split) - kb0, 0);
     const int fa0 = m0 / L, fa1 = min(R - 1, m0 + G2_AM - 1) / L;
     const int fb0 = min(n0, R - 1) / L, fb1 = min(R - 1, n0 + G2_BN - 1) / L;
-    const int nfa = fa1 - fa0 + 1, nfb = fb1 - fb0 + 1;
+    const int nfa = diag ? 0 : fa1 - fa0 + 1, nfb = fb1 - fb0 + 1;       // diagonal: no separate A frames
     const int slot_bytes = nfr_max * 128;
 
     if (threadIdx.x == 0) {
@@ -484,6 +496,7 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
                 issue_labels(i + GR_PF);             // refills the slot k-block i-1 used
                 make_desc(i + 1);
                 if (i >= STAGES) bar_wait(&empty[s], ((i / STAGES) - 1) & 1);
+                if (!(diag && isA)) {                // (whole warps: the A rows are the first 8 warps)
                 const uint8_t* lab = sLab + (i % (GR_PF + 1)) * slot_bytes + lab_off;
                 uint8_t* dst = sOps + s * (A_BYTES + B_BYTES) + row_off;
                 const uint2 d8 = *reinterpret_cast<const uint2*>(sDesc + (i & 1) * nfr_max * 8 + desc_off);
@@ -504,6 +517,7 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (MMA) reads
+                }
                 __syncwarp();
                 if (lane == 0) bar_arrive(&full[s]);                           // one arrival per producer warp
             }
@@ -514,7 +528,7 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
 #pragma unroll 1
                 for (int acc = 0; acc < 2; ++acc) {
                     const int row = m0 + acc * GM_BLOCK_M + warp * 32 + lane;
-                    int32_t* prow = part + ((int64_t)blockIdx.z * R + row) * Rp;
+                    int32_t* prow = part + ((int64_t)split * R + row) * Rp;
 #pragma unroll 1
                     for (int c0 = 0; c0 < G2_BN; c0 += 32) {
                         uint32_t v[32];
@@ -536,8 +550,9 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
                 const int s = i % STAGES;
                 bar_wait(&full[s], (i / STAGES) & 1);
                 tc_fence_after();
-                const uint64_t ad0 = umma_desc(s_u32(sOps + s * (A_BYTES + B_BYTES)));
-                const uint64_t ad1 = umma_desc(s_u32(sOps + s * (A_BYTES + B_BYTES) + GM_BLOCK_M * GM_BLOCK_K));
+                const uint8_t* abase = sOps + s * (A_BYTES + B_BYTES) + (diag ? A_BYTES : 0);     // diagonal: A = B
+                const uint64_t ad0 = umma_desc(s_u32(abase));
+                const uint64_t ad1 = umma_desc(s_u32(abase + GM_BLOCK_M * GM_BLOCK_K));
                 const uint64_t bd = umma_desc(s_u32(sOps + s * (A_BYTES + B_BYTES) + A_BYTES));
 #pragma unroll
                 for (int k = 0; k < GM_BLOCK_K / GM_UMMA_K; ++k) {
@@ -556,13 +571,15 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
 }
 
 // G[r][c] = sum over splits of part[s][r][c]  (row pitch Rp in part, R in G)
-__global__ void gram_reduce_kernel(const int32_t* __restrict__ part, int splits, int R, int Rp, int32_t* __restrict__ G) {
+// `splits_diag` > 0: 256 x 256 blocks on the diagonal were split `splits_diag` times, the others `splits` times
+__global__ void gram_reduce_kernel(const int32_t* __restrict__ part, int splits, int splits_diag, int R, int Rp, int32_t* __restrict__ G) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)R * R) return;
     const int r = (int)(i / R), c = (int)(i - (int64_t)r * R);
     const int rr = min(r, c), cc = max(r, c);          // only upper-triangle tiles were computed
+    const int ns = (splits_diag > 0 && (rr >> 8) == (cc >> 8)) ? splits_diag : splits;
     int acc = 0;
-    for (int s = 0; s < splits; ++s) acc += part[((int64_t)s * R + rr) * Rp + cc];
+    for (int s = 0; s < ns; ++s) acc += part[((int64_t)s * R + rr) * Rp + cc];
     G[i] = acc;
 }
 
@@ -584,15 +601,27 @@ static void gram_plan(int R, int BN, int64_t npix, int* mt, int* nt, int* kblock
     *Rp = *nt * BN;                          // every column an epilogue may store exists
 }
 
-static void gram2_plan(int R, int64_t npix, int* ntiles, int* nt, int* kblocks, int* per, int* splits, int* Rp) {
+// splits of the pixel range per block so that one wave of <= 148 CTAs finishes together: a diagonal block costs
+// G2_DIAG_COST of an off-diagonal one (it synthesises half the operand rows, but see the constant)
+constexpr double G2_DIAG_COST = 1.0;   // measured: the per-k-block latency chain, not the number of rows, sets the pace
+static void gram2_plan(int R, int64_t npix, int* nt, int* kblocks, int* s_off, int* s_diag, int* per_off, int* per_diag, int* Rp) {
     *nt = (R + G2_BN - 1) / G2_BN;
-    *ntiles = *nt * (*nt + 1) / 2;            // 256 x 256 blocks on or above the diagonal
+    const int nd = *nt, no = *nt * (*nt - 1) / 2;
     *kblocks = (int)((npix + GM_BLOCK_K - 1) / GM_BLOCK_K);
-    int sp = 148 / *ntiles;                  // one wave of CTAs (1 CTA per SM)
-    if (sp > *kblocks) sp = *kblocks;
-    if (sp < 1) sp = 1;
-    *per = (*kblocks + sp - 1) / sp;
-    *splits = (*kblocks + *per - 1) / *per;
+    int best_o = no ? 1 : 0, best_d = 1;
+    double best = 1e300;
+    for (int sd = 1; sd <= 148; ++sd) {
+        const int so = no ? (148 - nd * sd) / no : 0;
+        if (no && so < 1) break;
+        const double t = std::max(no ? 1.0 / so : 0.0, G2_DIAG_COST / sd);       // time of the slowest CTA
+        if (t < best) { best = t; best_o = so; best_d = sd; }
+    }
+    if (best_d > *kblocks) best_d = *kblocks;
+    if (best_o > *kblocks) best_o = *kblocks;
+    *per_off = best_o ? (*kblocks + best_o - 1) / best_o : 0;
+    *per_diag = (*kblocks + best_d - 1) / best_d;
+    *s_off = best_o ? (*kblocks + *per_off - 1) / *per_off : 0;       // no empty splits
+    *s_diag = (*kblocks + *per_diag - 1) / *per_diag;
     *Rp = *nt * G2_BN;
 }
 
@@ -610,12 +639,13 @@ static int launch_gram2(const uint8_t* labels, int F, int L, int64_t npix, int32
     if (smem > 227 * 1024) { set_error("s2d_overlap_gram_labels: nlab=%d is too small for the label ring (needs %d B of shared memory)", L, smem); return -1; }
     cudaError_t e = cudaFuncSetAttribute(gram_labels2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("gram_labels2_kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return -2; }
-    int ntiles, nt, kblocks, per, splits, Rp;
-    gram2_plan(R, npix, &ntiles, &nt, &kblocks, &per, &splits, &Rp);
-    dim3 grid(ntiles, 1, splits);
-    gram_labels2_kernel<<<grid, G2_PRODUCERS + 32, smem, st>>>(labels, F, L, npix, kblocks, per, nfr_max, Rp, work);
+    int nt, kblocks, s_off, s_diag, per_off, per_diag, Rp;
+    gram2_plan(R, npix, &nt, &kblocks, &s_off, &s_diag, &per_off, &per_diag, &Rp);
+    const int nctas = nt * s_diag + nt * (nt - 1) / 2 * s_off;
+    gram_labels2_kernel<<<nctas, G2_PRODUCERS + 32, smem, st>>>(labels, F, L, npix, kblocks, nt, s_off, s_diag, per_off, per_diag,
+                                                              nfr_max, Rp, work);
     S2D_CHECK_LAUNCH("gram_labels2_kernel");
-    gram_reduce_kernel<<<(unsigned)(((int64_t)R * R + 255) / 256), 256, 0, st>>>(work, splits, R, Rp, G);
+    gram_reduce_kernel<<<(unsigned)(((int64_t)R * R + 255) / 256), 256, 0, st>>>(work, s_off, s_diag, R, Rp, G);
     S2D_CHECK_LAUNCH("gram_reduce_kernel");
     return 0;
 }
@@ -634,7 +664,7 @@ static int launch_gram(const uint8_t* labels, int F, int L, int64_t npix, int32_
     dim3 grid(gram_tiles(mt, nt, BN), 1, splits);
     kfn<<<grid, GR_GROUPS * (GM_BLOCK_M + BN) + 32, smem, st>>>(labels, F, L, npix, kblocks, per, nfr_max, Rp, mt, work);
     S2D_CHECK_LAUNCH("gram_labels_kernel");
-    gram_reduce_kernel<<<(unsigned)(((int64_t)R * R + 255) / 256), 256, 0, st>>>(work, splits, R, Rp, G);
+    gram_reduce_kernel<<<(unsigned)(((int64_t)R * R + 255) / 256), 256, 0, st>>>(work, splits, 0, R, Rp, G);
     S2D_CHECK_LAUNCH("gram_reduce_kernel");
     return 0;
 }
@@ -716,9 +746,9 @@ extern "C" int s2d_overlap_gram_work_ints(int nframes, int nlab, int64_t npix, i
     gram_plan(R, BN, npix, &mt, &nt, &kblocks, &per, &splits, &Rp);
     int64_t need = (int64_t)splits * R * Rp + 4;
     if (R > 128) {                            // the two-m-tile kernel uses more, shorter splits
-        int ntiles;
-        gram2_plan(R, npix, &ntiles, &nt, &kblocks, &per, &splits, &Rp);
-        const int64_t need2 = (int64_t)splits * R * Rp + 4;
+        int s_off, s_diag, per_off, per_diag;
+        gram2_plan(R, npix, &nt, &kblocks, &s_off, &s_diag, &per_off, &per_diag, &Rp);
+        const int64_t need2 = (int64_t)(s_off > s_diag ? s_off : s_diag) * R * Rp + 4;
         if (need2 > need) need = need2;
     }
     *out = need;
