@@ -393,29 +393,33 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
 constexpr int G2_AM = 256;               // A rows per CTA (two M = 128 instruction tiles)
 constexpr int G2_BN = 256;
 constexpr int G2_STAGES = 3;
-constexpr int G2_PRODUCERS = G2_AM + G2_BN;
+constexpr int G2_GROUPS = 2;             // producer groups working on alternate k-blocks
+constexpr int G2_GTHREADS = 256;         // threads per group: thread t builds A row t and B row t
+constexpr int G2_PRODUCERS = G2_GROUPS * G2_GTHREADS;
 
 __global__ void __launch_bounds__(G2_PRODUCERS + 32, 1)
 gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npix, int kblocks_total,
                     int nt, int s_off, int s_diag, int per_off, int per_diag, int nfr_max, int Rp,
                     int32_t* __restrict__ part) {
     constexpr int STAGES = G2_STAGES;
-    constexpr int PRODUCERS = G2_PRODUCERS;
+    constexpr int GT = G2_GTHREADS;
     constexpr int A_BYTES = G2_AM * GM_BLOCK_K;
     constexpr int B_BYTES = G2_BN * GM_BLOCK_K;
+    static_assert(G2_AM == GT && G2_BN == GT, "one A row and one B row per producer thread");
     extern __shared__ __align__(1024) uint8_t gsm_raw[];
     uint8_t* gsm = gsm_raw + ((1024u - (s_u32(gsm_raw) & 1023u)) & 1023u);
     uint8_t* sOps = gsm;                                         // STAGES x (A tile | B tile)
-    uint8_t* sLab = gsm + STAGES * (A_BYTES + B_BYTES);          // (GR_PF + 1) label slots x nfr_max x 128 B
-    uint8_t* sDesc = sLab + (GR_PF + 1) * nfr_max * 128;         // 2 slots x nfr_max x 8 chunk descriptors
+    const int grp = threadIdx.x / GT;                            // 0, 1: producer groups; 2: MMA warp
+    // per producer group: (GR_PF + 1) label slots x nfr_max x 128 B, then 2 slots x nfr_max x 8 chunk descriptors
+    uint8_t* sLab = gsm + STAGES * (A_BYTES + B_BYTES) + (grp & 1) * ((GR_PF + 1) * nfr_max * 128 + 2 * nfr_max * 8);
+    uint8_t* sDesc = sLab + (GR_PF + 1) * nfr_max * 128;
     __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], accum_full;
     __shared__ uint32_t tmem_base;
 
     const int R = F * L;
-    const int tid = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = threadIdx.x % GT, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // tid: index inside the group
     // symmetric: block column nj holds the block rows 0 .. nj (256 x 256 blocks). A diagonal block's A rows ARE its
-    // B rows: it synthesises the B tile only and points both A descriptors into it - half the producer work - so it
-    // gets fewer, longer pixel splits than an off-diagonal block (s_diag vs s_off) and all CTAs finish together.
+    // B rows: it synthesises the B tile only and points both A descriptors into it.
     int x = blockIdx.x, mi = 0, nj = 0;
     for (;;) {
         const int cnt = (mi == nj) ? s_diag : s_off;
@@ -434,7 +438,7 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
     const int slot_bytes = nfr_max * 128;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], PRODUCERS / 32); bar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { bar_init(&full[s], GT / 32); bar_init(&empty[s], 1); }
         bar_init(&accum_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -445,23 +449,22 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
     const uint32_t tmem = tmem_base;
 
     if (nkb > 0) {
-        if (tid < PRODUCERS) {
-            // ---- operand producers: one thread per operand row, every k-block ----
-            const bool isA = tid < G2_AM;
-            const int rl = isA ? tid : tid - G2_AM;
-            const int r = (isA ? m0 : n0) + rl;
-            const bool rvalid = r < R;
-            const int f = rvalid ? r / L : 0;
-            const uint32_t sp = rvalid ? (uint32_t)(r - f * L) * 0x01010101u : 0xFEFEFEFEu;   // 0xFE never matches (L <= 254)
-            const int lab_off = (isA ? (f - fa0) : nfa + (f - fb0)) * 128;
-            const int row_off = (isA ? 0 : A_BYTES) + rl * 128;
-            const int r7 = rl & 7;
+        if (grp < G2_GROUPS) {
+            // ---- operand producers: thread t of a group builds A row t and B row t; group g takes k-blocks g, g+2, ... ----
+            const int rA = m0 + tid, rB = n0 + tid;
+            const bool vA = rA < R && !diag, vB = rB < R;
+            const int fA = rA < R ? rA / L : 0, fB = vB ? rB / L : 0;
+            const uint32_t spA = vA ? (uint32_t)(rA - fA * L) * 0x01010101u : 0xFEFEFEFEu;   // 0xFE never matches (L <= 254)
+            const uint32_t spB = vB ? (uint32_t)(rB - fB * L) * 0x01010101u : 0xFEFEFEFEu;
+            const int frA = diag ? 0 : fA - fa0, frB = nfa + (fB - fb0);                      // frame slots in the label ring
+            const int r7 = tid & 7;
 
-            auto issue_labels = [&](int i) {        // label bytes of k-block i -> ring slot i % (GR_PF + 1)
+            auto issue_labels = [&](int ii) {       // label bytes of local k-block ii -> ring slot ii % (GR_PF + 1)
+                const int i = ii * G2_GROUPS + grp;
                 if (i < nkb) {
-                    uint8_t* slot = sLab + (i % (GR_PF + 1)) * slot_bytes;
+                    uint8_t* slot = sLab + (ii % (GR_PF + 1)) * slot_bytes;
                     const int64_t px0 = (int64_t)(kb0 + i) * GM_BLOCK_K;
-                    for (int j = tid; j < (nfa + nfb) * 8; j += PRODUCERS) {
+                    for (int j = tid; j < (nfa + nfb) * 8; j += GT) {
                         const int fr = j >> 3, c = j & 7;
                         const int ff = fr < nfa ? fa0 + fr : fb0 + (fr - nfa);
                         const int64_t px = px0 + 16 * c;
@@ -471,35 +474,25 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
                 }
                 cp_async_commit();
             };
-            auto make_desc = [&](int i) {           // per 16-pixel chunk: its single label, 0xFF when mixed
-                if (i < nkb) {
-                    const uint8_t* slot = sLab + (i % (GR_PF + 1)) * slot_bytes;
-                    for (int j = tid; j < (nfa + nfb) * 8; j += PRODUCERS) {
+            auto make_desc = [&](int ii) {          // per 16-pixel chunk: its single label, 0xFF when mixed
+                if (ii * G2_GROUPS + grp < nkb) {
+                    const uint8_t* slot = sLab + (ii % (GR_PF + 1)) * slot_bytes;
+                    for (int j = tid; j < (nfa + nfb) * 8; j += GT) {
                         const uint4 w = *reinterpret_cast<const uint4*>(slot + j * 16);
                         const bool uni = (w.x == w.y) & (w.y == w.z) & (w.z == w.w) & (w.x == __byte_perm(w.x, 0, 0x0000));
-                        sDesc[(i & 1) * nfr_max * 8 + j] = uni ? (uint8_t)(w.x & 255u) : (uint8_t)0xFF;
+                        sDesc[(ii & 1) * nfr_max * 8 + j] = uni ? (uint8_t)(w.x & 255u) : (uint8_t)0xFF;
                     }
                 }
             };
-            for (int j = 0; j < GR_PF; ++j) issue_labels(j);
-            cp_async_wait<GR_PF - 1>();
-            asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");
-            make_desc(0);
+            auto group_sync = [&]() {
+                if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(GT) : "memory");
+                else asm volatile("bar.sync 2, %0;" ::"n"(GT) : "memory");
+            };
             const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
             const uint4 zeros = make_uint4(0, 0, 0, 0);
-            const uint32_t mylab = sp & 255u;
-            const int desc_off = (isA ? (f - fa0) : nfa + (f - fb0)) * 8;
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES;
-                cp_async_wait<GR_PF - 2>();          // this thread's copies of k-blocks <= i+1 have landed
-                asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");   // everybody's; desc(i) visible; k-block i-1 consumed
-                issue_labels(i + GR_PF);             // refills the slot k-block i-1 used
-                make_desc(i + 1);
-                if (i >= STAGES) bar_wait(&empty[s], ((i / STAGES) - 1) & 1);
-                if (!(diag && isA)) {                // (whole warps: the A rows are the first 8 warps)
-                const uint8_t* lab = sLab + (i % (GR_PF + 1)) * slot_bytes + lab_off;
-                uint8_t* dst = sOps + s * (A_BYTES + B_BYTES) + row_off;
-                const uint2 d8 = *reinterpret_cast<const uint2*>(sDesc + (i & 1) * nfr_max * 8 + desc_off);
+            // one operand row of the k-block: 8 chunks of 16 pixels
+            auto build_row = [&](uint8_t* dst, const uint8_t* lab, uint2 d8, uint32_t sp, bool rvalid) {
+                const uint32_t mylab = sp & 255u;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const uint32_t u = ((c < 4 ? d8.x : d8.y) >> (8 * (c & 3))) & 255u;
@@ -516,10 +509,29 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
                         *out = o;
                     }
                 }
+            };
+            const int nloc = (nkb - grp + G2_GROUPS - 1) / G2_GROUPS;
+            for (int j = 0; j < GR_PF; ++j) issue_labels(j);
+            cp_async_wait<GR_PF - 1>();
+            group_sync();
+            make_desc(0);
+            for (int ii = 0; ii < nloc; ++ii) {
+                const int i = ii * G2_GROUPS + grp;
+                const int s = i % STAGES;
+                cp_async_wait<GR_PF - 2>();          // this thread's copies of local k-blocks <= ii+1 have landed
+                group_sync();                        // everybody's; desc(ii) visible; local k-block ii-1 consumed
+                issue_labels(ii + GR_PF);            // refills the slot local k-block ii-1 used
+                make_desc(ii + 1);
+                if (i >= STAGES) bar_wait(&empty[s], ((i / STAGES) - 1) & 1);
+                const uint8_t* slot = sLab + (ii % (GR_PF + 1)) * slot_bytes;
+                const uint8_t* dsc = sDesc + (ii & 1) * nfr_max * 8;
+                uint8_t* stage = sOps + s * (A_BYTES + B_BYTES);
+                if (!diag)
+                    build_row(stage + tid * 128, slot + frA * 128, *reinterpret_cast<const uint2*>(dsc + frA * 8), spA, vA);
+                build_row(stage + A_BYTES + tid * 128, slot + frB * 128, *reinterpret_cast<const uint2*>(dsc + frB * 8), spB, vB);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (MMA) reads
-                }
                 __syncwarp();
-                if (lane == 0) bar_arrive(&full[s]);                           // one arrival per producer warp
+                if (lane == 0) bar_arrive(&full[s]);                           // one arrival per producer warp of the group
             }
             // ---- epilogue: warps 0-3 own the four TMEM lane quarters; two accumulators (A rows 0-127 and 128-255) ----
             if (warp < 4) {
@@ -635,7 +647,7 @@ static int launch_gram2(const uint8_t* labels, int F, int L, int64_t npix, int32
     const int R = F * L;
     const int per_tile = G2_AM / L + 2;
     const int nfr_max = 2 * (F < per_tile ? F : per_tile);
-    const int smem = G2_STAGES * (G2_AM + G2_BN) * GM_BLOCK_K + (GR_PF + 1) * nfr_max * 128 + 2 * nfr_max * 8 + 1024;
+    const int smem = G2_STAGES * (G2_AM + G2_BN) * GM_BLOCK_K + G2_GROUPS * ((GR_PF + 1) * nfr_max * 128 + 2 * nfr_max * 8) + 1024;
     if (smem > 227 * 1024) { set_error("s2d_overlap_gram_labels: nlab=%d is too small for the label ring (needs %d B of shared memory)", L, smem); return -1; }
     cudaError_t e = cudaFuncSetAttribute(gram_labels2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("gram_labels2_kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return -2; }
