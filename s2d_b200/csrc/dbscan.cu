@@ -11,6 +11,7 @@ namespace s2d {
 constexpr int DB_THREADS = 256;
 constexpr int DB_ROWS_I = 32;     // rows i per CTA: 8 warps x 4 rows
 constexpr int DB_NWC = 64;        // word chunk staged in shared memory
+constexpr int DB_JT = 1;          // 32-row tiles of rows j staged per barrier pair (4 was measured: no gain)
 
 __device__ __forceinline__ int uf_find(int32_t* parent, int i) {
     while (true) {
@@ -22,15 +23,24 @@ __device__ __forceinline__ int uf_find(int32_t* parent, int i) {
     }
 }
 
-// hook the larger root under the smaller one: the root of a component is its minimum index
-__device__ __forceinline__ void uf_unite(int32_t* parent, int a, int b) {
+// hook the larger root under the smaller one: the root of a component is its minimum index.
+// Returns the root the two rows shared when the call returned.
+__device__ __forceinline__ int uf_unite(int32_t* parent, int a, int b) {
     while (true) {
         a = uf_find(parent, a);
         b = uf_find(parent, b);
-        if (a == b) return;
+        if (a == b) return a;
         if (a < b) { int t = a; a = b; b = t; }
-        if (atomicCAS(&parent[a], a, b) == a) return;
+        if (atomicCAS(&parent[a], a, b) == a) return b;
     }
+}
+
+// carry-save adder on 32 bit lanes: (carry, sum) = a + b + c. POPC issues at a quarter of the LOP3 rate, so the
+// distance loops count four words with one POPC instead of four.
+__device__ __forceinline__ void csa(uint32_t& carry, uint32_t& sum, uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t u = a ^ b;
+    carry = (a & b) | (u & c);
+    sum = u ^ c;
 }
 
 template <int MODE>   // 0: neighbour counts -> core   1: unions   2: border -> min core root
@@ -41,16 +51,18 @@ __global__ void __launch_bounds__(DB_THREADS) db_pass_kernel(const DbProblem* __
     if (i0 >= N) return;
 
     __shared__ uint32_t xi[DB_ROWS_I][DB_NWC];
-    __shared__ uint32_t xjT[DB_NWC][33];
+    __shared__ uint32_t xjT[DB_NWC][32 * DB_JT + 1];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int irow[4];
     bool icore[4];
     int acc[4];   // MODE0: neighbour count; MODE2: min root
+    int imember[4];   // MODE1: a row of irow[r]'s component (lane-private view)
     bool mine = false;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         irow[r] = i0 + warp * 4 + r;
+        imember[r] = irow[r];
         icore[r] = false;
         acc[r] = (MODE == 2) ? INT_MAX : 0;
         if (MODE != 0 && irow[r] < N) icore[r] = p.core[irow[r]] != 0;
@@ -60,48 +72,88 @@ __global__ void __launch_bounds__(DB_THREADS) db_pass_kernel(const DbProblem* __
 
     const int jend = (MODE == 1) ? min(N, i0 + DB_ROWS_I) : N;   // unions only need j < i
     const bool single_chunk = p.nw <= DB_NWC;
-    for (int j0 = 0; j0 < jend; j0 += 32) {
-        int dist[4] = {0, 0, 0, 0};
+    constexpr int JROWS = 32 * DB_JT;            // rows j staged per round: DB_JT tiles of 32, one barrier pair for all
+    for (int j0 = 0; j0 < jend; j0 += JROWS) {
+        int dist[DB_JT][4];
+        uint32_t ones[DB_JT][4], twos[DB_JT][4];   // carry-save partial counts (weights 1 and 2)
+#pragma unroll
+        for (int jt = 0; jt < DB_JT; ++jt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { dist[jt][r] = 0; ones[jt][r] = 0; twos[jt][r] = 0; }
+        const int jrows = min(JROWS, ((jend - j0 + 31) >> 5) << 5);
         for (int c0 = 0; c0 < p.nw; c0 += DB_NWC) {
             const int cw = min(DB_NWC, p.nw - c0);
             __syncthreads();
             if (!(single_chunk && j0 > 0)) {
-                for (int idx = tid; idx < DB_ROWS_I * cw; idx += DB_THREADS) {
-                    const int r = idx / cw, w = idx - r * cw, row = i0 + r;
+                const int cwp = (cw + 3) & ~3;
+                for (int idx = tid; idx < DB_ROWS_I * cwp; idx += DB_THREADS) {
+                    const int r = idx / cwp, w = idx - r * cwp, row = i0 + r;
                     uint32_t v = 0;
-                    if (row < N && (!p.valid || p.valid[row])) v = p.bits[(int64_t)row * p.stride + p.w0 + c0 + w];
+                    if (w < cw && row < N && (!p.valid || p.valid[row])) v = p.bits[(int64_t)row * p.stride + p.w0 + c0 + w];
                     xi[r][w] = v;
                 }
             }
-            for (int idx = tid; idx < 32 * cw; idx += DB_THREADS) {
-                const int r = idx / cw, w = idx - r * cw, row = j0 + r;
+            const int cw4 = (cw + 3) & ~3;           // the distance loop eats 4 words at a time: pad with zeros
+            for (int idx = tid; idx < jrows * cw4; idx += DB_THREADS) {
+                const int r = idx / cw4, w = idx - r * cw4, row = j0 + r;
                 uint32_t v = 0;
-                if (row < N && (!p.valid || p.valid[row])) v = p.bits[(int64_t)row * p.stride + p.w0 + c0 + w];
+                if (w < cw && row < N && (!p.valid || p.valid[row])) v = p.bits[(int64_t)row * p.stride + p.w0 + c0 + w];
                 xjT[w][r] = v;
             }
             __syncthreads();
-            for (int w = 0; w < cw; ++w) {
-                const uint32_t xj = xjT[w][lane];
+            for (int w = 0; w < cw4; w += 4) {
+                uint32_t x[4][4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) dist[r] += __popc(xi[warp * 4 + r][w] ^ xj);
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) x[r][k] = xi[warp * 4 + r][w + k];
+#pragma unroll
+                for (int jt = 0; jt < DB_JT; ++jt) {
+                    if (jt * 32 < jrows) {
+                        uint32_t xj[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) xj[k] = xjT[w + k][jt * 32 + lane];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            uint32_t ta, tb, f;
+                            csa(ta, ones[jt][r], ones[jt][r], x[r][0] ^ xj[0], x[r][1] ^ xj[1]);
+                            csa(tb, ones[jt][r], ones[jt][r], x[r][2] ^ xj[2], x[r][3] ^ xj[3]);
+                            csa(f, twos[jt][r], twos[jt][r], ta, tb);
+                            dist[jt][r] += __popc(f);                 // in units of 4
+                        }
+                    }
+                }
             }
         }
-        const int j = j0 + lane;
-        const bool jv = j < N;
-        bool jcore = false;
-        if (MODE != 0 && jv) jcore = p.core[j] != 0;
-        int jroot = INT_MAX;
-        if (MODE == 2 && jcore) jroot = uf_find(p.parent, j);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const bool nb = jv && irow[r] < N && dist[r] <= p.kmax;
-            if (MODE == 0) {
-                acc[r] += __popc(__ballot_sync(0xffffffffu, nb));
-            } else if (MODE == 1) {
-                if (nb && icore[r] && jcore && j < irow[r]) uf_unite(p.parent, irow[r], j);
-            } else {
-                const int cand = (nb && !icore[r] && jcore) ? jroot : INT_MAX;
-                acc[r] = min(acc[r], __reduce_min_sync(0xffffffffu, cand));
+        for (int jt = 0; jt < DB_JT; ++jt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) dist[jt][r] = 4 * dist[jt][r] + 2 * __popc(twos[jt][r]) + __popc(ones[jt][r]);
+#pragma unroll
+        for (int jt = 0; jt < DB_JT; ++jt) {
+            if (jt * 32 >= jrows) break;
+            const int j = j0 + jt * 32 + lane;
+            const bool jv = j < N;
+            bool jcore = false;
+            if (MODE != 0 && jv) jcore = p.core[j] != 0;
+            int jroot = INT_MAX;
+            if (MODE == 2 && jcore) jroot = uf_find(p.parent, j);
+            // MODE 1: a row of j's component (its parent when read). Equal to a row known to be in i's component =>
+            // already united; components never split, so a stale value only costs a redundant find.
+            int jmember = -1;
+            if (MODE == 1 && jcore) jmember = p.parent[j];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const bool nb = jv && irow[r] < N && dist[jt][r] <= p.kmax;
+                if (MODE == 0) {
+                    acc[r] += __popc(__ballot_sync(0xffffffffu, nb));
+                } else if (MODE == 1) {
+                    if (nb && icore[r] && jcore && j < irow[r] && jmember != imember[r])
+                        imember[r] = jmember = uf_unite(p.parent, irow[r], j);
+                } else {
+                    const int cand = (nb && !icore[r] && jcore) ? jroot : INT_MAX;
+                    acc[r] = min(acc[r], __reduce_min_sync(0xffffffffu, cand));
+                }
             }
         }
     }

@@ -50,16 +50,26 @@ label_hist_kernel(const s2d_video_desc* __restrict__ descs, int32_t* __restrict_
         }
     }
     const int4* vp = reinterpret_cast<const int4*>(base + vbeg);
-    for (int64_t i = threadIdx.x; i < nvec; i += LH_THREADS) {
-        int4 w = ld_stream(vp + i);
-        const uint32_t splat = (uint32_t)cur * 0x01010101u;
-        if (((uint32_t)w.x == splat) & ((uint32_t)w.y == splat) & ((uint32_t)w.z == splat) & ((uint32_t)w.w == splat)) {
+    // a thread's consecutive vectors are 4 KB apart, so the label it carries rarely matches the next vector: test the
+    // vector (then each word) for "one label throughout" against its own first byte, not against `cur`
+    auto eat = [&](const int4 w) {
+        const uint32_t ws[4] = {(uint32_t)w.x, (uint32_t)w.y, (uint32_t)w.z, (uint32_t)w.w};
+        const uint32_t s0 = __byte_perm(ws[0], 0, 0x0000);
+        if ((ws[0] == s0) & (ws[1] == s0) & (ws[2] == s0) & (ws[3] == s0)) {
+            const int v = (int)(s0 & 255u);
+            if (v != cur) { hist_flush(mywh, cur, cnt); cur = v; cnt = 0; }
             cnt += 16;
-            continue;
+            return;
         }
-        uint32_t ws[4] = {(uint32_t)w.x, (uint32_t)w.y, (uint32_t)w.z, (uint32_t)w.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+            const uint32_t sk = __byte_perm(ws[k], 0, 0x0000);
+            if (ws[k] == sk) {
+                const int v = (int)(sk & 255u);
+                if (v != cur) { hist_flush(mywh, cur, cnt); cur = v; cnt = 0; }
+                cnt += 4;
+                continue;
+            }
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 int v = (ws[k] >> (8 * b)) & 255;
@@ -67,7 +77,15 @@ label_hist_kernel(const s2d_video_desc* __restrict__ descs, int32_t* __restrict_
                 ++cnt;
             }
         }
+    };
+    // four independent 128-bit streaming loads in flight per thread, then the (divergent) run-length pass over them
+    int64_t i = threadIdx.x;
+    for (; i + 3 * LH_THREADS < nvec; i += 4 * LH_THREADS) {
+        const int4 w0 = ld_stream(vp + i), w1 = ld_stream(vp + i + LH_THREADS);
+        const int4 w2 = ld_stream(vp + i + 2 * LH_THREADS), w3 = ld_stream(vp + i + 3 * LH_THREADS);
+        eat(w0); eat(w1); eat(w2); eat(w3);
     }
+    for (; i < nvec; i += LH_THREADS) eat(ld_stream(vp + i));
     hist_flush(mywh, cur, cnt);
     __syncthreads();
     int32_t* out = area + (d.frame0 + t) * S2D_MAX_LABELS;
