@@ -156,6 +156,14 @@ __global__ void __launch_bounds__(DB_THREADS) db_pass_kernel(const DbProblem* __
                 }
             }
         }
+        if (MODE == 0) {
+            // only "count >= min_samples" is ever read: stop scanning once every row of the CTA has got there
+            // (rows of one object are mutual neighbours, so a handful of frames' worth of rows j is usually enough)
+            bool done = true;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) done &= irow[r] >= N || acc[r] >= p.min_samples;
+            if (__syncthreads_and(done)) break;
+        }
     }
     if (lane == 0) {
 #pragma unroll

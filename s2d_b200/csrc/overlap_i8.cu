@@ -643,11 +643,18 @@ static bool gram_use_v2(int R) {
     return R > 256;
 }
 
-static int launch_gram2(const uint8_t* labels, int F, int L, int64_t npix, int32_t* work, int32_t* G, cudaStream_t st) {
-    const int R = F * L;
+// shared memory of the two-m-tile kernel: the label ring grows with the frames a 256-row tile touches (256 / L + 2)
+static int gram2_smem(int F, int L, int* nfr_max_out) {
     const int per_tile = G2_AM / L + 2;
     const int nfr_max = 2 * (F < per_tile ? F : per_tile);
-    const int smem = G2_STAGES * (G2_AM + G2_BN) * GM_BLOCK_K + G2_GROUPS * ((GR_PF + 1) * nfr_max * 128 + 2 * nfr_max * 8) + 1024;
+    if (nfr_max_out) *nfr_max_out = nfr_max;
+    return G2_STAGES * (G2_AM + G2_BN) * GM_BLOCK_K + G2_GROUPS * ((GR_PF + 1) * nfr_max * 128 + 2 * nfr_max * 8) + 1024;
+}
+
+static int launch_gram2(const uint8_t* labels, int F, int L, int64_t npix, int32_t* work, int32_t* G, cudaStream_t st) {
+    const int R = F * L;
+    int nfr_max;
+    const int smem = gram2_smem(F, L, &nfr_max);
     if (smem > 227 * 1024) { set_error("s2d_overlap_gram_labels: nlab=%d is too small for the label ring (needs %d B of shared memory)", L, smem); return -1; }
     cudaError_t e = cudaFuncSetAttribute(gram_labels2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("gram_labels2_kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return -2; }
@@ -662,11 +669,17 @@ static int launch_gram2(const uint8_t* labels, int F, int L, int64_t npix, int32
     return 0;
 }
 
+static int gram1_smem(int BN, int F, int L, int* nfr_max_out) {
+    const int nfr_max = (F < GM_BLOCK_M / L + 2 ? F : GM_BLOCK_M / L + 2) + (F < BN / L + 2 ? F : BN / L + 2);
+    if (nfr_max_out) *nfr_max_out = nfr_max;
+    return GR_STAGES * (GM_BLOCK_M + BN) * GM_BLOCK_K + GR_GROUPS * ((GR_PF + 1) * nfr_max * 128 + 2 * nfr_max * 8) + 1024;
+}
+
 template <int BN>
 static int launch_gram(const uint8_t* labels, int F, int L, int64_t npix, int32_t* work, int32_t* G, cudaStream_t st) {
     const int R = F * L;
-    const int nfr_max = (F < GM_BLOCK_M / L + 2 ? F : GM_BLOCK_M / L + 2) + (F < BN / L + 2 ? F : BN / L + 2);
-    const int smem = GR_STAGES * (GM_BLOCK_M + BN) * GM_BLOCK_K + GR_GROUPS * ((GR_PF + 1) * nfr_max * 128 + 2 * nfr_max * 8) + 1024;
+    int nfr_max;
+    const int smem = gram1_smem(BN, F, L, &nfr_max);
     if (smem > 227 * 1024) { set_error("s2d_overlap_gram_labels: nlab=%d is too small for the label ring (needs %d B of shared memory)", L, smem); return -1; }
     auto kfn = gram_labels_kernel<BN>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -753,10 +766,15 @@ extern "C" int s2d_overlap_i8(const uint8_t* A, int Na, const uint8_t* B, int Nb
 
 extern "C" int s2d_overlap_gram_work_ints(int nframes, int nlab, int64_t npix, int64_t* out) {
     if (!out || nframes <= 0 || nlab <= 0 || npix <= 0) return -1;
-    const int R = nframes * nlab, BN = R <= 128 ? 128 : 256;
+    const int R = nframes * nlab;
     int mt, nt, kblocks, per, splits, Rp;
-    gram_plan(R, BN, npix, &mt, &nt, &kblocks, &per, &splits, &Rp);
+    gram_plan(R, 128, npix, &mt, &nt, &kblocks, &per, &splits, &Rp);
     int64_t need = (int64_t)splits * R * Rp + 4;
+    if (R > 128) {                            // whichever tiling s2d_overlap_gram_labels ends up using
+        gram_plan(R, 256, npix, &mt, &nt, &kblocks, &per, &splits, &Rp);
+        const int64_t need1 = (int64_t)splits * R * Rp + 4;
+        if (need1 > need) need = need1;
+    }
     if (R > 128) {                            // the two-m-tile kernel uses more, shorter splits
         int s_off, s_diag, per_off, per_diag;
         gram2_plan(R, npix, &nt, &kblocks, &s_off, &s_diag, &per_off, &per_diag, &Rp);
@@ -776,6 +794,10 @@ extern "C" int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int n
     cudaStream_t st = (cudaStream_t)stream;
     const int R = nframes * nlab;
     if (R <= 128) return launch_gram<128>(labels, nframes, nlab, npix, work, G, st);
-    if (gram_use_v2(R)) return launch_gram2(labels, nframes, nlab, npix, work, G, st);
-    return launch_gram<256>(labels, nframes, nlab, npix, work, G, st);
+    // few labels per frame = many frames per operand tile = a bigger label ring: fall back to the narrower tilings
+    // (256 x 256 two-m-tile -> 128 x 256 -> 128 x 128) until the ring fits beside the operand stages
+    constexpr int SMEM_MAX = 227 * 1024;
+    if (gram_use_v2(R) && gram2_smem(nframes, nlab, nullptr) <= SMEM_MAX) return launch_gram2(labels, nframes, nlab, npix, work, G, st);
+    if (gram1_smem(256, nframes, nlab, nullptr) <= SMEM_MAX) return launch_gram<256>(labels, nframes, nlab, npix, work, G, st);
+    return launch_gram<128>(labels, nframes, nlab, npix, work, G, st);
 }

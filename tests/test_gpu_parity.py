@@ -278,7 +278,10 @@ def test_overlap_i8_tensor_core_vs_oracle(Na, Nb, H, W):
 
 
 @pytest.mark.parametrize("F,L,H,W", [(3, 4, 16, 32), (6, 21, 48, 64), (36, 21, 96, 128), (13, 30, 120, 160),
-                                     (10, 21, 17, 48), (50, 25, 64, 96), (12, 22, 19, 80)])
+                                     (10, 21, 17, 48), (50, 25, 64, 96), (12, 22, 19, 80),
+                                     # few labels per frame and more than 256 rows: the label ring of the 256 x 256
+                                     # tiling does not fit, the entry point falls back to 128 x 256 / 128 x 128 tiles
+                                     (24, 11, 48, 64), (24, 14, 48, 64), (48, 6, 32, 64), (100, 3, 16, 64), (30, 18, 32, 48)])
 def test_gram_labels_tensor_core_vs_oracle(F, L, H, W):
     """one-hot Gram matrix synthesised on-chip + tcgen05 kind::i8 == numpy one-hot contraction."""
     from s2d_b200 import _lib
