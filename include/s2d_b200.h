@@ -230,7 +230,9 @@ int s2d_overlap_i8(const uint8_t* A, int Na, const uint8_t* B, int Nb, int64_t n
                    void* stream);
 
 /* One-hot Gram form straight from label maps: rows r = f * nlab + l for `nframes` frames and labels
- * 0..nlab-1 (4 <= nlab <= 254); G[r, r'] = |mask(f,l) AND mask(f',l')| (int32 [R][R]). `work`: int32 scratch
+ * 0..nlab-1 (nlab <= 254; tested down to 3 - with fewer labels per frame and many frames the label ring of
+ * even the narrowest tiling does not fit in shared memory and the call returns an error);
+ * G[r, r'] = |mask(f,l) AND mask(f',l')| (int32 [R][R]). `work`: int32 scratch
  * of s2d_overlap_gram_work_ints() elements (per-split partial tiles, summed by a second kernel). The u8 0/1
  * operand tiles are synthesised in shared memory from the 1 B/px label bytes, so HBM traffic is
  * nframes*npix bytes for 2*R^2*npix tensor-core ops (the tensor-bound form). */

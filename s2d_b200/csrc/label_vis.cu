@@ -15,7 +15,7 @@ __device__ __forceinline__ void hist_flush(int* wh, int cur, int cnt) {
     if (cnt) atomicAdd(&wh[cur], cnt);
 }
 
-__global__ void __launch_bounds__(LH_THREADS, 6)
+__global__ void __launch_bounds__(LH_THREADS)
 label_hist_kernel(const s2d_video_desc* __restrict__ descs, int32_t* __restrict__ area) {
     const s2d_video_desc d = descs[blockIdx.z];
     const int t = blockIdx.y;
@@ -61,40 +61,21 @@ label_hist_kernel(const s2d_video_desc* __restrict__ descs, int32_t* __restrict_
             cnt += 16;
             return;
         }
-        // mixed vector: one pass per distinct label in it (2, rarely 3), counted with byte compares + POPC;
-        // the order of the runs does not matter to a histogram
-        uint32_t rem[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};   // 0xFF per byte not yet counted
-        for (int pass = 0;; ++pass) {
-            if (pass == 3) {        // many labels in 16 pixels (noise): finish byte by byte
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        if ((rem[j] >> (8 * b)) & 1u) {
-                            const int v = (ws[j] >> (8 * b)) & 255;
-                            if (v != cur) { hist_flush(mywh, cur, cnt); cur = v; cnt = 0; }
-                            ++cnt;
-                        }
-                    }
-                }
-                break;
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t sk = __byte_perm(ws[k], 0, 0x0000);
+            if (ws[k] == sk) {
+                const int v = (int)(sk & 255u);
+                if (v != cur) { hist_flush(mywh, cur, cnt); cur = v; cnt = 0; }
+                cnt += 4;
+                continue;
             }
-            int k = 0;
-            if (rem[0]) k = 0; else if (rem[1]) k = 1; else if (rem[2]) k = 2; else if (rem[3]) k = 3; else break;
-            const uint32_t word = k == 0 ? ws[0] : (k == 1 ? ws[1] : (k == 2 ? ws[2] : ws[3]));
-            const uint32_t rk = k == 0 ? rem[0] : (k == 1 ? rem[1] : (k == 2 ? rem[2] : rem[3]));
-            const int v = (int)((word >> ((__ffs(rk) - 1) & 24)) & 255u);
-            const uint32_t sv = (uint32_t)v * 0x01010101u;
-            int n = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t e = __vcmpeq4(ws[j], sv) & rem[j];
-                n += __popc(e);
-                rem[j] &= ~e;
+            for (int b = 0; b < 4; ++b) {
+                int v = (ws[k] >> (8 * b)) & 255;
+                if (v != cur) { hist_flush(mywh, cur, cnt); cur = v; cnt = 0; }
+                ++cnt;
             }
-            n >>= 3;
-            if (v != cur) { hist_flush(mywh, cur, cnt); cur = v; cnt = 0; }
-            cnt += n;
         }
     };
     // four independent 128-bit streaming loads in flight per thread, then the (divergent) run-length pass over them
