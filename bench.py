@@ -390,7 +390,7 @@ def run_k1(vids, batch, L):
     diag = G.reshape(R, R).diagonal().cpu().numpy()
     ops = 2.0 * R * R * H * W
     tops = ops / (ms * 1e-3) / 1e12
-    return {"kernel": "gram_labels2_kernel: one-hot operands synthesised in smem, two tcgen05.mma kind::i8 M128xN256 groups "
+    return {"kernel": "gram_labels2_kernel: one-hot operands synthesised in smem by two producer groups on alternate k-blocks, two tcgen05.mma kind::i8 M128xN256 groups "
                       "per k-block into 512 int32 TMEM columns; only the 256x256 blocks on or above the diagonal of the "
                       "symmetric overlap matrix are executed (2/3 of the MMAs at this shape), `achieved` counts the "
                       "algorithmic 2*R^2*pixels ops",
