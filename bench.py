@@ -390,10 +390,18 @@ def run_k1(vids, batch, L):
     diag = G.reshape(R, R).diagonal().cpu().numpy()
     ops = 2.0 * R * R * H * W
     tops = ops / (ms * 1e-3) / 1e12
-    return {"kernel": "gram_labels2_kernel: one-hot operands synthesised in smem by two producer groups on alternate k-blocks, two tcgen05.mma kind::i8 M128xN256 groups "
-                      "per k-block into 512 int32 TMEM columns; only the 256x256 blocks on or above the diagonal of the "
-                      "symmetric overlap matrix are executed (2/3 of the MMAs at this shape), `achieved` counts the "
-                      "algorithmic 2*R^2*pixels ops",
+    tiling = C.c_int(-1)
+    _lib.call("s2d_overlap_gram_tiling", T, L, C.byref(tiling))
+    kname = {2: "gram_labels2_kernel: one-hot operands synthesised in smem by two producer groups on alternate k-blocks, two "
+                "tcgen05.mma kind::i8 M128xN256 groups per k-block into 512 int32 TMEM columns; only the 256x256 blocks on or "
+                "above the diagonal of the symmetric overlap matrix are executed",
+             1: "gram_labels_kernel<256>: one-hot operands synthesised in smem, tcgen05.mma kind::i8 M128xN256, int32 in TMEM; "
+                "only the 128x256 tiles touching the upper triangle are executed (too few labels per frame for the label "
+                "ring of the 256x256 kernel)",
+             0: "gram_labels_kernel<128>: one-hot operands synthesised in smem, tcgen05.mma kind::i8 M128xN128, int32 in TMEM; "
+                "only the 128x128 tiles touching the upper triangle are executed (small matrix, or too few labels per frame "
+                "for the label ring of the wider tilings)"}[tiling.value]
+    return {"kernel": kname + "; `achieved` counts the algorithmic 2*R^2*pixels ops", "tiling": tiling.value,
             "rows": R, "pixels": H * W, "ms_per_video": ms, "achieved": tops, "unit": "TOP/s",
             "peak": peak, "peak_source": "measured here: torch._int_mm 8192^3 (cuBLASLt int8)", "frac": tops / peak,
             "frac_of_nominal_4500": tops / 4500.0, "hbm_bytes_per_video": int(T * H * W),

@@ -237,6 +237,10 @@ int s2d_overlap_i8(const uint8_t* A, int Na, const uint8_t* B, int Nb, int64_t n
  * operand tiles are synthesised in shared memory from the 1 B/px label bytes, so HBM traffic is
  * nframes*npix bytes for 2*R^2*npix tensor-core ops (the tensor-bound form). */
 int s2d_overlap_gram_work_ints(int nframes, int nlab, int64_t npix, int64_t* out);
+/* Which tiling s2d_overlap_gram_labels uses for this shape (host-only query): *out = 2: 256 x 256 blocks, two M128 x N256
+ * MMA groups per k-block (gram_labels2_kernel); 1: 128 x 256 tiles; 0: 128 x 128 tiles (gram_labels_kernel). The wider
+ * tilings need the label ring of 256 / nlab + 2 frames per operand to fit beside the operand stages. */
+int s2d_overlap_gram_tiling(int nframes, int nlab, int* out);
 int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int nlab, int64_t npix, int32_t* work,
                             int32_t* G, void* stream);
 

@@ -793,11 +793,22 @@ extern "C" int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int n
     S2D_CHECK_ARG((int64_t)nframes * nlab <= 46340, "s2d_overlap_gram_labels: too many rows");
     cudaStream_t st = (cudaStream_t)stream;
     const int R = nframes * nlab;
-    if (R <= 128) return launch_gram<128>(labels, nframes, nlab, npix, work, G, st);
+    int tiling = 0;
+    s2d_overlap_gram_tiling(nframes, nlab, &tiling);
+    if (tiling == 2) return launch_gram2(labels, nframes, nlab, npix, work, G, st);
+    if (tiling == 1) return launch_gram<256>(labels, nframes, nlab, npix, work, G, st);
+    return launch_gram<128>(labels, nframes, nlab, npix, work, G, st);
+}
+
+extern "C" int s2d_overlap_gram_tiling(int nframes, int nlab, int* out) {
+    if (!out || nframes <= 0 || nlab <= 0) return -1;
+    const int R = nframes * nlab;
+    *out = 0;
+    if (R <= 128) return 0;
     // few labels per frame = many frames per operand tile = a bigger label ring: fall back to the narrower tilings
     // (256 x 256 two-m-tile -> 128 x 256 -> 128 x 128) until the ring fits beside the operand stages
     constexpr int SMEM_MAX = 227 * 1024;
-    if (gram_use_v2(R) && gram2_smem(nframes, nlab, nullptr) <= SMEM_MAX) return launch_gram2(labels, nframes, nlab, npix, work, G, st);
-    if (gram1_smem(256, nframes, nlab, nullptr) <= SMEM_MAX) return launch_gram<256>(labels, nframes, nlab, npix, work, G, st);
-    return launch_gram<128>(labels, nframes, nlab, npix, work, G, st);
+    if (gram_use_v2(R) && gram2_smem(nframes, nlab, nullptr) <= SMEM_MAX) *out = 2;
+    else if (gram1_smem(256, nframes, nlab, nullptr) <= SMEM_MAX) *out = 1;
+    return 0;
 }

@@ -49,3 +49,19 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libs2d_b200.so")
     with pytest.raises(_lib.S2DError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_gram_tiling_query_is_host_only():
+    """which Gram tiling a shape gets (2: 256x256 two-m-tile kernel, 1: 128x256, 0: 128x128) - no GPU needed."""
+    from s2d_b200 import _lib
+    _lib.load()
+    got = {}
+    for F, L in [(36, 21), (64, 31), (30, 18), (24, 14), (24, 11), (48, 6), (100, 3), (3, 4)]:
+        t = C.c_int(-1)
+        _lib.call("s2d_overlap_gram_tiling", F, L, C.byref(t))
+        got[(F, L)] = t.value
+    assert got == {(36, 21): 2, (64, 31): 2, (30, 18): 2, (24, 14): 1, (24, 11): 0, (48, 6): 0, (100, 3): 0, (3, 4): 0}
+    n = C.c_int64()
+    for F, L in got:                       # the scratch size covers whichever tiling is chosen
+        _lib.call("s2d_overlap_gram_work_ints", F, L, 64 * 48, C.byref(n))
+        assert n.value >= (F * L) ** 2
