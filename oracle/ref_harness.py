@@ -20,6 +20,7 @@ import io
 import json
 import os
 import sys
+import time
 import types
 
 import numpy as np
@@ -104,8 +105,10 @@ def write_scene_to_disk(scene, root, video_name="vid0"):
 
 
 def run_reference(scene, workdir, *, visibility_threshold=0.3, matching_threshold=0.5,
-                  video_name="vid0", quiet=True):
-    """Returns a JSON-able dict with every intermediate of stages A-D."""
+                  video_name="vid0", quiet=True, log_pairs=True):
+    """Returns a JSON-able dict with every intermediate of stages A-D. `log_pairs=False` leaves
+    compute_point_mask_intersection unwrapped (no per-pair (I, U) record): the timing runs use it so that the
+    harness adds nothing to the reference's inner loop."""
     factory = _FakePredictorFactory(scene)
     _install_stubs(factory)
     real_exists = os.path.exists
@@ -138,13 +141,19 @@ def run_reference(scene, workdir, *, visibility_threshold=0.3, matching_threshol
             pair_log.append((int(torch.sum(pm & mk).item()), int(torch.sum(pm | mk).item()), float(iou)))
             return iou
 
-        cotracker_matching.compute_point_mask_intersection = logged_pmi
+        if log_pairs:
+            cotracker_matching.compute_point_mask_intersection = logged_pmi
         comparisons_log = []
         orig_emm = cotracker_matching.extract_mask_matches
 
+        timing = {"extract_mask_matches_s": 0.0, "extract_mask_matches_calls": 0}
+
         def logged_emm(*a, **k):
             start = len(pair_log)
+            _t = time.perf_counter()
             matches, comps = orig_emm(*a, **k)
+            timing["extract_mask_matches_s"] += time.perf_counter() - _t
+            timing["extract_mask_matches_calls"] += 1
             comparisons_log.append(dict(frame_id=int(a[3]), v_range=[int(a[4][0]), int(a[4][1])],
                                         grid_size=int(a[5]), pairs=pair_log[start:],
                                         comps=[(int(c["frame_id"]), int(c["mask_id"]),
@@ -173,27 +182,35 @@ def run_reference(scene, workdir, *, visibility_threshold=0.3, matching_threshol
         import warnings
         with ctx, ctx2, warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            out = {}
+            out = {"timing": timing}
+            _t0 = time.perf_counter()
             visdata = cotracker_occlusions.extract_object_visibility_data(vdir, mdir, os.path.join(workdir, "videos"),
                                                                           vismaps, False)
+            timing["stage_a_s"] = time.perf_counter() - _t0
             out["stage_a"] = visdata
             ref_labels = cotracker_occlusions.load_masks(mdir)[..., 0].numpy()
             out["labels_equal"] = bool(np.array_equal(ref_labels, scene.labels.astype(np.int64)))
             if visdata is None:
                 out["status"] = None
                 return out
+            _t0 = time.perf_counter()
             windows = identify_visibility_windows.get_visibility_windows_for_video(
                 visdata, "ytvis2021", "train", video_name, visclus, visibility_threshold, False)
+            timing["stage_b_s"] = time.perf_counter() - _t0
             out["stage_b"] = json.loads(json.dumps(windows))
+            _t0 = time.perf_counter()
             imgs, imgs_orig, lbls, meta = crw_utils.load_frames_and_masks(vdir, mdir, windows, "ytvis2021")
             cm_path = keymask_utils.save_segmentation_masks(imgs, imgs_orig, lbls, meta, save_path, False)
+            timing["stage_c_s"] = time.perf_counter() - _t0
             out["candidate_files"] = sorted(os.path.relpath(p, cm_path) for p in
                                             glob.glob(os.path.join(cm_path, "cluster_*", "*.png")))
+            _t0 = time.perf_counter()
             try:
                 status = cotracker_matching.temporal_correspondence_match(
                     vdir, mdir, cm_path, vismaps, visclus, matching_threshold, False)
             except Exception as e:  # the driver catches per stage (main_keymask_ident.py:127-132)
                 status = f"exception:{type(e).__name__}"
+            timing["stage_d_s"] = time.perf_counter() - _t0
             out["status"] = status
             out["tracker_calls"] = factory.calls
             out["queries"] = comparisons_log
