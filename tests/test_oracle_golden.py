@@ -110,5 +110,12 @@ def test_coco_rle_restatement_known_answers_and_roundtrip():
         c = cr.counts(mm)
         assert sum(c) == h * w and np.array_equal(cr.decode(c, h, w), mm)
         assert codec.from_string(codec.to_string(c)) == c
+    # hand-derived strings (maskApi.c rleToString: 5 data bits per character from the low end, bit 0x20 = "more",
+    # offset 48; counts after the third are stored as the difference to the count two places back):
+    #   2, 3, 1 -> '2' '3' '1';   0, 2, 1, 1 -> last is 1 - 2 = -1 = 0b11111 with the sign bit set, no more -> chr(31 + 48) = 'O'
+    #   5, 4, 3, 2 -> last is 2 - 4 = -2 -> chr(30 + 48) = 'N';   100 = 0b00011_00100 -> chr(4 + 32 + 48) = 'T', chr(3 + 48) = '3'
+    for cnts, text in [([2, 3, 1], "231"), ([0, 2, 1, 1], "021O"), ([5, 4, 3, 2], "543N"), ([100], "T3"),
+                       ([12], "<"), ([0, 16], "0`0")]:
+        assert codec.to_string(cnts) == text and codec.from_string(text) == cnts
     big = [0, 5, 100000, 3, 70000, 1, 1, 40]                   # multi-character counts and negative deltas
     assert codec.from_string(codec.to_string(big)) == big
