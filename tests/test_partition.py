@@ -27,6 +27,31 @@ def test_lpt_is_balanced_and_deterministic():
     assert worst(lpt_partition(costs, 8)) < worst(contiguous_partition(len(costs), 8))
 
 
+def test_c4_mixture_of_512_videos_is_balanced_on_2_4_8_ranks():
+    """BASELINE.json configs[3]: 512 videos mixing MOSE-like (480p-1080p, 20-60 frames) and VIPSeg-like (720p, 50-120
+    frames) shapes, partitioned by video: every video lands on exactly one rank, the partition does not depend on
+    anything but the costs, and the most loaded rank is within 1 % of the mean (contiguous slices are not)."""
+    rng = np.random.default_rng(4)
+    costs = []
+    for i in range(512):
+        if i % 2 == 0:                                            # MOSE-like
+            H, W = [(480, 854), (720, 1280), (1080, 1920)][rng.integers(0, 3)]
+            T = int(rng.integers(20, 61))
+        else:                                                     # VIPSeg-like
+            H, W, T = 720, 1280, int(rng.integers(50, 121))
+        M = int(rng.integers(5, 31))
+        costs.append(video_cost(T, H, W, M * T, 4096))
+    costs = np.asarray(costs)
+    for n in (2, 4, 8):
+        parts = lpt_partition(costs, n)
+        assert sorted(i for p in parts for i in p) == list(range(512))
+        loads = np.asarray([costs[p].sum() for p in parts])
+        assert loads.max() <= 1.01 * loads.mean()
+        cont = np.asarray([costs[p].sum() for p in contiguous_partition(512, n)])
+        assert loads.max() <= cont.max()
+        assert parts == lpt_partition(list(costs), n)
+
+
 def test_contiguous_matches_reference_slicing():
     # main_keymask_ident.py:20-23: start = job_id * videos_per_job
     assert contiguous_partition(10, 4) == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9]]
