@@ -134,3 +134,20 @@ def test_coco_rle_restatement_known_answers_and_roundtrip():
         assert codec.to_string(cnts) == text and codec.from_string(text) == cnts
     big = [0, 5, 100000, 3, 70000, 1, 1, 40]                   # multi-character counts and negative deltas
     assert codec.from_string(codec.to_string(big)) == big
+
+
+def test_colour_to_label_rule_vs_reference_golden():
+    """f1: the product's host rule for colour-coded mask frames (rank of the RGB tuple among the frame's non-black
+    colours, lexicographic) against outputs of the unmodified reference's convert_lblimg_to_maskid
+    (crw_utils.py:688-711; fixture from oracle/make_golden_colors.py). The GPU kernel is compared with this host rule
+    in tests/test_gpu_parity.py::test_color_to_labels_vs_host_rule."""
+    import os
+    from s2d_b200.keymask_ident.crw_utils import convert_lblimg_to_maskid, rgb_to_label_ids
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_cpu", "colors.npz"))
+    n = len([k for k in z.files if k.startswith("rgb")])
+    assert n >= 5
+    for i in range(n):
+        rgb, want = z[f"rgb{i}"], z[f"ids{i}"]
+        assert np.array_equal(rgb_to_label_ids(rgb), want[..., 0])
+        got = np.asarray(convert_lblimg_to_maskid(rgb))
+        assert got.shape == want.shape and np.array_equal(got, want)
