@@ -132,13 +132,20 @@ int s2d_windows(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_TW,
  * rowinfo == NULL votes every (q,t); vidinfo == NULL ignores the stage-B status.
  * vec4_ok != 0 promises P even and 16-byte aligned tracks for every video (128-bit loads).
  * work: int32 scratch of s2d_point_votes_work_ints(total_rows) elements, 16-byte aligned; with it
- * (and vec4_ok, P <= 16384; 8192 for variant 1) a persistent kernel runs: a device-side plan lists the (row, frame)
+ * (and vec4_ok, P <= 16384) a persistent kernel runs: a device-side plan lists the (row, frame)
  * tiles and 2-4 CTAs per SM stream them through cp.async.bulk. Variant 0 (default) pulls the
  * tile's bounding box of the label map into shared memory and resolves de-duplication and label
- * lookup with one shared-memory atomic per point; variant 1 de-duplicates in a shared bitmap and
- * gathers labels from global memory; variant 2 (also used when work == NULL or the promises above
+ * lookup with one shared-memory atomic per point; variant 2 (also used when work == NULL or the promises above
  * do not hold) is the one-CTA-per-tile kernel. All variants give identical results.
  * H, W <= 65535; P <= 32768.
+ * Alignment / slack: when a video's label maps are fetched row by row (no descriptors: W or the base address
+ * not a multiple of 16) each row copy is widened to whole 16-byte blocks, so up to 15 bytes before `labels` and
+ * after its last byte are READ (never used): the buffer must sit inside an allocation that extends to the
+ * enclosing 16-byte boundaries on both sides (any cudaMalloc / framework allocation does; an exact-size
+ * sub-allocation at the very edge of a mapping does not).
+ * Device: every entry point makes the device of `stream` current for the duration of the call (and restores the
+ * caller's afterwards), so a caller may drive several GPUs from one thread; descs and all buffers must live on
+ * that device.
  * label_tmaps (optional, may be NULL): DEVICE copy (64-byte aligned) of the buffer that
  * s2d_point_votes_tmaps fills on the HOST from a host copy of the descriptors - S2D_PV_TMAP_BYTES
  * per video: TMA descriptors of the video's label maps, so that variant 0 fetches a tile's table
@@ -146,7 +153,8 @@ int s2d_windows(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_TW,
  * a multiple of 16 get no descriptors and keep the row-by-row fetch. */
 #define S2D_PV_TMAPS 32                            /* box widths 16, 32, ... 512 pixels, 16 rows each */
 #define S2D_PV_TMAP_BYTES (S2D_PV_TMAPS * 128 + 128)
-int s2d_point_votes_variant(int variant);   /* process-wide; 0 label table, 1 bitmap, 2 CTA per tile */
+int s2d_point_votes_variant(int variant);   /* process-wide; 0 label table, 2 one CTA per tile (1, the superseded
+                                             * bitmap kernel, only exists in the experiments build: make exp) */
 int s2d_point_votes_work_ints(int64_t total_rows, int64_t* out);
 int s2d_point_votes_tmaps(const s2d_video_desc* host_descs, int nvideos, void* host_out);
 int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max_T, int max_Nm, int max_P,
@@ -190,7 +198,10 @@ int s2d_rle_area_bbox(const int32_t* counts, const int64_t* offsets, int N, cons
 /* K4a. Scores and selection per candidate query: iou = hits/uniq (double), match bit when
  * iou > matching_threshold (cotracker_matching.py:710), one-to-many flag when >= one2x_frames
  * frames hold more than one mask with iou > one2x_iou (cotracker_matching.py:1082-1111).
- * mbits is cleared inside. Maintains vidinfo[2] (max matched gid, matching.py:770-773). */
+ * mbits is cleared inside. Maintains vidinfo[2] (max matched gid, matching.py:770-773).
+ * With windowed track storage (desc.tstart / desc.Ttr) only the frames [tstart[q], tstart[q] + Ttr) of a
+ * query carry votes; every other frame of its [v0, v1] is scored as intersection 0 / union 0 (iou 0.0), never
+ * from whatever hits / uniq held before. */
 int s2d_select(const s2d_video_desc* descs, int nvideos, int max_Nm, int64_t total_mbits_words,
                const int32_t* hits, const int32_t* uniq, const int32_t* gid_of,
                const int32_t* rowinfo, double matching_threshold, double one2x_iou,
@@ -241,6 +252,10 @@ int s2d_overlap_gram_work_ints(int nframes, int nlab, int64_t npix, int64_t* out
  * MMA groups per k-block (gram_labels2_kernel); 1: 128 x 256 tiles; 0: 128 x 128 tiles (gram_labels_kernel). The wider
  * tilings need the label ring of 256 / nlab + 2 frames per operand to fit beside the operand stages. */
 int s2d_overlap_gram_tiling(int nframes, int nlab, int* out);
+/* Multiply-accumulate work the tensor cores actually EXECUTE for this shape (host-only query): 2 * M * N * K summed over the
+ * launched tiles - only the tiles touching the upper triangle of the symmetric matrix run, and partial tiles run in full. The
+ * algorithmic figure is 2 * R^2 * npix; tensor-pipe utilisation must be quoted from the executed figure. */
+int s2d_overlap_gram_executed_ops(int nframes, int nlab, int64_t npix, double* out);
 int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int nlab, int64_t npix, int32_t* work,
                             int32_t* G, void* stream);
 

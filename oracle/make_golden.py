@@ -74,17 +74,16 @@ CASES = {
 }
 
 
-# Host-only fixtures (tests/golden_cpu/): they pin the oracle only - the -m gpu tests enumerate tests/golden/.
-#   long: 40 frames, i.e. more than one 32-bit word per visibility / match bit row, ending with status 1
-CASES_CPU = {
+# 36- and 40-frame videos that end with status 1: more than one 32-bit word per visibility / match bit row, so
+# select / group run with TW = 2 on the GPU and are compared with the reference's output (tests/golden/ like the rest).
+CASES.update({
     "long": (dict(seed=1250, T=40, H=48, W=64, M=3, P=48), None, 0.3, 0.5),
     "long_thr": (dict(seed=1251, T=36, H=60, W=80, M=4, P=64, noise=1.5), None, 0.4, 0.6),
-}
-GOLDEN_CPU_DIR = os.path.join(os.path.dirname(GOLDEN_DIR), "golden_cpu")
+})
 
 
 def build_case(name):
-    kw, mut, vthr, mthr = (CASES.get(name) or CASES_CPU[name])
+    kw, mut, vthr, mthr = CASES[name]
     sc = make_scene(**kw)
     if mut is not None:
         mut(sc)
@@ -96,9 +95,8 @@ def main(names=None):
     from oracle.ref_harness import run_reference
 
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    os.makedirs(GOLDEN_CPU_DIR, exist_ok=True)
-    for name in (names or list(CASES) + list(CASES_CPU)):
-        outdir = GOLDEN_DIR if name in CASES else GOLDEN_CPU_DIR
+    for name in (names or list(CASES)):
+        outdir = GOLDEN_DIR
         sc, vthr, mthr = build_case(name)
         with tempfile.TemporaryDirectory() as d:
             out = run_reference(sc, d, visibility_threshold=vthr, matching_threshold=mthr)

@@ -107,6 +107,19 @@ def main():
         ext = mat.extend_pointgrid(torch.from_numpy(pm).bool(), gs).numpy()
         iou = mat.compute_point_mask_iou(torch.from_numpy(pm), torch.from_numpy(mask), gs)
         pg[f"pm{i}"], pg[f"mask{i}"], pg[f"grid{i}"], pg[f"ext{i}"], pg[f"iou{i}"] = pm, mask, gs, ext, np.float64(iou)
+    # pred_tracks_to_binary_masks(return_mask=True) (cotracker_matching.py:453-503): hull fill, the 1-2 point fallback,
+    # empty frames, NaN / out-of-bounds / half-integer coordinates
+    H, W = 60, 90
+    tr = rng.uniform(-6, 96, size=(2, 6, 40, 2)).astype(np.float32)
+    tr[..., 1] = tr[..., 1] * (H / W)
+    tr[0, 0, :10] = np.nan; tr[0, 1, 3] = (10.5, 20.5); tr[0, 1, 4] = (W - 0.5, 3.0)
+    tr[1, 2] = -50.0                                   # nothing in bounds
+    tr[1, 3, 2:] = 1e9; tr[1, 3, 0] = (5.2, 7.7); tr[1, 3, 1] = (80.0, 41.0)      # two points: discs
+    tr[1, 4, 1:] = np.inf; tr[1, 4, 0] = (0.4, 0.4)                               # one point at the corner
+    pg["hull_tracks"] = tr
+    pg["hull_hw"] = np.asarray([H, W])
+    pg["hull_masks"] = mat.pred_tracks_to_binary_masks(torch.from_numpy(tr), H, W, return_mask=True).numpy()
+    pg["point_masks"] = mat.pred_tracks_to_binary_masks(torch.from_numpy(tr), H, W, return_mask=False).numpy()
     pg["n"] = len(shapes)
     pg["grid7"] = mat.get_points_on_a_grid(7, (48, 64)).numpy()
     path = os.path.join(ROOT, "tests", "golden", "pointgrid.npz")

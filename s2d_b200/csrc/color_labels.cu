@@ -161,6 +161,7 @@ extern "C" int s2d_color_to_labels_work_ints(int nframes, int64_t* out) {
 
 extern "C" int s2d_color_to_labels(const uint8_t* rgb, int nframes, int64_t npix, uint32_t* work, uint8_t* labels,
                                    int32_t* ncolors, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(rgb && work && labels && ncolors && nframes > 0 && nframes <= 65535 && npix > 0, "s2d_color_to_labels: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* gtab = work;

@@ -16,6 +16,7 @@ constexpr int DB_JT = 1;          // 32-row tiles of rows j staged per barrier p
 __device__ __forceinline__ int uf_find(int32_t* parent, int i) {
     while (true) {
         int p = parent[i];
+        S2D_DEV_ASSERT(p >= 0 && p <= i);          // roots are component minima: parents never point upwards
         if (p == i) return i;
         int gp = parent[p];
         if (gp != p) parent[i] = gp;   // path halving (benign race)
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(DB_THREADS) db_pass_kernel(const DbProblem* __
                     const int r = idx / cwp, w = idx - r * cwp, row = i0 + r;
                     uint32_t v = 0;
                     if (w < cw && row < N && (!p.valid || p.valid[row])) v = p.bits[(int64_t)row * p.stride + p.w0 + c0 + w];
+                    S2D_DEV_ASSERT(r < DB_ROWS_I && w < DB_NWC);
                     xi[r][w] = v;
                 }
             }
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(DB_THREADS) db_pass_kernel(const DbProblem* __
                 const int r = idx / cw4, w = idx - r * cw4, row = j0 + r;
                 uint32_t v = 0;
                 if (w < cw && row < N && (!p.valid || p.valid[row])) v = p.bits[(int64_t)row * p.stride + p.w0 + c0 + w];
+                S2D_DEV_ASSERT(w < DB_NWC && r < 32 * DB_JT);
                 xjT[w][r] = v;
             }
             __syncthreads();
@@ -210,6 +213,7 @@ __global__ void __launch_bounds__(1024) db_label_kernel(const DbProblem* __restr
     for (int i = tid; i < N; i += 1024) {
         const int a = p.aux[i];
         int lab = -1;
+        S2D_DEV_ASSERT(!(p.core[i] || a != INT_MAX) || (a >= 0 && a < N));
         if (p.core[i] || a != INT_MAX) lab = p.parent[a];
         p.labels[i] = lab;
     }
@@ -292,6 +296,7 @@ extern "C" int s2d_dbscan_visibility(const s2d_video_desc* descs, int nvideos, i
                                      int64_t total_rows, const uint32_t* xbits, double eps,
                                      int min_samples, int32_t* work, int32_t* labels1,
                                      int32_t* vidinfo, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(descs && xbits && work && labels1 && vidinfo, "s2d_dbscan_visibility: null pointer");
     S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_Nm > 0, "s2d_dbscan_visibility: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
@@ -308,6 +313,7 @@ extern "C" int s2d_dbscan_visibility(const s2d_video_desc* descs, int nvideos, i
 
 extern "C" int s2d_hamming_dbscan(const uint32_t* bits, int N, int stride, int D, double eps,
                                   int min_samples, int32_t* work, int32_t* labels, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(bits && work && labels, "s2d_hamming_dbscan: null pointer");
     S2D_CHECK_ARG(N > 0 && D > 0 && stride >= (D + 31) / 32, "s2d_hamming_dbscan: bad sizes N=%d D=%d stride=%d", N, D, stride);
     cudaStream_t st = (cudaStream_t)stream;

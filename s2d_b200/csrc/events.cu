@@ -20,6 +20,7 @@ namespace s2d {
 __device__ __forceinline__ int reflect_idx(int j, int n) {       // torch 'reflect' padding, |pad| < n
     if (j < 0) j = -j;
     if (j >= n) j = 2 * (n - 1) - j;
+    S2D_DEV_ASSERT(j >= 0 && j < n);
     return j;
 }
 
@@ -64,6 +65,7 @@ appearance_events_kernel(const float* __restrict__ V, int N, int T, int sw, floa
     int ns = 0, ne = 0;
     for (int base = 0; base < T2 - 1; base += 32) {
         const int i = base + lane;
+        S2D_DEV_ASSERT(T2 <= T && T1 <= T);
         const int d = (i < T2 - 1) ? (int)op[i + 1] - (int)op[i] : 0;
         const uint32_t ms = __ballot_sync(0xffffffffu, d == 1), me = __ballot_sync(0xffffffffu, d == -1);
         const uint32_t below = (1u << lane) - 1u;
@@ -87,6 +89,7 @@ using namespace s2d;
 extern "C" int s2d_appearance_events(const float* V, int N, int T, int smoothing_window, float thresh,
                                      int min_run_length, int max_events, int32_t* nstart, int32_t* nend,
                                      int32_t* starts, int32_t* ends, uint8_t* opened, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(V && nstart && nend && starts && ends, "s2d_appearance_events: null pointer");
     S2D_CHECK_ARG(N > 0 && T > 0 && max_events > 0, "s2d_appearance_events: bad sizes");
     S2D_CHECK_ARG(smoothing_window >= 1 && (smoothing_window & 1), "s2d_appearance_events: smoothing_window must be odd and >= 1");
@@ -109,6 +112,7 @@ extern "C" int s2d_appearance_events(const float* V, int N, int T, int smoothing
 }
 
 extern "C" int s2d_boolean_visibility(const float* V, int64_t n, float threshold, uint8_t* out, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(V && out && n > 0, "s2d_boolean_visibility: bad arguments");
     boolean_visibility_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(V, n, threshold, out);
     S2D_CHECK_LAUNCH("boolean_visibility_kernel");

@@ -85,6 +85,7 @@ label_hist_kernel(const s2d_video_desc* __restrict__ descs, int32_t* __restrict_
         const int4 w2 = ld_stream(vp + i + 2 * LH_THREADS), w3 = ld_stream(vp + i + 3 * LH_THREADS);
         eat(w0); eat(w1); eat(w2); eat(w3);
     }
+    S2D_DEV_ASSERT(vbeg + nvec * 16 <= end && end <= npix);
     for (; i < nvec; i += LH_THREADS) eat(ld_stream(vp + i));
     hist_flush(mywh, cur, cnt);
     __syncthreads();
@@ -127,6 +128,7 @@ frame_tables_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __r
         int gid = -1;
         if (p && l != minlab) {
             gid = gid_base + below - 1;
+            S2D_DEV_ASSERT(gid >= 0);
             if (gid < d.Nm) {
                 qframe[d.row0 + gid] = t;
                 qlabel[d.row0 + gid] = l;
@@ -209,6 +211,7 @@ extern "C" int s2d_label_stats(const s2d_video_desc* descs, int nvideos, int max
                                int64_t total_frames, int32_t* area,
                                int32_t* gid_of, int32_t* frameinfo, int32_t* qframe, int32_t* qlabel,
                                int32_t* vidinfo, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(descs && area && gid_of && frameinfo && qframe && qlabel && vidinfo,
                   "s2d_label_stats: null pointer");
     S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_T > 0 && max_T <= 65535 && max_npix > 0,
@@ -225,6 +228,7 @@ extern "C" int s2d_label_stats(const s2d_video_desc* descs, int nvideos, int max
 
 extern "C" int s2d_vis_reduce(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_T,
                               int32_t* cnt, float* V, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(descs && cnt && V, "s2d_vis_reduce: null pointer");
     S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_rows_x_T > 0, "s2d_vis_reduce: bad sizes");
     dim3 grid((unsigned)((max_rows_x_T + VR_WARPS - 1) / VR_WARPS), nvideos);
@@ -235,6 +239,7 @@ extern "C" int s2d_vis_reduce(const s2d_video_desc* descs, int nvideos, int64_t 
 
 extern "C" int s2d_binarize(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_TW,
                             const float* V, float visibility_threshold, uint32_t* xbits, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(descs && V && xbits, "s2d_binarize: null pointer");
     S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_rows_x_TW > 0, "s2d_binarize: bad sizes");
     dim3 grid((unsigned)((max_rows_x_TW + 255) / 256), nvideos);

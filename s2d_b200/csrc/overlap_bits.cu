@@ -100,6 +100,7 @@ __global__ void row_popc_kernel(const uint32_t* __restrict__ X, int N, int64_t n
 using namespace s2d;
 
 extern "C" int s2d_pack_bits(const uint8_t* planes, int N, int64_t npix, uint32_t* bits, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(planes && bits && N > 0 && npix > 0, "s2d_pack_bits: bad arguments");
     const int64_t wpr = (npix + 31) / 32, total = wpr * N;
     pack_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(planes, total, npix, wpr, bits);
@@ -108,6 +109,7 @@ extern "C" int s2d_pack_bits(const uint8_t* planes, int N, int64_t npix, uint32_
 }
 
 extern "C" int s2d_rasterise_tracks(const float* tracks, int T, int P, int H, int W, uint8_t* planes, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(tracks && planes && T > 0 && P > 0 && H > 0 && W > 0, "s2d_rasterise_tracks: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(planes, 0, (size_t)T * H * W, st);
@@ -118,6 +120,7 @@ extern "C" int s2d_rasterise_tracks(const float* tracks, int T, int P, int H, in
 
 extern "C" int s2d_overlap_bits(const uint32_t* Abits, int Na, const uint32_t* Bbits, int Nb, int64_t nwords,
                                 int32_t* I, int32_t* areaA, int32_t* areaB, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(Abits && Bbits && I && Na > 0 && Nb > 0 && nwords > 0, "s2d_overlap_bits: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(I, 0, (size_t)Na * Nb * sizeof(int32_t), st);

@@ -172,6 +172,7 @@ overlap_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int col = n0 + c0 + j;
+                        S2D_DEV_ASSERT(col >= Nb || ((int64_t)row * Nb + col < (int64_t)Na * Nb));
                         if (col < Nb && v[j]) atomicAdd(&I[(int64_t)row * Nb + col], (int)v[j]);
                     }
                 }
@@ -210,7 +211,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int BN>
 __global__ void __launch_bounds__(GR_GROUPS * (GM_BLOCK_M + BN) + 32, 1)
 gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npix, int kblocks_total,
-                   int kblocks_per_split, int nfr_max, int Rp, int mt, int32_t* __restrict__ part) {
+                   int kblocks_per_split, int nfr_max, int Rp, int mt, int32_t* __restrict__ part, int64_t part_ints) {
     constexpr int STAGES = GR_STAGES;
     constexpr int PRODUCERS = GM_BLOCK_M + BN;
     constexpr int A_BYTES = GM_BLOCK_M * GM_BLOCK_K;
@@ -278,6 +279,7 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
                         const int fr = j >> 3, c = j & 7;
                         const int ff = fr < nfa ? fa0 + fr : fb0 + (fr - nfa);
                         const int64_t px = px0 + 16 * c;
+                        S2D_DEV_ASSERT(fr < nfr_max && ff >= 0 && ff < F && slot + fr * 128 + 16 * c + 16 <= sDesc);
                         if (px < npix) cp_async16(slot + fr * 128 + 16 * c, labels + (int64_t)ff * npix + px);
                         else *reinterpret_cast<uint4*>(slot + fr * 128 + 16 * c) = make_uint4(~0u, ~0u, ~0u, ~0u);   // 0xFF: no label
                     }
@@ -293,6 +295,7 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
                     for (int j = tid; j < (nfa + nfb) * 8; j += PRODUCERS) {
                         const uint4 w = *reinterpret_cast<const uint4*>(slot + j * 16);
                         const bool uni = (w.x == w.y) & (w.y == w.z) & (w.z == w.w) & (w.x == __byte_perm(w.x, 0, 0x0000));
+                        S2D_DEV_ASSERT(j < nfr_max * 8);
                         sDesc[(ii & 1) * nfr_max * 8 + j] = uni ? (uint8_t)(w.x & 255u) : (uint8_t)0xFF;
                     }
                 }
@@ -320,6 +323,7 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
                 if (i >= STAGES) bar_wait(&empty[s], ((i / STAGES) - 1) & 1);
                 const uint8_t* lab = sLab + (ii % (GR_PF + 1)) * slot_bytes + lab_off;
                 uint8_t* dst = sOps + s * (A_BYTES + B_BYTES) + row_off;
+                S2D_DEV_ASSERT(s < STAGES && row_off + 128 <= A_BYTES + B_BYTES && lab_off + 128 <= slot_bytes && desc_off + 8 <= nfr_max * 8);
                 const uint2 d8 = *reinterpret_cast<const uint2*>(sDesc + (ii & 1) * nfr_max * 8 + desc_off);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -356,6 +360,7 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const int col = n0 + c0 + j;
+                            S2D_DEV_ASSERT(col >= Rp || (((int64_t)blockIdx.z * R + row) * Rp + col + 4 <= part_ints));
                             if (col < Rp) *reinterpret_cast<uint4*>(prow + col) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                         }
                     }
@@ -400,7 +405,7 @@ constexpr int G2_PRODUCERS = G2_GROUPS * G2_GTHREADS;
 __global__ void __launch_bounds__(G2_PRODUCERS + 32, 1)
 gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npix, int kblocks_total,
                     int nt, int s_off, int s_diag, int per_off, int per_diag, int nfr_max, int Rp,
-                    int32_t* __restrict__ part) {
+                    int32_t* __restrict__ part, int64_t part_ints) {
     constexpr int STAGES = G2_STAGES;
     constexpr int GT = G2_GTHREADS;
     constexpr int A_BYTES = G2_AM * GM_BLOCK_K;
@@ -468,6 +473,7 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
                         const int fr = j >> 3, c = j & 7;
                         const int ff = fr < nfa ? fa0 + fr : fb0 + (fr - nfa);
                         const int64_t px = px0 + 16 * c;
+                        S2D_DEV_ASSERT(fr < nfr_max && ff >= 0 && ff < F && slot + fr * 128 + 16 * c + 16 <= sDesc);
                         if (px < npix) cp_async16(slot + fr * 128 + 16 * c, labels + (int64_t)ff * npix + px);
                         else *reinterpret_cast<uint4*>(slot + fr * 128 + 16 * c) = make_uint4(~0u, ~0u, ~0u, ~0u);   // 0xFF: no label
                     }
@@ -480,6 +486,7 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
                     for (int j = tid; j < (nfa + nfb) * 8; j += GT) {
                         const uint4 w = *reinterpret_cast<const uint4*>(slot + j * 16);
                         const bool uni = (w.x == w.y) & (w.y == w.z) & (w.z == w.w) & (w.x == __byte_perm(w.x, 0, 0x0000));
+                        S2D_DEV_ASSERT(j < nfr_max * 8);
                         sDesc[(ii & 1) * nfr_max * 8 + j] = uni ? (uint8_t)(w.x & 255u) : (uint8_t)0xFF;
                     }
                 }
@@ -526,6 +533,7 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
                 const uint8_t* slot = sLab + (ii % (GR_PF + 1)) * slot_bytes;
                 const uint8_t* dsc = sDesc + (ii & 1) * nfr_max * 8;
                 uint8_t* stage = sOps + s * (A_BYTES + B_BYTES);
+                S2D_DEV_ASSERT(s < STAGES && frA >= 0 && frA < nfr_max && frB >= 0 && frB < nfr_max && (frB + 1) * 128 <= slot_bytes);
                 if (!diag)
                     build_row(stage + tid * 128, slot + frA * 128, *reinterpret_cast<const uint2*>(dsc + frA * 8), spA, vA);
                 build_row(stage + A_BYTES + tid * 128, slot + frB * 128, *reinterpret_cast<const uint2*>(dsc + frB * 8), spB, vB);
@@ -549,6 +557,7 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const int col = n0 + c0 + j;
+                                S2D_DEV_ASSERT(col >= Rp || (((int64_t)split * R + row) * Rp + col + 4 <= part_ints));
                                 if (col < Rp) *reinterpret_cast<uint4*>(prow + col) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                             }
                         }
@@ -591,6 +600,7 @@ __global__ void gram_reduce_kernel(const int32_t* __restrict__ part, int splits,
     const int rr = min(r, c), cc = max(r, c);          // only upper-triangle tiles were computed
     const int ns = (splits_diag > 0 && (rr >> 8) == (cc >> 8)) ? splits_diag : splits;
     int acc = 0;
+    S2D_DEV_ASSERT(cc < Rp);
     for (int s = 0; s < ns; ++s) acc += part[((int64_t)s * R + rr) * Rp + cc];
     G[i] = acc;
 }
@@ -638,8 +648,10 @@ static void gram2_plan(int R, int64_t npix, int* nt, int* kblocks, int* s_off, i
 }
 
 static bool gram_use_v2(int R) {
+#ifdef S2D_EXPERIMENTS   // A/B runs of the one-m-tile kernel on every shape (make exp)
     static const int forced = getenv("S2D_GRAM_V2") ? atoi(getenv("S2D_GRAM_V2")) : -1;
     if (forced >= 0) return forced != 0 && R > 128;
+#endif
     return R > 256;
 }
 
@@ -662,7 +674,8 @@ static int launch_gram2(const uint8_t* labels, int F, int L, int64_t npix, int32
     gram2_plan(R, npix, &nt, &kblocks, &s_off, &s_diag, &per_off, &per_diag, &Rp);
     const int nctas = nt * s_diag + nt * (nt - 1) / 2 * s_off;
     gram_labels2_kernel<<<nctas, G2_PRODUCERS + 32, smem, st>>>(labels, F, L, npix, kblocks, nt, s_off, s_diag, per_off, per_diag,
-                                                              nfr_max, Rp, work);
+                                                              nfr_max, Rp, work,
+                                                              (int64_t)(s_off > s_diag ? s_off : s_diag) * R * Rp);
     S2D_CHECK_LAUNCH("gram_labels2_kernel");
     gram_reduce_kernel<<<(unsigned)(((int64_t)R * R + 255) / 256), 256, 0, st>>>(work, s_off, s_diag, R, Rp, G);
     S2D_CHECK_LAUNCH("gram_reduce_kernel");
@@ -687,7 +700,7 @@ static int launch_gram(const uint8_t* labels, int F, int L, int64_t npix, int32_
     int mt, nt, kblocks, per, splits, Rp;
     gram_plan(R, BN, npix, &mt, &nt, &kblocks, &per, &splits, &Rp);
     dim3 grid(gram_tiles(mt, nt, BN), 1, splits);
-    kfn<<<grid, GR_GROUPS * (GM_BLOCK_M + BN) + 32, smem, st>>>(labels, F, L, npix, kblocks, per, nfr_max, Rp, mt, work);
+    kfn<<<grid, GR_GROUPS * (GM_BLOCK_M + BN) + 32, smem, st>>>(labels, F, L, npix, kblocks, per, nfr_max, Rp, mt, work, (int64_t)splits * R * Rp);
     S2D_CHECK_LAUNCH("gram_labels_kernel");
     gram_reduce_kernel<<<(unsigned)(((int64_t)R * R + 255) / 256), 256, 0, st>>>(work, splits, 0, R, Rp, G);
     S2D_CHECK_LAUNCH("gram_reduce_kernel");
@@ -753,6 +766,7 @@ static int launch_overlap_i8(const uint8_t* A, int Na, const uint8_t* B, int Nb,
 using namespace s2d;
 
 extern "C" int s2d_overlap_i8(const uint8_t* A, int Na, const uint8_t* B, int Nb, int64_t npix, int32_t* I, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(A && B && I && Na > 0 && Nb > 0 && npix > 0, "s2d_overlap_i8: bad arguments");
     S2D_CHECK_ARG(npix % 16 == 0 && (((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0,
                   "s2d_overlap_i8: planes must be 16-byte aligned with a pixel count that is a multiple of 16 (TMA); "
@@ -787,6 +801,7 @@ extern "C" int s2d_overlap_gram_work_ints(int nframes, int nlab, int64_t npix, i
 
 extern "C" int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int nlab, int64_t npix, int32_t* work,
                                        int32_t* G, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(labels && G && work && nframes > 0 && nlab > 0 && nlab <= 254 && npix > 0, "s2d_overlap_gram_labels: bad arguments");
     S2D_CHECK_ARG(npix % 16 == 0 && (((uintptr_t)labels) & 15) == 0 && (((uintptr_t)work) & 15) == 0,
                   "s2d_overlap_gram_labels: label maps / work must be 16-byte aligned with a pixel count that is a multiple of 16");
@@ -798,6 +813,23 @@ extern "C" int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int n
     if (tiling == 2) return launch_gram2(labels, nframes, nlab, npix, work, G, st);
     if (tiling == 1) return launch_gram<256>(labels, nframes, nlab, npix, work, G, st);
     return launch_gram<128>(labels, nframes, nlab, npix, work, G, st);
+}
+
+extern "C" int s2d_overlap_gram_executed_ops(int nframes, int nlab, int64_t npix, double* out) {
+    if (!out || nframes <= 0 || nlab <= 0 || npix <= 0) return -1;
+    const int R = nframes * nlab;
+    int tiling = 0;
+    s2d_overlap_gram_tiling(nframes, nlab, &tiling);
+    const double kpix = (double)((npix + GM_BLOCK_K - 1) / GM_BLOCK_K) * GM_BLOCK_K;
+    if (tiling == 2) {
+        const int nt = (R + G2_BN - 1) / G2_BN;
+        *out = (double)(nt * (nt + 1) / 2) * 2.0 * G2_AM * G2_BN * kpix;
+    } else {
+        const int BN = tiling == 1 ? 256 : 128;
+        const int mt = (R + GM_BLOCK_M - 1) / GM_BLOCK_M, nt = (R + BN - 1) / BN;
+        *out = (double)gram_tiles(mt, nt, BN) * 2.0 * GM_BLOCK_M * BN * kpix;
+    }
+    return 0;
 }
 
 extern "C" int s2d_overlap_gram_tiling(int nframes, int nlab, int* out) {

@@ -252,7 +252,7 @@ point_votes_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __re
 }
 
 // ==========================================================================================
-// Persistent, TMA-fed variant (the production path for even P and 16-byte aligned tracks).
+// Persistent, TMA-fed bitmap variant (round-1 first design; compiled only with -DS2D_EXPERIMENTS).
 //
 // A small plan pass turns (candidate rows x window frames) into a flat list of tiles; 2 CTAs per
 // SM pull chunks of consecutive tiles from an atomic counter. Each CTA has one producer warp that
@@ -356,6 +356,7 @@ __device__ __forceinline__ void consumer_sync(int nthreads) {   // named barrier
     asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
+#ifdef S2D_EXPERIMENTS   // superseded round-1 design (bitmap + global gathers), kept for A/B runs: `make exp`
 // THREADS consumer threads + one producer warp (the last warp of the CTA)
 template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS + 32, (THREADS * PPT <= 1024) ? 4 : ((THREADS * PPT <= 4096) ? 2 : 1))
@@ -571,6 +572,8 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     }
 }
 
+#endif  // S2D_EXPERIMENTS
+
 // ==========================================================================================
 // Label-table variant: ONE shared-memory atomic per point does both the de-duplication and the
 // label lookup (the production path when it applies: even P, 16-byte aligned tracks, P <= 8192).
@@ -706,16 +709,12 @@ __device__ __forceinline__ bool pv_plan_next(PvPlan& pl, PvTile* rec, int lane, 
     return true;
 }
 
-// PF = true: the tracks never touch shared memory. Each thread pulls its PPT points of the NEXT tile
-// into registers with 128-bit streaming loads right after the current tile's S1, so they fly while the
-// current tile waits for its table and votes; the buffer is then the table only (bigger bands), and the
-// serial chain of a tile shrinks to phase A -> table -> votes. Costs PPT * 2 registers.
-template <int THREADS, int PPT, int CTAS, bool PF>
+template <int THREADS, int PPT, int CTAS>
 __global__ void __launch_bounds__(THREADS, CTAS)
 point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __restrict__ rowplan,
                        int total_rows, int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
                        int32_t* __restrict__ uniq, const uint8_t* __restrict__ tmaps) {
-    constexpr int BUF_BYTES = PF ? pv_buf_bytes(THREADS, 0, CTAS) : pv_buf_bytes(THREADS, PPT, CTAS);
+    constexpr int BUF_BYTES = pv_buf_bytes(THREADS, PPT, CTAS);
     constexpr int NWARPS = THREADS / 32;
     // the fallback bitmap lives in the buffer: the largest power of two of words that fits (at most 2^13 = 32 KB)
     constexpr int FB_LOGW = BUF_BYTES >= 32768 ? 13 : (BUF_BYTES >= 16384 ? 12 : 11);
@@ -729,7 +728,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     __shared__ __align__(8) uint2 wred[NWARPS];        // per-warp packed (min, max + 1) of (iy, ix)
     __shared__ uint32_t dummy[32];                     // all ones: target of points outside the band
     __shared__ __align__(8) uint64_t full, full2, tabbar;   // tracks arrive in two halves: phase A starts on the first
-    __shared__ PvTile tinfo[3];                        // PF: ring of 3 (current, next being loaded, being planned); else 2
+    __shared__ PvTile tinfo[2];                        // current tile, next tile (planned during the current one)
     __shared__ PvPlan plan_s;                          // scheduler state (kept out of the registers)
     __shared__ const float* nsrc_s;                    // tracks of the planned tile
     __shared__ int more_s;
@@ -757,17 +756,6 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         __syncwarp();
         if (lane == 0) { plan_s = pl; nsrc_s = src; more_s = ok ? 1 : 0; }
     };
-    int4 raw[PF ? PPT / 2 : 1];                        // PF: the tile's points, two per register quad
-    auto load_raw = [&](const PvTile* t) {
-        const int4* gp = reinterpret_cast<const int4*>(t->src);
-        const int np2 = t->pad >> 1;                   // 16-byte pairs of points in the tile
-#pragma unroll
-        for (int k = 0; k < (PF ? PPT / 2 : 1); ++k) {
-            const int idx = k * THREADS + tid;
-            raw[k] = make_int4(0, 0, 0, 0);
-            if (idx < np2) raw[k] = ld_stream(gp + idx);
-        }
-    };
     // tracks of the planned tile -> buffer, as two bulk copies on two mbarriers (the halves of the k loop of phase A)
     auto issue_tracks = [&](int P) {
         const uint32_t bytes = (uint32_t)P * 8u;
@@ -781,26 +769,19 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     if (warp == 0) {
         plan(&tinfo[0]);
         __syncwarp();
-        if (PF) {
-            plan(&tinfo[1]);
-        } else if (lane == 0 && more_s) {
-            issue_tracks(tinfo[0].pad);
-        }
+        if (lane == 0 && more_s) issue_tracks(tinfo[0].pad);
     }
     __syncthreads();
-    if (PF && tinfo[0].valid) load_raw(&tinfo[0]);
 
     const uint32_t tab_s = smem_u32(buf);
     const uint32_t dummy_s = smem_u32(&dummy[lane]);
     uint32_t tabphase = 0;
-    int scur = 0, snxt = 1, spl = PF ? 2 : 1;         // slots of tile j, tile j + 1, and of the tile planned during tile j
+    int scur = 0, snxt = 1;                           // slots of tile j and of tile j + 1 (planned during tile j)
     for (int j = 0;; ++j) {
         const PvTile* ti = &tinfo[scur];
         if (!ti->valid) break;                        // written before the barrier that precedes this read
-        if (!PF) {                                    // one warp polls the mbarrier, the rest park at the hardware barrier
-            if (warp == 0) mbar_wait(&full, j & 1);
-            __syncthreads();
-        }
+        if (warp == 0) mbar_wait(&full, j & 1);       // one warp polls the mbarrier, the rest park at the hardware barrier
+        __syncthreads();
         const uint32_t W = ti->W, H = ti->H;
         if (W > 65535u || H > 65535u) __trap();      // packed 16-bit coordinates (documented limit)
         const int n = ti->n;
@@ -809,13 +790,10 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         uint32_t pk[PPT];
         uint32_t mn = 0xFFFFFFFFu, mx = 0;
         const float4* sp = reinterpret_cast<const float4*>(buf);
-        auto point_pair = [&](int k) -> float4 {
-            if (PF) return make_float4(__int_as_float(raw[k].x), __int_as_float(raw[k].y), __int_as_float(raw[k].z), __int_as_float(raw[k].w));
-            return sp[k * THREADS + tid];
-        };
+        auto point_pair = [&](int k) -> float4 { return sp[k * THREADS + tid]; };
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            if (half == 1 && !PF) {                   // second half of the tracks
+            if (half == 1) {                          // second half of the tracks
                 if (warp == 0) mbar_wait(&full2, j & 1);
                 __syncthreads();
             }
@@ -850,7 +828,6 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
             if (lane == 0) wred[warp] = make_uint2((mny << 16) | mnx, (mxy << 16) | mxx);
         }
         __syncthreads();                              // S1: boxes complete, nobody reads the tracks any more
-        if (PF && tinfo[snxt].valid) load_raw(&tinfo[snxt]);       // planned during the previous tile
         uint32_t bmn = 0xFFFFFFFFu, bmx = 0;
 #pragma unroll
         for (int w = 0; w < NWARPS; ++w) {
@@ -919,7 +896,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                         }
                     }
                     if (warp == 0 && !planned) {      // overlap the plan's dependent loads with the table's flight
-                        plan(&tinfo[spl]);
+                        plan(&tinfo[snxt]);
                         planned = true;
                     }
                     if (warp == 0) mbar_wait(&tabbar, tabphase);
@@ -991,10 +968,10 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                 }
             }
         }
-        if (warp == 0 && !planned) plan(&tinfo[spl]);
+        if (warp == 0 && !planned) plan(&tinfo[snxt]);
         fence_proxy_async();                          // buffer atomics before the next tile's bulk copy
         __syncthreads();                              // S2: histogram complete, buffer free, next record visible
-        if (!PF && tid == 0 && more_s) {              // the next tile's tracks fly during the output phase
+        if (tid == 0 && more_s) {                     // the next tile's tracks fly during the output phase
             issue_tracks(tinfo[snxt].pad);
         }
 #pragma unroll
@@ -1007,21 +984,19 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         }
         // the next tile's S1 orders the histogram resets before its votes; this tile's record is
         // rewritten only after that S1 as well (the next plan runs behind it)
-        if (PF) { const int t0 = scur; scur = snxt; snxt = spl; spl = t0; }
-        else { scur ^= 1; snxt ^= 1; spl = snxt; }
+        scur ^= 1; snxt ^= 1;
     }
 }
 
-template <int THREADS, int PPT, int CTAS, bool PF>
+template <int THREADS, int PPT, int CTAS>
 static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, const int4* rowplan,
                          int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq, const uint8_t* tmaps) {
-    const int smem = (PF ? pv_buf_bytes(THREADS, 0, CTAS) : pv_buf_bytes(THREADS, PPT, CTAS)) + 64;
-    auto kfn = point_votes_tab_kernel<THREADS, PPT, CTAS, PF>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = pv_buf_bytes(THREADS, PPT, CTAS) + 64;
+    auto kfn = point_votes_tab_kernel<THREADS, PPT, CTAS>;
+    static bool configured[S2D_MAX_DEVICES] = {};
+    {
+        cudaError_t e = opt_in_smem(kfn, smem, configured);
         if (e != cudaSuccess) { set_error("point_votes_tab_kernel: cannot opt in to %d B of shared memory: %s", smem, cudaGetErrorString(e)); return -2; }
-        configured = true;
     }
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, THREADS, smem);
@@ -1031,16 +1006,16 @@ static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, 
     return 0;
 }
 
+#ifdef S2D_EXPERIMENTS
 template <int THREADS, int PPT>
 static int launch_pv_tma(cudaStream_t st, int nsm, const s2d_video_desc* descs, const int4* rowplan,
                          int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq) {
     const int smem = 2 * THREADS * PPT * 8 + PV_BM_WORDS * 4;
     auto kfn = point_votes_tma_kernel<THREADS, PPT>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static bool configured[S2D_MAX_DEVICES] = {};
+    {
+        cudaError_t e = opt_in_smem(kfn, smem, configured);
         if (e != cudaSuccess) { set_error("point_votes_tma_kernel: cannot opt in to %d B of shared memory: %s", smem, cudaGetErrorString(e)); return -2; }
-        configured = true;
     }
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, THREADS + 32, smem);
@@ -1049,6 +1024,8 @@ static int launch_pv_tma(cudaStream_t st, int nsm, const s2d_video_desc* descs, 
     S2D_CHECK_LAUNCH("point_votes_tma_kernel");
     return 0;
 }
+
+#endif
 
 template <int THREADS, int PPT>
 static int launch_pv(bool vec4, dim3 grid, cudaStream_t st, const s2d_video_desc* descs, const int32_t* rowinfo,
@@ -1068,7 +1045,12 @@ using namespace s2d;
 static int g_pv_variant = 0;
 
 extern "C" int s2d_point_votes_variant(int variant) {
+#ifdef S2D_EXPERIMENTS
     S2D_CHECK_ARG(variant >= 0 && variant <= 2, "s2d_point_votes_variant: %d not in {0 label table, 1 bitmap, 2 one CTA per tile}", variant);
+#else
+    S2D_CHECK_ARG(variant == 0 || variant == 2, "s2d_point_votes_variant: %d not in {0 label table, 2 one CTA per tile} "
+                  "(1, the superseded bitmap kernel, exists only in the experiments build: make -C s2d_b200/csrc exp)", variant);
+#endif
     g_pv_variant = variant;
     return 0;
 }
@@ -1131,6 +1113,7 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
                                int vec4_ok, int64_t total_rows, const int32_t* rowinfo,
                                const int32_t* vidinfo, int32_t* work, const void* label_tmaps,
                                int32_t* hits, int32_t* uniq, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG((((uintptr_t)label_tmaps) & 63) == 0, "s2d_point_votes: label_tmaps must be 64-byte aligned");
     const uint8_t* tm = static_cast<const uint8_t*>(label_tmaps);
     S2D_CHECK_ARG(descs && hits && uniq, "s2d_point_votes: null pointer");
@@ -1154,30 +1137,26 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
         S2D_CHECK_LAUNCH("pv_scan_kernel");
         const int tr = (int)total_rows;
         if (variant == 0) {      // label-table kernels
-            static const int ctas = getenv("S2D_PV_CTAS") ? atoi(getenv("S2D_PV_CTAS")) : 6;
-            static const int pf = getenv("S2D_PV_PF") ? atoi(getenv("S2D_PV_PF")) : 0;
-            if (max_P <= 128 * 8) return launch_pv_tab<128, 8, 6, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-            if (max_P <= 128 * 16) return launch_pv_tab<128, 16, 6, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+            if (max_P <= 128 * 8) return launch_pv_tab<128, 8, 6>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+            if (max_P <= 128 * 16) return launch_pv_tab<128, 16, 6>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+#ifdef S2D_EXPERIMENTS   // CTAs per SM of the 4096-point configuration (A/B runs; 6 x 128 threads is the measured best)
             if (max_P <= 256 * 16) {
-                if (pf) {
-                    if (ctas == 2) return launch_pv_tab<256, 16, 2, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-                    if (ctas == 4) return launch_pv_tab<256, 16, 4, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-                    return launch_pv_tab<256, 16, 3, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-                }
-                if (ctas == 3) return launch_pv_tab<256, 16, 3, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-                if (ctas == 5) return launch_pv_tab<128, 32, 5, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-                if (ctas == 6) return launch_pv_tab<128, 32, 6, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-                return launch_pv_tab<256, 16, 4, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                const int ctas = getenv("S2D_PV_CTAS") ? atoi(getenv("S2D_PV_CTAS")) : 6;
+                if (ctas == 3) return launch_pv_tab<256, 16, 3>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                if (ctas == 4) return launch_pv_tab<256, 16, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                if (ctas == 5) return launch_pv_tab<128, 32, 5>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
             }
-            if (max_P <= 256 * 32) return launch_pv_tab<256, 32, 3, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-            return launch_pv_tab<512, 32, 1, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);     // 128 KB tiles: one CTA per SM
+#endif
+            if (max_P <= 128 * 32) return launch_pv_tab<128, 32, 6>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+            if (max_P <= 256 * 32) return launch_pv_tab<256, 32, 3>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+            return launch_pv_tab<512, 32, 1>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);     // 128 KB tiles: one CTA per SM
         }
+#ifdef S2D_EXPERIMENTS
         if (max_P <= 256 * 4) return launch_pv_tma<256, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);   // 4 CTAs/SM
         if (max_P <= 512 * 4) return launch_pv_tma<512, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
-        if (max_P <= 4096) {
-            return launch_pv_tma<512, 8>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
-        }
+        if (max_P <= 4096) return launch_pv_tma<512, 8>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
         return launch_pv_tma<512, 16>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+#endif
     }
     dim3 grid((unsigned)max_T, (unsigned)max_Nm, nvideos);
 #define PV_ARGS v4, grid, st, descs, rowinfo, vidinfo, hits, uniq

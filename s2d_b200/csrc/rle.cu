@@ -48,6 +48,7 @@ rle_colbits_kernel(const uint8_t* __restrict__ masks, int H, int W, int HW, uint
         if (lane == i) mine = w;
     }
     const int x = x0 + lane;
+    S2D_DEV_ASSERT(x >= W || (yw < HW && n < (int)gridDim.z));
     if (x < W) colbits[((int64_t)n * W + x) * HW + yw] = mine;
     // area and bounding box
     const int cnt = __reduce_add_sync(0xffffffffu, __popc(mine));
@@ -116,6 +117,7 @@ rle_runs_kernel(const uint32_t* __restrict__ colbits, int H, int W, int HW, int 
         while (t) {                                   // edges: column-major position of every transition
             const int bit = __ffs(t) - 1;
             t &= t - 1;
+            S2D_DEV_ASSERT(idx >= 0 && x * H + j * 32 + bit <= H * W);
             if (idx < max_runs) ed[idx] = x * H + j * 32 + bit;
             ++idx;
         }
@@ -132,6 +134,7 @@ rle_runs_kernel(const uint32_t* __restrict__ colbits, int H, int W, int HW, int 
     for (int k = tid; k < total_runs && k < max_runs; k += RLE_THREADS) {
         const int lo = k == 0 ? 0 : ed[k - 1];
         const int hi = k < ntr ? ed[k] : H * W;
+        S2D_DEV_ASSERT(hi >= lo && k < max_runs);
         ct[k] = hi - lo;
     }
     if (tid == 0) nruns[n] = total_runs;
@@ -149,6 +152,7 @@ extern "C" int s2d_rle_work_ints(int N, int H, int W, int max_runs, int64_t* out
 
 extern "C" int s2d_rle_encode(const uint8_t* masks, int N, int H, int W, int max_runs, int32_t* work,
                               int32_t* counts, int32_t* nruns, int32_t* area, int32_t* bbox, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(masks && work && counts && nruns && area && bbox, "s2d_rle_encode: null pointer");
     S2D_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0 && max_runs > 0, "s2d_rle_encode: bad sizes");
     S2D_CHECK_ARG((int64_t)H * W < INT_MAX, "s2d_rle_encode: mask too large");
@@ -192,6 +196,7 @@ rle_area_bbox_kernel(const int32_t* __restrict__ counts, const int64_t* __restri
     bool full_rows = false;
     for (int base = 0; base < m; base += 32) {
         const int j = base + lane;
+        S2D_DEV_ASSERT(j >= m || j < nr);
         const unsigned v = j < m ? (unsigned)c[j] : 0u;
         unsigned incl = v;
 #pragma unroll
@@ -228,6 +233,7 @@ rle_area_bbox_kernel(const int32_t* __restrict__ counts, const int64_t* __restri
 
 extern "C" int s2d_rle_area_bbox(const int32_t* counts, const int64_t* offsets, int N, const int32_t* heights,
                                  int32_t* area, int32_t* bbox, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(counts && offsets && heights && area && bbox && N > 0, "s2d_rle_area_bbox: bad arguments");
     rle_area_bbox_kernel<<<(N + 3) / 4, 128, 0, (cudaStream_t)stream>>>(counts, offsets, N, heights, area, bbox);
     S2D_CHECK_LAUNCH("rle_area_bbox_kernel");

@@ -42,6 +42,10 @@ select_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __restric
     __shared__ int c25s[SEL_WARPS][SEL_MAX_T];
     int* c25 = c25s[threadIdx.x >> 5];
     const int L = d.L;
+    // windowed track storage: only frames [ts0, ts0 + Ttr) of the query were voted on (s2d_point_votes clips its
+    // tiles to them and leaves the rest of hits / uniq untouched); every other frame of [v0, v1] counts as "no
+    // tracked point landed in the frame": intersection 0, union 0, iou 0.0
+    const int ts0 = d.tstart ? d.tstart[q] : 0, ts1 = ts0 + d.Ttr;
     for (int t0 = max(ri.z, 0); t0 <= min(ri.w, d.T - 1); t0 += SEL_MAX_T) {      // one segment unless the window is huge
         const int t1 = min(min(ri.w, d.T - 1), t0 + SEL_MAX_T - 1);
         for (int t = t0 + lane; t <= t1; t += 32) c25[t - t0] = 0;
@@ -54,7 +58,8 @@ select_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __restric
 #pragma unroll 8
         for (int j = lane; j < ncell; j += 32) {
             const int gid = g0[tt * S2D_MAX_LABELS + l];
-            const int I = h0[j], U = u0[tt];              // unconditional: the three loads of all unrolled steps fly together
+            int I = h0[j], U = u0[tt];                    // unconditional: the three loads of all unrolled steps fly together
+            if (t0 + tt < ts0 || t0 + tt >= ts1) { I = 0; U = 0; }
             if (gid >= 0) {
                 // iou = intersection / union as python floats, 0.0 when union == 0 (matching.py:659-662).
                 // The comparison iou > thr is decided without the division whenever I - thr * U is clearly
@@ -68,6 +73,7 @@ select_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __restric
                     m1 = dm > tol ? true : (dm < -tol ? false : (fI / fU > match_thr));
                     m2 = d2 > tol ? true : (d2 < -tol ? false : (fI / fU > one2x_iou));
                 }
+                S2D_DEV_ASSERT(gid < d.Nm && tt <= t1 - t0);
                 if (m1) {
                     atomicOr(&mrow[gid >> 5], 1u << (gid & 31));
                     ++nm;
@@ -221,6 +227,7 @@ group_finalize_kernel(const s2d_video_desc* __restrict__ descs, const uint32_t* 
             }
         }
         glabel[d.row0 + q] = lab;
+        S2D_DEV_ASSERT(lab < d.Nm);
         if (lab >= 0) {
             atomicAdd(&s_matched, 1);
             if (atomicAdd(&gn[lab], 1) == 0) atomicAdd(&s_factor, 1);
@@ -259,6 +266,7 @@ extern "C" int s2d_select(const s2d_video_desc* descs, int nvideos, int max_Nm, 
                           const int32_t* rowinfo, double matching_threshold, double one2x_iou,
                           int one2x_frames, uint32_t* mbits, int32_t* one2x, int32_t* nmatch,
                           int32_t* vidinfo, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(descs && hits && uniq && gid_of && rowinfo && mbits && one2x && nmatch && vidinfo,
                   "s2d_select: null pointer");
     S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_Nm > 0, "s2d_select: bad sizes");
@@ -281,6 +289,7 @@ extern "C" int s2d_group(const s2d_video_desc* descs, int nvideos, int max_Nm, i
                          const uint32_t* mbits, const int32_t* rowinfo, const int32_t* one2x,
                          int32_t* work, int32_t* glabel, int32_t* grp_n, int32_t* grp_one2x,
                          int32_t* vidinfo, int32_t* clusterinfo, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(descs && mbits && rowinfo && one2x && work && glabel && grp_n && grp_one2x && vidinfo && clusterinfo,
                   "s2d_group: null pointer");
     S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_Nm > 0, "s2d_group: bad sizes");

@@ -19,10 +19,12 @@ __global__ void cluster_count_kernel(const s2d_video_desc* __restrict__ descs,
     if (c < 0) return;
     if (w == 0) atomicAdd(&clrow[(d.row0 + c) * 4 + 0], 1);
     uint32_t m = xbits[d.xbits_off + i];
+    S2D_DEV_ASSERT(c < d.Nm);
     int32_t* dst = ccount + d.vt_off + (int64_t)c * d.T + w * 32;
     while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
+        S2D_DEV_ASSERT(w * 32 + b < d.T);
         atomicAdd(&dst[b], 1);
     }
 }
@@ -114,6 +116,7 @@ windows_kernel(const s2d_video_desc* __restrict__ descs, const uint32_t* __restr
                     const int end = t - 1, len = end - start + 1;
                     // frac = counts / length in float32, frac > 0.3 (float32), windows.py:100-103
                     if (__fdiv_rn((float)cntv, (float)len) > winner_fraction) {
+                        S2D_DEV_ASSERT((run >> 5) < TW);
                         wb[run >> 5] |= 1u << (run & 31);
                         if (f >= start && f <= end) cand = run;
                     }
@@ -169,6 +172,7 @@ extern "C" int s2d_windows(const s2d_video_desc* descs, int nvideos, int64_t max
                            int32_t* ccount, int32_t* clrow, uint32_t* majbits, uint32_t* rsbits,
                            uint32_t* rebits, uint32_t* winbits, int32_t* rowinfo, int32_t* vidinfo,
                            int32_t* clusterinfo, void* stream) {
+    S2D_ENTER(stream);
     S2D_CHECK_ARG(descs && xbits && labels1 && qframe && ccount && clrow && majbits && rsbits && rebits &&
                       winbits && rowinfo && vidinfo && clusterinfo, "s2d_windows: null pointer");
     S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535, "s2d_windows: bad nvideos %d", nvideos);

@@ -108,9 +108,11 @@ def get_masks_for_vrange(masks, v_range):
 
 def pred_tracks_to_binary_masks(pred_tracks: torch.Tensor, height: int, width: int, return_mask: bool = False):
     """(B,T,P,2) tracks -> (B,T,H,W) uint8 rasters of the rounded in-bounds points (K1's A operand,
-    rasterise kernel). The convex-hull variant (return_mask=True) is not on the keymask path."""
+    rasterise kernel). return_mask=True fills the convex hull of each frame's points instead
+    (cotracker_matching.py:488-499; not used by the driver): the hull and the polygon fill stay OpenCV's on the
+    host, exactly the calls the reference makes, so the rasters are identical."""
     if return_mask:
-        raise NotImplementedError("convex-hull rasterisation is not used by keymask discovery")
+        return _hull_masks(pred_tracks, height, width)
     B, T, P, _ = pred_tracks.shape
     dev = _engine.device()
     out = torch.empty((B, T, height, width), dtype=torch.uint8, device=dev)
@@ -120,6 +122,23 @@ def pred_tracks_to_binary_masks(pred_tracks: torch.Tensor, height: int, width: i
         _lib.call("s2d_rasterise_tracks", tr.data_ptr(), T, P, height, width, out[b].data_ptr(), st)
     torch.cuda.synchronize(dev)
     return out.to(pred_tracks.device)
+
+
+def _hull_masks(pred_tracks: torch.Tensor, height: int, width: int) -> torch.Tensor:
+    """convex-hull rasters: >= 3 in-bounds points -> filled hull, 1-2 points -> radius-1 discs, none -> empty."""
+    B, T, _, _ = pred_tracks.shape
+    xy = torch.round(pred_tracks.detach().to("cpu", torch.float32)).to(torch.int64).numpy()   # half-to-even; NaN / inf -> INT64_MIN
+    out = np.zeros((B, T, height, width), np.uint8)
+    for b, t in np.ndindex(B, T):
+        p = xy[b, t]
+        inside = (p[:, 0] >= 0) & (p[:, 0] < width) & (p[:, 1] >= 0) & (p[:, 1] < height)
+        p = p[inside]
+        if len(p) >= 3:
+            cv2.fillPoly(out[b, t], [cv2.convexHull(p.astype(np.int32))], color=1)
+        else:
+            for x, y in p:
+                cv2.circle(out[b, t], (int(x), int(y)), radius=1, color=1, thickness=-1)
+    return torch.from_numpy(out).to(pred_tracks.device)
 
 
 def compute_point_mask_intersection(pointmask: torch.Tensor, mask: torch.Tensor, grid_size: int) -> float:

@@ -59,7 +59,11 @@ class Batch:
     """Descriptor table + workspace for a list of videos. Allocation happens here, once; `run`
     only enqueues kernels, so a Batch can be re-run (benchmarks) without touching the allocator."""
 
-    def __init__(self, videos: List[VideoInput], device=None, stages: str = "LVBD"):
+    def __init__(self, videos: List[VideoInput], device=None, stages: str = "LVBD", persistent_votes: bool = True,
+                 label_tmaps: bool = True):
+        """`persistent_votes=False` runs K2 as one CTA per tile (the library's fallback for odd P / unaligned
+        tracks), `label_tmaps=False` makes the persistent kernel fetch its label tables row by row instead of as TMA
+        boxes; both exist for tests and profiling comparisons, the defaults are the product path."""
         assert len(videos) > 0
         self.videos = videos
         first = next(t for t in (videos[0].labels, videos[0].tracks, videos[0].vis) if t is not None) \
@@ -157,8 +161,8 @@ class Batch:
         if "D" in st:
             _lib.call("s2d_point_votes_work_ints", row0, C.byref(n))
             self.pvwork = z(n.value + 4)
-            # TMA descriptors of the label maps (host-encoded once per batch, S2D_PV_TMA_DESC=0 disables)
-            if os.environ.get("S2D_PV_TMA_DESC", "1") != "0" and all(v.labels is not None for v in videos):
+            # TMA descriptors of the label maps (host-encoded once per batch)
+            if label_tmaps and all(v.labels is not None for v in videos):
                 hbuf = np.zeros(nv * S2D_PV_TMAP_BYTES, np.uint8)
                 _lib.call("s2d_point_votes_tmaps", descs, nv, hbuf.ctypes.data)
                 self.pvtmaps = torch.from_numpy(hbuf).to(dev)
@@ -174,15 +178,18 @@ class Batch:
             self.grp_n = z(16 * row0)
             self.grp_one2x = z(16 * row0)
         self.kernel_launches_per_run = 0
-        # persistent TMA-fed votes kernel (the library falls back by itself when P is odd);
-        # S2D_PV_TMA=0 selects the one-CTA-per-tile kernel (profiling comparisons)
-        self.use_tma = os.environ.get("S2D_PV_TMA", "1") != "0"
+        # persistent TMA-fed votes kernel (the library falls back by itself when P is odd)
+        self.use_tma = bool(persistent_votes)
 
     # ------------------------------------------------------------------ enqueue
     def run(self, params: Params = Params(), stream=None, stages: Optional[str] = None, timers=None):
         """Enqueue the whole path on `stream` (default: torch's current stream). Returns the
         number of kernel launches enqueued. `timers`: optional dict name -> list; a pair of CUDA
         events is recorded around every C-ABI call on torch's current stream (bench.py)."""
+        with torch.cuda.device(self.device):       # events and launches on the batch's device, whatever is current
+            return self._run(params, stream, stages, timers)
+
+    def _run(self, params, stream, stages, timers):
         st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
         p = lambda t: t.data_ptr() if t is not None else None
         d, nv = p(self.descs), self.nv
@@ -236,11 +243,12 @@ class Batch:
         instead of ~20 (small batches - a single short video - are launch-bound). The C-ABI calls only
         enqueue kernels and memsets on the current stream, so they capture as they are; the first,
         un-captured run() configures the kernels' attributes."""
-        self.run(params, stages=stages)
-        torch.cuda.synchronize(self.device)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.device(self.device):
             self.run(params, stages=stages)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run(params, stages=stages)
         self._graph = g
         return g
 

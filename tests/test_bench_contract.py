@@ -37,3 +37,15 @@ def test_reference_arm_other_ranks_exit_without_work():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0, r.stderr[-2000:]
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_reference_arm_ignores_torchrun_thread_cap():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must still use every host core, or the per-N
+    ratios of the scaling run are not comparable (round-1 verdict)."""
+    r = _run({"OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    # both arms print the same `config` (bench.make_config)
+    assert set(d["config"]) == {"workload", "videos_per_gpu", "frames_per_video", "resolution", "masks_per_frame",
+                                "tracks_per_query", "queries_per_video", "point_order", "partition", "cache"}

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+# (every test but the host-only hull raster test is marked gpu individually below)
 
 
 def _write_video(root, labels, name="vid0"):
@@ -64,6 +64,7 @@ class _Model:
         return self.rp.predict(video, grid_size, grid_query_frame, segm_mask, backward_tracking)
 
 
+@pytest.mark.gpu
 def test_dropin_stages_match_reference_files(golden_case, tmp_path):
     from oracle.compare import _close
     from s2d_b200.keymask_ident import (_engine, cotracker_matching, cotracker_occlusions, crw_utils,
@@ -135,6 +136,7 @@ def test_dropin_stages_match_reference_files(golden_case, tmp_path):
         _engine.set_tracker_factory(None)
 
 
+@pytest.mark.gpu
 def test_dropin_helpers_on_gpu():
     from s2d_b200.keymask_ident import cotracker_matching as cm, identify_visibility_windows as ivw
     rng = np.random.default_rng(0)
@@ -330,3 +332,82 @@ def test_rle_area_bbox_and_results_conversion(tmp_path):
     a = d["annotations"][0]
     assert a["id"] == 1 and a["length"] == 3 and a["segmentations"] == seg
     assert a["areas"] == [want[10][0], None, want[12][0]] and a["bboxes"] == [want[10][1], None, want[12][1]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["basic", "long"])
+def test_flat_imports_like_the_reference_driver(case, tmp_path):
+    """INTEGRATION.md mode 1: the reference driver imports its stage modules FLAT (main_keymask_ident.py:4-9:
+    `import crw_utils`, `from cotracker_occlusions import ...`). With s2d_b200/keymask_ident first on PYTHONPATH those
+    names must resolve to the CUDA-backed modules (their `except ImportError` branches), run the five stages in the
+    driver's order in a fresh interpreter, and write what the unmodified reference wrote (golden)."""
+    import subprocess
+    import sys
+    import textwrap
+    from tests.conftest import load_golden
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g, labels, tracks, vis = load_golden(case)
+    vdir, mdir = _write_video(str(tmp_path), labels)
+    script = tmp_path / "flat_driver.py"
+    script.write_text(textwrap.dedent(f"""
+        import glob, json, os, sys
+        import numpy as np
+        # --- the reference driver's own import block (main_keymask_ident.py:4-9) ---
+        import crw_utils
+        from cotracker_occlusions import extract_object_visibility_data
+        from identify_visibility_windows import get_visibility_windows_for_video
+        from keymask_utils import save_segmentation_masks
+        from cotracker_matching import temporal_correspondence_match
+        from annotations import write_annotation_for_video
+        import _engine, cotracker_matching
+        here = os.path.realpath(os.path.dirname(crw_utils.__file__))
+        assert here == os.path.realpath({os.path.join(root, 's2d_b200', 'keymask_ident')!r}), here
+        assert "s2d_b200.keymask_ident.crw_utils" not in sys.modules and cotracker_matching.crw_utils is crw_utils
+        sys.path.insert(0, {root!r})
+        from tests.test_dropin_gpu import _Model, _Replay
+        z = np.load({os.path.join(root, 'tests', 'golden', case + '.npz')!r})
+        rp = _Replay(z["labels"], z["tracks"], z["vis"])
+        _engine.set_tracker_factory(lambda checkpoint=None: _Model(rp))
+        root = {str(tmp_path)!r}
+        vismaps, visclus, save = os.path.join(root, "vm"), os.path.join(root, "vc"), os.path.join(root, "seg")
+        a = extract_object_visibility_data({vdir!r}, {mdir!r}, os.path.join(root, "videos"), vismaps, False)
+        w = get_visibility_windows_for_video(a, "ytvis2021", "train", "vid0", visclus, {g['visibility_threshold']!r}, False)
+        imgs, imgs_orig, lbls, meta = crw_utils.load_frames_and_masks({vdir!r}, {mdir!r}, w, "ytvis2021")
+        cm = save_segmentation_masks(imgs, imgs_orig, lbls, meta, save, False)
+        status = temporal_correspondence_match({vdir!r}, {mdir!r}, cm, vismaps, visclus, {g['matching_threshold']!r}, False)
+        write_annotation_for_video({vdir!r}, cm, os.path.join(root, "ann"), w)
+        groups = sorted(os.path.relpath(p, cm) for p in glob.glob(os.path.join(cm, "cluster_*", "group_*", "*.png")))
+        ann = json.load(open(os.path.join(root, "ann", "vid0.json")))
+        json.dump({{"status": status, "clusters": w["clusters"], "groups": groups, "n_ann": len(ann["annotations"]),
+                   "length": ann["videos"][0]["length"]}}, open(os.path.join(root, "out.json"), "w"))
+    """))
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(root, "s2d_b200", "keymask_ident"), root])
+    r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.load(open(tmp_path / "out.json"))
+    assert out["status"] == g["status"] == 1
+    assert out["clusters"] == g["clusters"]
+    assert out["groups"] == g["group_files"]
+    assert out["n_ann"] == len({os.path.dirname(p) for p in g["group_files"]}) and out["length"] == labels.shape[0]
+
+
+def test_hull_rasters_vs_reference_golden():
+    """pred_tracks_to_binary_masks(return_mask=True) (cotracker_matching.py:488-499: convex hull fill, 1-2 point disc
+    fallback, empty frames) against rasters produced by the unmodified reference. Host-only (OpenCV), runs without a GPU."""
+    from s2d_b200.keymask_ident import cotracker_matching as cm
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pointgrid.npz"))
+    H, W = (int(v) for v in g["hull_hw"])
+    got = cm.pred_tracks_to_binary_masks(torch.from_numpy(g["hull_tracks"]), H, W, return_mask=True)
+    assert got.dtype == torch.uint8 and np.array_equal(got.numpy(), g["hull_masks"])
+    assert g["hull_masks"][1, 2].sum() == 0 and 0 < g["hull_masks"][1, 4].sum() <= 5 and g["hull_masks"][0, 2].sum() > 1000
+
+
+@pytest.mark.gpu
+def test_point_rasters_vs_reference_golden():
+    """pred_tracks_to_binary_masks(return_mask=False) - the rasterise kernel - against the unmodified reference's rasters."""
+    from s2d_b200.keymask_ident import cotracker_matching as cm
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pointgrid.npz"))
+    H, W = (int(v) for v in g["hull_hw"])
+    got = cm.pred_tracks_to_binary_masks(torch.from_numpy(g["hull_tracks"]), H, W)
+    assert np.array_equal(got.cpu().numpy(), g["point_masks"])

@@ -65,7 +65,11 @@ def test_point_votes_all_pairs_vs_oracle(golden_case):
 def pv_variant(request):
     """run a test once per point-votes kernel variant (include/s2d_b200.h: s2d_point_votes_variant)"""
     from s2d_b200 import _lib
-    _lib.call("s2d_point_votes_variant", request.param)
+    try:
+        _lib.call("s2d_point_votes_variant", request.param)
+    except _lib.S2DError:
+        assert request.param == 1     # the superseded bitmap kernel only exists in the experiments build (make exp)
+        pytest.skip("variant 1 is compiled only into libs2d_b200_exp.so")
     yield request.param
     _lib.call("s2d_point_votes_variant", 0)
 
@@ -327,6 +331,27 @@ def test_color_to_labels_vs_host_rule():
             assert ncols[f] == len(np.unique(ref[ref > 0]))
 
 
+def _assert_same_as_oracle(res, ref, min_queries):
+    """every field of a pipeline result against the oracle's: visibility floats exact, clusters / windows / candidates,
+    per query (cluster, frame, mask, one2x, matches, per-pair intersection and union counts), groups, coverages, one2x."""
+    assert res["status"] == ref["status"] == 1
+    assert np.array_equal(res["V"], ref["V"], equal_nan=True)
+    assert np.array_equal(res["labels1"], ref["labels1"])
+    assert json_eq(res["clusters"], ref["clusters"])
+    assert len(res["queries"]) == len(ref["queries"]) > min_queries
+    for a, b in zip(res["queries"], ref["queries"]):
+        assert (a["cluster_id"], a["frame_id"], a["mask_id"], a["one2x"]) == (b["cluster_id"], b["frame_id"], b["mask_id"], b["one2x"])
+        assert a["matches"] == b["matches"]
+        assert tuple(a["v_range"]) == tuple(b["v_range"]) and a["grid_size"] == b["grid_size"]
+        assert [c[:5] for c in a["comps"]] == [c[:5] for c in b["comps"]]
+        assert all(abs(x[5] - y[5]) <= 1e-6 * abs(y[5]) for x, y in zip(a["comps"], b["comps"]))   # iou: 1e-6 relative (north_star)
+    ga = [(g["cluster_id"], g["visibility_to_temporal_factor"], g["overall_mask_ids_per_label"]) for g in res["groupings"]]
+    gb = [(g["cluster_id"], g["visibility_to_temporal_factor"], g["overall_mask_ids_per_label"]) for g in ref["groupings"]]
+    assert ga == gb
+    assert res["video_coverage"] == ref["video_coverage"] and res["cluster_coverages"] == ref["cluster_coverages"]
+    assert res["one2x"] == ref["one2x"]
+
+
 def test_c1_shape_full_pipeline_vs_oracle():
     """BASELINE.json configs[0]: one 24-frame 480x854 video, 10 masks/frame, 1000 tracks per query -
     the whole device pipeline against the CPU oracle (counts, windows, matches, groups bit-exact)."""
@@ -335,20 +360,22 @@ def test_c1_shape_full_pipeline_vs_oracle():
     sc = make_scene(1234, T=24, H=480, W=854, M=10, P=1000, specials=True)
     res = discover_keymasks([_video(sc.labels, sc.tracks, sc.vis, max_label=10)], Params())[0]
     ref = ko.discover(sc.labels, sc.tracks, sc.vis)
-    assert res["status"] == ref["status"] == 1
-    assert np.array_equal(res["V"], ref["V"], equal_nan=True)
-    assert np.array_equal(res["labels1"], ref["labels1"])
-    assert json_eq(res["clusters"], ref["clusters"])
-    assert len(res["queries"]) == len(ref["queries"]) > 200
-    for a, b in zip(res["queries"], ref["queries"]):
-        assert (a["cluster_id"], a["frame_id"], a["mask_id"], a["one2x"]) == (b["cluster_id"], b["frame_id"], b["mask_id"], b["one2x"])
-        assert a["matches"] == b["matches"]
-        assert [c[:5] for c in a["comps"]] == [c[:5] for c in b["comps"]]
-    ga = [(g["cluster_id"], g["visibility_to_temporal_factor"], g["overall_mask_ids_per_label"]) for g in res["groupings"]]
-    gb = [(g["cluster_id"], g["visibility_to_temporal_factor"], g["overall_mask_ids_per_label"]) for g in ref["groupings"]]
-    assert ga == gb
-    assert res["video_coverage"] == ref["video_coverage"] and res["cluster_coverages"] == ref["cluster_coverages"]
-    assert res["one2x"] == ref["one2x"]
+    _assert_same_as_oracle(res, ref, 200)
+
+
+@pytest.mark.parametrize("order", ["raster", "random"])
+def test_c2_shape_full_pipeline_vs_oracle(order):
+    """BASELINE.json configs[1], the benchmarked shape: a 36-frame 720p video, 20 masks/frame, 4096 tracks per query
+    (the generator, seed and point order of bench.py's video 0) through the whole device pipeline - two words per
+    frame-bit row (T > 32), 23 words per match-bit row (Nm ~ 708), the 128-thread x 32-point label-table kernel with
+    TMA boxes - against the CPU oracle, every field."""
+    from s2d_b200.pipeline import Params, VideoInput, discover_keymasks
+    from s2d_b200.synth import make_scene_device
+    sc = make_scene_device(2024, 36, 720, 1280, 20, 4096, _dev(), point_order=order)
+    res = discover_keymasks([VideoInput(sc["labels"], sc["tracks"], sc["vis"], max_label=20)], Params())[0]
+    ref = ko.discover(sc["labels"].cpu().numpy(), sc["tracks"].cpu().numpy(), sc["vis"].cpu().numpy())
+    _assert_same_as_oracle(res, ref, 600)
+    assert sc["labels"].shape[0] > 32 and len(res["query_frame"]) > 640
 
 
 def json_eq(a, b):
@@ -407,6 +434,38 @@ def test_windowed_track_storage(P):
             h, u = ko.point_votes(full[q], labels, int(v0[q]), int(v1[q]), nbins=5)
             assert np.array_equal(uniq[q, inside], u) and np.array_equal(hits[q, inside], h), q
         assert (uniq[q, ~inside] == -5).all() and (hits[q, ~inside] == -5).all(), q
+
+
+def test_windowed_track_storage_partial_cover():
+    """a stored track window [tstart, tstart + Ttr) that covers only part of the device-computed [v0, v1]: the frames
+    without tracks must count as "no point landed" (iou 0) in selection and grouping, whatever hits / uniq held
+    before - identical to a full-length run whose missing frames are NaN."""
+    from s2d_b200.pipeline import Batch, VideoInput
+    from s2d_b200.synth import make_scene
+    sc = make_scene(77, T=20, H=60, W=80, M=4, P=64, occlude=False)
+    Nm, T, P, _ = sc.tracks.shape
+    rng = np.random.default_rng(5)
+    Tw = 9
+    ts = rng.integers(0, T - Tw + 1, size=Nm)
+    rowinfo = np.stack([np.zeros(Nm), np.zeros(Nm), np.full(Nm, 2), np.full(Nm, T - 3)], axis=1).astype(np.int32)
+    d = _dev()
+    lab = torch.from_numpy(sc.labels).to(d)
+    win = np.ascontiguousarray(np.stack([sc.tracks[q, ts[q]:ts[q] + Tw] for q in range(Nm)]))
+    full = np.full_like(sc.tracks, np.nan)
+    for q in range(Nm):
+        full[q, ts[q]:ts[q] + Tw] = sc.tracks[q, ts[q]:ts[q] + Tw]
+    outs = []
+    for vid, poison in ((VideoInput(labels=lab, tracks=torch.from_numpy(win).to(d), tstart=torch.from_numpy(ts.astype(np.int32)).to(d)), 12345),
+                        (VideoInput(labels=lab, tracks=torch.from_numpy(full).to(d)), 0)):
+        b = Batch([vid], stages="LD")
+        b.upload_stage_b(rowinfo, 1, 1)
+        b.hits.fill_(poison); b.uniq.fill_(max(poison, 1))
+        b.run()
+        torch.cuda.synchronize()
+        outs.append({k: getattr(b, k).cpu().numpy().copy() for k in ("mbits", "one2x", "nmatch", "glabel", "vidinfo", "clusterinfo")})
+    assert outs[1]["nmatch"].sum() > 0
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
 
 
 def test_appearance_events_vs_reference_golden():

@@ -14,18 +14,12 @@ def test_oracle_matches_reference_golden(golden_case):
 
 
 @pytest.mark.parametrize("name", ["long", "long_thr"])
-def test_oracle_matches_host_only_goldens_longer_than_one_bit_word(name):
-    """tests/golden_cpu/: 36- and 40-frame videos that end with status 1 in the unmodified reference (more than one
-    32-bit word per visibility / match bit row); they pin the oracle only, the -m gpu tests enumerate tests/golden/."""
-    import json
-    import os
-    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_cpu")
-    with open(os.path.join(d, f"{name}.json")) as f:
-        g = json.load(f)
-    z = np.load(os.path.join(d, f"{name}.npz"))
-    assert g["status"] == 1 and z["labels"].shape[0] > 32
-    res = ko.discover(z["labels"], z["tracks"], z["vis"], g["visibility_threshold"], g["matching_threshold"])
-    check_against_golden(res, g)
+def test_goldens_longer_than_one_bit_word_end_with_status_1(name):
+    """36- and 40-frame videos that end with status 1 in the unmodified reference: more than one 32-bit word per
+    visibility / match bit row. They sit in tests/golden/ so that the -m gpu tests run select / group with TW = 2."""
+    from tests.conftest import load_golden
+    g, labels, tracks, vis = load_golden(name)
+    assert g["status"] == 1 and labels.shape[0] > 32
 
 
 def test_candidate_files_match(golden_case):
