@@ -205,6 +205,9 @@ def main():
                     help="replay the step as one CUDA graph (launch-bound small workloads such as c1); per-stage "
                          "times then come from one extra un-timed pass")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-vis", default="bits", choices=["bits", "bytes"], help="wire format of the visibility flags in the e2e leg")
+    ap.add_argument("--e2e-pool", default="huge", choices=["huge", "torch"],
+                    help="host staging pool of the e2e leg: huge-page mapping + cudaHostRegister, or torch pin_memory")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-k1", action="store_true")
     args = ap.parse_args()
@@ -227,6 +230,10 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    from s2d_b200 import hostmem
+    all_cores = os.sched_getaffinity(0)
+    # cores (and with them the first-touch placement of the pinned pools) next to this rank's GPU
+    binding = hostmem.bind_to_gpu(local_rank, local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     if world > 1:
         # NCCL prints its version banner on STDOUT (NCCL_DEBUG=VERSION/WARN in this image): send its log to
         # stderr so that stdout holds the one JSON line the driver parses
@@ -330,7 +337,7 @@ def main():
     # ---- e2e: host buffers, H2D of every video's inputs + D2H of the summary inside the timed region
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, vids, dev, world, params, barrier)
+        e2e = run_e2e(args, vids, dev, world, params, barrier, binding)
 
     # ---- K1 on the tensor cores: one-hot Gram matrix of each video's label maps (outside the timed step)
     k1 = None
@@ -339,6 +346,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, all_cores)            # the CPU baseline uses every host core, not just the GPU's node
         fps, dt, npairs, n = cpu_sample(vids[0], args.cpu_queries, threads=host_threads())
         cpu = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": (f"{n} of {vids[0].tracks.shape[0]} queries of video 0, full-video window, {npairs} (query,mask) "
@@ -455,84 +463,56 @@ def run_k1(vids, batch, L):
             "checks": checks}
 
 
-def run_e2e(args, vids, dev, world, params, barrier):
-    """Same metric through the public API with HOST buffers: every step copies every video's inputs
-    from pinned host memory (a pool of distinct videos, cycled), runs the path, reads the summary
-    back. Chunks of videos are double-buffered on two streams so copies overlap compute."""
+def run_e2e(args, vids, dev, world, params, barrier, binding):
+    """Same metric through the public host-buffer API (s2d_b200.hostpipe.HostPipeline): every step copies every video's
+    inputs from page-locked host memory (a pool of distinct videos, cycled), runs the path, reads the result tables
+    back. Chunks of videos are double-buffered on two copy streams so the DMA overlaps the kernels. Visibility flags
+    travel bit-packed (the producer-side wire format, S2D_DESC_VIS_BITS) unless --e2e-vis bytes."""
     import torch
     import torch.distributed as dist
-    from s2d_b200.pipeline import Batch, VideoInput
+    from s2d_b200 import hostmem
+    from s2d_b200.hostpipe import HostPipeline, HostVideo
+    from s2d_b200.pipeline import pack_vis_bits
     nvid, T, H, W, M, P, _ = WORKLOADS[args.workload]
     chunk = min(4, nvid)
     npool = min(nvid, 2 * chunk)
-    pool = []
+    bits = args.e2e_vis == "bits"
+    src = []
     for i in range(npool):
         v = vids[i]
-        pool.append((v.labels.cpu().pin_memory(), v.tracks.cpu().pin_memory(), v.vis.cpu().pin_memory()))
-    # two device staging sets of `chunk` videos each
-    sets = []
-    for s in range(2):
-        # set s, slot j always receives pool video (s*chunk + j) % npool -> same shapes every chunk
-        src = [vids[(s * chunk + j) % npool] for j in range(chunk)]
-        dv = [VideoInput(torch.empty_like(v.labels), torch.empty_like(v.tracks), torch.empty_like(v.vis),
-                         max_label=M) for v in src]
-        b = Batch(dv)
-        outs_host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                     for t in (b.vidinfo, b.clusterinfo, b.rowinfo, b.glabel, b.one2x)]
-        sets.append((dv, b, outs_host))
-    copy_st = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-    comp_st = torch.cuda.Stream(dev)
-    nchunks = (nvid + chunk - 1) // chunk
-    h2d = sum(sum(x.numel() * x.element_size() for x in pool[(c * chunk + j) % npool])
-              for c in range(nchunks) for j in range(chunk))
-    d2h = 0
+        src += [v.labels, v.tracks, pack_vis_bits(v.vis) if bits else v.vis]
+    if args.e2e_pool == "huge":
+        pool, host = hostmem.pooled_copies(src, huge=True)
+        pool_desc = {"kind": "anonymous mapping + cudaHostRegister", "transparent_huge_pages": bool(pool.huge), "bytes": pool.nbytes}
+    else:
+        pool, host = None, [t.cpu().pin_memory() for t in src]
+        pool_desc = {"kind": "cudaHostAlloc (torch pin_memory)"}
+    del src
+    hv = [HostVideo(host[3 * i], host[3 * i + 1], host[3 * i + 2], vis_bits=bits, max_label=M) for i in range(npool)]
+    pipe = HostPipeline(hv[:chunk], dev, params)
     steps = max(2, min(args.steps, 5))
+    order = [hv[i % npool] for i in range(nvid)]
 
-    def one_step():
-        nonlocal d2h
-        d2h = 0
-        done = [None, None]
-        outs = []
-        for c in range(nchunks):
-            s = c % 2
-            dv, b, host = sets[s]
-            if done[s] is not None:
-                copy_st[s].wait_event(done[s])           # staging set free again
-            with torch.cuda.stream(copy_st[s]):
-                for j in range(chunk):
-                    hl, ht, hv = pool[(c * chunk + j) % npool]
-                    dv[j].labels.copy_(hl, non_blocking=True)
-                    dv[j].tracks.copy_(ht, non_blocking=True)
-                    dv[j].vis.copy_(hv, non_blocking=True)
-                ready = torch.cuda.Event()
-                ready.record()
-            comp_st.wait_event(ready)
-            with torch.cuda.stream(comp_st):
-                b.run(params)
-                for hbuf, t in zip(host, (b.vidinfo, b.clusterinfo, b.rowinfo, b.glabel, b.one2x)):
-                    hbuf.copy_(t, non_blocking=True)
-                done[s] = torch.cuda.Event()
-                done[s].record()
-            outs.append(host)   # consumed by the caller after the step's final synchronize
-            d2h += sum(t.numel() * t.element_size() for t in host)
-        comp_st.synchronize()
-        return outs
-
-    one_step()
+    pipe.run(order)                                   # warm-up (allocates the pinned result tables)
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        one_step()
+        pipe.run(order)
     barrier()
     dt = time.perf_counter() - t0
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
-    return {"value": nvid * T * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": 1000 * dt / steps,
-            "note": f"{nchunks} chunks of {chunk} videos per step from a pinned pool of {npool} distinct videos, "
-                    f"copies double-buffered against compute; PCIe-bound"}
+    nchunks = nvid // chunk
+    return {"value": nvid * T * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(pipe.h2d_bytes),
+            "d2h_bytes_per_step": int(pipe.d2h_bytes), "steps": steps, "ms_per_step": 1000 * dt / steps,
+            "h2d_gbs_per_gpu": pipe.h2d_bytes * steps / dt / 1e9, "gpu_launches_per_step": pipe.launches,
+            "wire_format": {"tracks": "f32 (x, y) as produced", "labels": "u8",
+                            "visibility": "bit-packed u32 (S2D_DESC_VIS_BITS)" if bits else "u8 flags"},
+            "host_pool": pool_desc, "cpu_binding": binding,
+            "note": f"{nchunks} chunks of {chunk} videos per step from a page-locked pool of {npool} distinct videos, "
+                    f"copies double-buffered against compute; bound by the host -> device DMA"}
 
 
 if __name__ == "__main__":

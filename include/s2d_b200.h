@@ -40,6 +40,8 @@ extern "C" {
 #define S2D_VIDINFO_WORDS 8
 #define S2D_CLINFO_WORDS 16
 
+#define S2D_DESC_VIS_BITS 1     /* desc.flags: `vis` is bit-packed by the producer (1/8 of the flag bytes on the wire) */
+
 typedef struct s2d_video_desc {
     int32_t T, H, W, P;
     int32_t Nm;          /* rows = (frame,label) queries of this video                      */
@@ -50,11 +52,12 @@ typedef struct s2d_video_desc {
     int64_t frame0;      /* first frame in batch-wide per-frame arrays                      */
     const uint8_t* labels;  /* device, u8  [T][H][W]      label maps, 0 = background          */
     const float*   tracks;  /* device, f32 [Nm][T][P][2]  CoTracker pred_tracks (x, y)        */
-    const uint8_t* vis;     /* device, u8  [Nm][T][P]     CoTracker pred_visibility bytes     */
+    const uint8_t* vis;     /* device, u8  [Nm][T][P]     CoTracker pred_visibility bytes; with     */
+                            /* S2D_DESC_VIS_BITS: u32 [Nm][T][ceil(P/32)], bit p%32 of word p/32 = flag p */
     const int32_t* npts;    /* device, i32 [Nm] valid points per query (<= P) or NULL = all P  */
     const int32_t* tstart;  /* device, i32 [Nm] first frame stored in `tracks` per query, NULL = 0:  */
     int32_t Ttr;            /* tracks is [Nm][Ttr][P][2]; Ttr == T unless only the window is stored */
-    int32_t pad0;           /* (long videos: SA-V-shaped configs keep Tw <= 64 frames per query)    */
+    int32_t flags;          /* S2D_DESC_* bits (long videos: SA-V-shaped configs keep Tw <= 64 frames per query) */
     int64_t vt_off;      /* elements of [Nm][T] arrays                                       */
     int64_t hits_off;    /* int32 elements                                                   */
     int64_t xbits_off;   /* u32 words of [Nm][TW] arrays                                     */
@@ -77,6 +80,15 @@ int s2d_version(void);
 int s2d_desc_size(void);            /* sizeof(s2d_video_desc), for binding self-checks */
 int s2d_device_sm_count(int device);
 
+/* Host-side helpers of the end-to-end path (host buffers -> device -> results). s2d_host_register page-locks a
+ * caller-allocated host range (e.g. an mmap'ed, huge-page backed staging pool placed on the GPU's NUMA node) so that
+ * cudaMemcpyAsync from it is a true asynchronous DMA; s2d_device_pci_bus_id writes "dddd:bb:dd.f" of a device (its sysfs
+ * node gives the NUMA node: /sys/bus/pci/devices/<id>/numa_node). The reference has no counterpart: it copies per call
+ * from pageable memory (cotracker_occlusions.py:346-356). */
+int s2d_host_register(void* ptr, int64_t bytes);
+int s2d_host_unregister(void* ptr);
+int s2d_device_pci_bus_id(int device, char* out, int len);
+
 /* All `max_*` / `total_*` arguments are host-side bounds over the batch (grid sizing and memset
  * extents): max_T = max frames, max_npix = max H*W, max_rows_x_T = max Nm*T, total_rows = sum Nm,
  * total_frames = sum T, total_vt = sum Nm*T ... */
@@ -92,7 +104,9 @@ int s2d_label_stats(const s2d_video_desc* descs, int nvideos, int max_T, int64_t
                     void* stream);
 
 /* K3a. Visibility reduce: cnt[q,t] = #nonzero flags, V = float32(cnt) / float32(P) (IEEE
- * division), replaces torch.mean(pred_visibility.float(), dim=2) (cotracker_occlusions.py:359). */
+ * division), replaces torch.mean(pred_visibility.float(), dim=2) (cotracker_occlusions.py:359).
+ * Videos flagged S2D_DESC_VIS_BITS hand the flags over bit-packed (u32 words, 4-byte aligned rows of ceil(P/32)
+ * words; bits at positions >= P of a row's last word are ignored): same counts from 1/8 of the bytes. */
 int s2d_vis_reduce(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_T,
                    int32_t* cnt, float* V, void* stream);
 

@@ -16,6 +16,7 @@ S2D_MAX_CLUSTERS = 16
 S2D_VIDINFO_WORDS = 8
 S2D_CLINFO_WORDS = 16
 S2D_PV_TMAP_BYTES = 32 * 128 + 128
+S2D_DESC_VIS_BITS = 1
 
 
 class VideoDesc(C.Structure):
@@ -25,7 +26,7 @@ class VideoDesc(C.Structure):
         ("Nm", C.c_int32), ("L", C.c_int32), ("TW", C.c_int32), ("NW", C.c_int32),
         ("row0", C.c_int64), ("frame0", C.c_int64),
         ("labels", C.c_void_p), ("tracks", C.c_void_p), ("vis", C.c_void_p), ("npts", C.c_void_p),
-        ("tstart", C.c_void_p), ("Ttr", C.c_int32), ("pad0", C.c_int32),
+        ("tstart", C.c_void_p), ("Ttr", C.c_int32), ("flags", C.c_int32),
         ("vt_off", C.c_int64), ("hits_off", C.c_int64), ("xbits_off", C.c_int64), ("mbits_off", C.c_int64),
     ]
 
@@ -39,6 +40,9 @@ SIGNATURES = {
     "s2d_version": [],
     "s2d_desc_size": [],
     "s2d_device_sm_count": [_I],
+    "s2d_host_register": [_P, _L],
+    "s2d_host_unregister": [_P],
+    "s2d_device_pci_bus_id": [_I, C.c_char_p, _I],
     "s2d_label_stats": [_P, _I, _I, _L, _L, _P, _P, _P, _P, _P, _P, _P],
     "s2d_vis_reduce": [_P, _I, _L, _P, _P, _P],
     "s2d_binarize": [_P, _I, _L, _P, _F, _P, _P],

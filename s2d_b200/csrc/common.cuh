@@ -36,8 +36,14 @@ struct StreamDeviceGuard {
         cudaGetDevice(&prev);
         dev = prev;
         cudaStream_t st = (cudaStream_t)stream;
+        if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return;
+        // a capturing stream must not be queried (it invalidates the capture); whoever captures has the stream's
+        // device current already (CUDA requires it for the launches being recorded)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); return; }
+        if (cap != cudaStreamCaptureStatusNone) return;
         int d = -1;
-        if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread && cudaStreamGetDevice(st, &d) == cudaSuccess && d >= 0) dev = d;
+        if (cudaStreamGetDevice(st, &d) == cudaSuccess && d >= 0) dev = d;
         else cudaGetLastError();
         if (dev != prev) cudaSetDevice(dev);
     }

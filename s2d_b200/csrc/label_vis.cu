@@ -159,7 +159,23 @@ vis_reduce_kernel(const s2d_video_desc* __restrict__ descs, int32_t* __restrict_
     const int n = d.npts ? min(max(d.npts[q], 0), d.P) : d.P;
     const uint8_t* row = d.vis + rt * d.P;
     int c = 0;
-    if (n == d.P && (d.P & 15) == 0 && (((uintptr_t)row) & 15) == 0) {
+    if (d.flags & S2D_DESC_VIS_BITS) {
+        // bit-packed flags: ceil(P / 32) words per row, only the first n bits count
+        const int pw = (d.P + 31) >> 5;
+        const uint32_t* wrow = reinterpret_cast<const uint32_t*>(d.vis) + rt * pw;
+        const int nfull = n >> 5;                                   // whole words
+        if ((pw & 3) == 0 && (((uintptr_t)wrow) & 15) == 0) {
+            const int4* vp = reinterpret_cast<const int4*>(wrow);
+            for (int i = lane; i < (nfull >> 2); i += 32) {
+                const int4 a = ld_stream(vp + i);
+                c += __popc((uint32_t)a.x) + __popc((uint32_t)a.y) + __popc((uint32_t)a.z) + __popc((uint32_t)a.w);
+            }
+            for (int i = (nfull & ~3) + lane; i < nfull; i += 32) c += __popc(wrow[i]);
+        } else {
+            for (int i = lane; i < nfull; i += 32) c += __popc(wrow[i]);
+        }
+        if (lane == 0 && (n & 31)) c += __popc(wrow[nfull] & ((1u << (n & 31)) - 1u));
+    } else if (n == d.P && (d.P & 15) == 0 && (((uintptr_t)row) & 15) == 0) {
         const int4* vp = reinterpret_cast<const int4*>(row);
         const int nv = d.P >> 4;
         int i = lane;

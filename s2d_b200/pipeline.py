@@ -26,7 +26,8 @@ class VideoInput:
     """Device tensors of one video (see s2d_b200.synth for the layout)."""
     labels: Optional[torch.Tensor] = None   # u8  [T,H,W]
     tracks: Optional[torch.Tensor] = None   # f32 [Nm,T,P,2]
-    vis: Optional[torch.Tensor] = None      # u8/bool [Nm,T,P]
+    vis: Optional[torch.Tensor] = None      # u8/bool [Nm,T,P]; or int32 [Nm,T,ceil(P/32)] bit-packed (pack_vis_bits) with vis_bits=True
+    vis_bits: bool = False                  # `vis` holds the flags bit-packed by the producer (1/8 of the bytes on the wire)
     npts: Optional[torch.Tensor] = None     # i32 [Nm]
     tstart: Optional[torch.Tensor] = None   # i32 [Nm]: tracks hold frames [tstart[q], tstart[q] + tracks.shape[1]) only
     max_label: Optional[int] = None         # upper bound of the label ids (default 255)
@@ -89,12 +90,19 @@ class Batch:
                     assert dm.setdefault("T", v.tracks.shape[1]) == v.tracks.shape[1]
                 dm["Nm"], dm["P"] = v.tracks.shape[0], v.tracks.shape[2]
             if v.vis is not None:
-                assert v.vis.dtype in (torch.uint8, torch.bool) and v.vis.is_contiguous() and v.vis.dim() == 3
-                if v.tracks is not None:
-                    assert tuple(v.vis.shape) == (dm["Nm"], dm["T"], dm["P"]), "inconsistent video tensors"
-                else:
+                assert v.vis.is_contiguous() and v.vis.dim() == 3
+                if v.vis_bits:
+                    assert v.vis.dtype == torch.int32 and "P" in dm, "bit-packed flags need P (from tracks or dims)"
+                    assert v.vis.shape[2] == (dm["P"] + 31) // 32 and dm.setdefault("Nm", v.vis.shape[0]) == v.vis.shape[0]
                     assert dm.setdefault("T", v.vis.shape[1]) == v.vis.shape[1]
-                    dm["Nm"], dm["P"] = v.vis.shape[0], v.vis.shape[2]
+                else:
+                    assert v.vis.dtype in (torch.uint8, torch.bool)
+                    if v.tracks is not None and v.tstart is None:
+                        assert tuple(v.vis.shape) == (dm["Nm"], dm["T"], dm["P"]), "inconsistent video tensors"
+                    else:
+                        assert dm.setdefault("T", v.vis.shape[1]) == v.vis.shape[1]
+                        assert dm.setdefault("Nm", v.vis.shape[0]) == v.vis.shape[0]
+                        assert dm.setdefault("P", v.vis.shape[2]) == v.vis.shape[2]
             T, H, W = dm["T"], dm.get("H", 1), dm.get("W", 1)
             Nm, P = dm["Nm"], dm.get("P", 1)
             assert Nm >= 1 and T >= 1
@@ -110,6 +118,7 @@ class Batch:
             d.npts = v.npts.data_ptr() if v.npts is not None else None
             d.tstart = v.tstart.data_ptr() if v.tstart is not None else None
             d.Ttr = v.tracks.shape[1] if v.tracks is not None else T
+            d.flags = _lib.S2D_DESC_VIS_BITS if (v.vis is not None and v.vis_bits) else 0
             d.vt_off, d.hits_off, d.xbits_off, d.mbits_off = vt, hits, xw, mw
             if P % 2 or (v.tracks is not None and v.tracks.data_ptr() % 16):
                 self.vec4 = 0
@@ -409,6 +418,19 @@ class Batch:
                 res["one2x"] = one2x_video
             results.append(res)
         return results
+
+
+def pack_vis_bits(vis: torch.Tensor) -> torch.Tensor:
+    """[Nm,T,P] visibility flags (bool / u8) -> int32 [Nm,T,ceil(P/32)] words, bit p % 32 of word p // 32 = flag p: the
+    producer-side wire format of S2D_DESC_VIS_BITS (torch plumbing; one pass over the flags where they are born)."""
+    Nm, T, P = vis.shape
+    pw = (P + 31) // 32
+    b = (vis != 0)
+    if pw * 32 != P:
+        b = torch.nn.functional.pad(b, (0, pw * 32 - P))
+    w = b.reshape(Nm, T, pw, 32).to(torch.int64) << torch.arange(32, device=vis.device, dtype=torch.int64)
+    w = w.sum(dim=3)
+    return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32).contiguous()
 
 
 def _setbits(words: np.ndarray, limit: int):

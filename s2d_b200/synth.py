@@ -172,10 +172,19 @@ def scene_object_map(scene: Scene) -> np.ndarray:
 # --------------------------------------------------------------------------------------
 
 def make_scene_device(seed: int, T: int, H: int, W: int, M: int, P: int, device, *,
-                      noise: float = 0.7, occlude: bool = True, point_order: str = "raster"):
+                      noise: float = 0.7, occlude: bool = True, point_order: str = "raster",
+                      window: int = 0, vis_bits: bool = False):
     """Same scene family as make_scene, built directly in HBM with torch ops (vectorised per
     frame). Returns dict(labels u8 [T,H,W], tracks f32 [Nm,T,P,2], vis u8 [Nm,T,P],
-    query_frame i32 [Nm], query_label i32 [Nm]). Background is always present."""
+    query_frame i32 [Nm], query_label i32 [Nm]). Background is always present.
+
+    `window` > 0 (long videos): full-length tracks are never materialised (SA-V-shaped videos would need 177 GB
+    each). The dict then holds `tracks` = an UNINITIALISED f32 [Nm, window, P, 2] buffer, `tstart` i32 [Nm] (zeros)
+    and `fill_window(tstart)`, which writes the tracks of frames [tstart[q], tstart[q] + window) of every query into
+    the buffer - what a windowed tracker run hands over once stage B has produced the windows.
+    `vis_bits`: the flags come bit-packed (int32 [Nm,T,ceil(P/32)], S2D_DESC_VIS_BITS); they are drawn word-wise
+    (OR / AND of four random words: 15/16 visible while the object is present, 1/16 while it is not) so that a
+    300-frame video's 22 G flags never exist as bytes."""
     import torch
 
     g = torch.Generator(device="cpu")
@@ -185,36 +194,47 @@ def make_scene_device(seed: int, T: int, H: int, W: int, M: int, P: int, device,
     ry = u(0.06, 0.14, M) * H
     cx = rx + torch.rand(M, generator=g, dtype=torch.float64) * (W - 2 * rx)
     cy = ry + torch.rand(M, generator=g, dtype=torch.float64) * (H - 2 * ry)
-    vx = u(-0.006, 0.006, M) * W
-    vy = u(-0.006, 0.006, M) * H
+    vscale = min(1.0, 36.0 / T)                       # long videos: same total displacement as a 36-frame one
+    vx = u(-0.006, 0.006, M) * W * vscale
+    vy = u(-0.006, 0.006, M) * H * vscale
     occl = (T // 3, (2 * T) // 3) if occlude else (0, 0)
 
     f32 = torch.float32
     yy = torch.arange(H, device=device, dtype=f32)[None, :, None]
     xx = torch.arange(W, device=device, dtype=f32)[None, None, :]
-    ts = torch.arange(T, device=device, dtype=f32)[:, None, None]
-    omap = torch.full((T, H, W), -1, dtype=torch.int16, device=device)
-    for k in range(M):
-        ccx = float(cx[k]) + float(vx[k]) * ts
-        ccy = float(cy[k]) + float(vy[k]) * ts
-        if k % 2:
-            m = ((xx - ccx) / float(rx[k])) ** 2 + ((yy - ccy) / float(ry[k])) ** 2 <= 1.0
-        else:
-            m = ((xx - ccx).abs() <= float(rx[k])) & ((yy - ccy).abs() <= float(ry[k]))
-        if k == 0 and occl[1] > occl[0]:
-            m[occl[0]:occl[1]] = False
-        omap[m] = k
-        del m
-    flat = omap.reshape(T, -1).long() + 1
+    labels = torch.empty((T, H, W), dtype=torch.uint8, device=device)
     area = torch.zeros((T, M + 1), dtype=torch.int64, device=device)
-    area.scatter_add_(1, flat, torch.ones_like(flat))
+    pres_l, rank_l = [], []
+    TC = max(1, min(T, (1 << 26) // (H * W)))         # frames painted at a time (bounded temporaries)
+    for t0 in range(0, T, TC):
+        t1 = min(T, t0 + TC)
+        ts = torch.arange(t0, t1, device=device, dtype=f32)[:, None, None]
+        omap = torch.full((t1 - t0, H, W), -1, dtype=torch.int16, device=device)
+        for k in range(M):
+            ccx = float(cx[k]) + float(vx[k]) * ts
+            ccy = float(cy[k]) + float(vy[k]) * ts
+            if k % 2:
+                m = ((xx - ccx) / float(rx[k])) ** 2 + ((yy - ccy) / float(ry[k])) ** 2 <= 1.0
+            else:
+                m = ((xx - ccx).abs() <= float(rx[k])) & ((yy - ccy).abs() <= float(ry[k]))
+            if k == 0 and occl[1] > occl[0]:
+                lo, hi = max(occl[0], t0) - t0, min(occl[1], t1) - t0
+                if hi > lo:
+                    m[lo:hi] = False
+            omap[m] = k
+            del m
+        flat = omap.reshape(t1 - t0, -1).long() + 1
+        a = torch.zeros((t1 - t0, M + 1), dtype=torch.int64, device=device)
+        a.scatter_add_(1, flat, torch.ones_like(flat))
+        area[t0:t1] = a
+        pres = a[:, 1:] > 0
+        rank = torch.cumsum(pres.long(), dim=1) * pres.long()      # 1-based rank among present
+        lut = torch.cat([torch.zeros((t1 - t0, 1), dtype=torch.long, device=device), rank], dim=1)
+        labels[t0:t1] = torch.gather(lut, 1, flat).reshape(t1 - t0, H, W).to(torch.uint8)
+        del flat, omap
     pres = area[:, 1:] > 0                                     # [T,M]
-    rank = torch.cumsum(pres.long(), dim=1) * pres.long()      # 1-based rank among present
-    lut = torch.cat([torch.zeros((T, 1), dtype=torch.long, device=device), rank], dim=1)
-    labels = torch.gather(lut, 1, flat).reshape(T, H, W).to(torch.uint8)
-    del flat, omap
 
-    pres_h, rank_h = pres.cpu(), rank.cpu()
+    pres_h = pres.cpu()
     n_t = pres_h.sum(1).tolist()
     Nm = int(sum(n_t))
     qf = torch.repeat_interleave(torch.arange(T), torch.tensor(n_t)).to(torch.int32)
@@ -222,12 +242,17 @@ def make_scene_device(seed: int, T: int, H: int, W: int, M: int, P: int, device,
 
     dg = torch.Generator(device=device)
     dg.manual_seed(seed * 7919 + 13)
-    tracks = torch.empty((Nm, T, P, 2), dtype=f32, device=device)
-    vis = torch.empty((Nm, T, P), dtype=torch.uint8, device=device)
+    Ttr = window if window > 0 else T
+    tracks = torch.empty((Nm, Ttr, P, 2), dtype=f32, device=device)
+    PW = (P + 31) // 32
+    vis = torch.empty((Nm, T, PW), dtype=torch.int32, device=device) if vis_bits else \
+        torch.empty((Nm, T, P), dtype=torch.uint8, device=device)
     vx_d = vx.to(device=device, dtype=f32)
     vy_d = vy.to(device=device, dtype=f32)
     dts = torch.arange(T, device=device, dtype=f32)
     pvis_obj = torch.where(pres, 0.95, 0.05).to(f32)            # [T,M]
+    base = torch.empty((Nm, P, 2), dtype=f32, device=device) if window > 0 else None
+    vel = torch.empty((Nm, 2), dtype=f32, device=device) if window > 0 else None
     row = 0
     for t in range(T):
         n = n_t[t]
@@ -246,13 +271,49 @@ def make_scene_device(seed: int, T: int, H: int, W: int, M: int, P: int, device,
         pix = order[idx]                                        # [n,P]
         px = (pix % W).to(f32) + (torch.rand((n, P), generator=dg, device=device) - 0.5) * 0.8
         py = (pix // W).to(f32) + (torch.rand((n, P), generator=dg, device=device) - 0.5) * 0.8
-        nz = torch.randn((n, T, P, 2), generator=dg, device=device) * noise
-        nz[:, t] = 0
-        dt = dts - t
-        blk = tracks[row:row + n]
-        blk[..., 0] = px[:, None, :] + (vx_d[ks][:, None] * dt[None, :])[:, :, None] + nz[..., 0]
-        blk[..., 1] = py[:, None, :] + (vy_d[ks][:, None] * dt[None, :])[:, :, None] + nz[..., 1]
+        if window > 0:
+            base[row:row + n, :, 0] = px
+            base[row:row + n, :, 1] = py
+            vel[row:row + n, 0] = vx_d[ks]
+            vel[row:row + n, 1] = vy_d[ks]
+        else:
+            nz = torch.randn((n, T, P, 2), generator=dg, device=device) * noise
+            nz[:, t] = 0
+            dt = dts - t
+            blk = tracks[row:row + n]
+            blk[..., 0] = px[:, None, :] + (vx_d[ks][:, None] * dt[None, :])[:, :, None] + nz[..., 0]
+            blk[..., 1] = py[:, None, :] + (vy_d[ks][:, None] * dt[None, :])[:, :, None] + nz[..., 1]
         pv = pvis_obj[:, ks].t()                                # [n,T]
-        vis[row:row + n] = (torch.rand((n, T, P), generator=dg, device=device) < pv[:, :, None]).to(torch.uint8)
+        if vis_bits:
+            w = torch.randint(-2 ** 31, 2 ** 31, (4, n, T, PW), generator=dg, device=device, dtype=torch.int64).to(torch.int32)
+            hi_ = w[0] | w[1] | w[2] | w[3]                     # each bit set with probability 15/16
+            lo_ = w[0] & w[1] & w[2] & w[3]                     # ... 1/16
+            wv = torch.where((pv > 0.5)[:, :, None], hi_, lo_)
+            if P % 32:
+                wv[:, :, -1] &= (1 << (P % 32)) - 1
+            vis[row:row + n] = wv
+            del w, hi_, lo_, wv
+        else:
+            vis[row:row + n] = (torch.rand((n, T, P), generator=dg, device=device) < pv[:, :, None]).to(torch.uint8)
         row += n
-    return dict(labels=labels, tracks=tracks, vis=vis, query_frame=qf.to(device), query_label=ql.to(device))
+    out = dict(labels=labels, tracks=tracks, vis=vis, query_frame=qf.to(device), query_label=ql.to(device))
+    if window > 0:
+        qf_d = out["query_frame"]
+
+        def fill_window(tstart, rows_per_pass: int = 256):
+            """tracks[q, j] = point + velocity * (tstart[q] + j - frame(q)) + N(0, noise), exact at the query frame"""
+            ts_ = tstart.to(device=device, dtype=f32)
+            j = torch.arange(Ttr, device=device, dtype=f32)
+            for r0 in range(0, Nm, rows_per_pass):
+                r1 = min(Nm, r0 + rows_per_pass)
+                dt = ts_[r0:r1, None] + j[None, :] - qf_d[r0:r1, None].to(f32)          # [n,Ttr]
+                nz = torch.randn((r1 - r0, Ttr, P, 2), generator=dg, device=device) * noise
+                nz *= (dt != 0)[:, :, None, None]
+                nz += base[r0:r1, None, :, :]
+                nz += dt[:, :, None, None] * vel[r0:r1, None, None, :]
+                tracks[r0:r1] = nz
+                del nz
+
+        out["tstart"] = torch.zeros(Nm, dtype=torch.int32, device=device)
+        out["fill_window"] = fill_window
+    return out

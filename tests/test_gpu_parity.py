@@ -171,6 +171,35 @@ def test_ragged_npts(pv_variant):
         assert np.array_equal(V[q], ko.visibility_mean(vis[q][:, :n]), equal_nan=True), q
 
 
+@pytest.mark.parametrize("P", [4096, 1000, 77, 32, 5])
+def test_vis_reduce_bit_packed_flags(P):
+    """S2D_DESC_VIS_BITS: the producer hands the visibility flags over bit-packed (1/8 of the bytes); counts and the
+    float32 means are the ones of the byte flags = the oracle's torch.mean restatement, ragged point counts included."""
+    from s2d_b200.pipeline import Batch, VideoInput, pack_vis_bits
+    rng = np.random.default_rng(P)
+    Nm, T = 7, 5
+    vis = (rng.random((Nm, T, P)) < 0.6).astype(np.uint8)
+    npts = rng.integers(0, P + 1, size=Nm).astype(np.int32)
+    npts[0] = P
+    d = _dev()
+    dv = torch.from_numpy(vis).to(d)
+    for use_npts in (False, True):
+        kw = dict(npts=torch.from_numpy(npts).to(d)) if use_npts else {}
+        res = []
+        for v in (VideoInput(vis=dv, dims=dict(H=8, W=8), **kw),
+                  VideoInput(vis=pack_vis_bits(dv), vis_bits=True, dims=dict(H=8, W=8, P=P), **kw)):
+            b = Batch([v], stages="V")
+            b.run()
+            torch.cuda.synchronize()
+            res.append((b.cnt.cpu().numpy().reshape(Nm, T), b.V.cpu().numpy().reshape(Nm, T)))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1], equal_nan=True)
+        if not use_npts:
+            assert np.array_equal(res[1][1], ko.visibility_mean(vis))
+        else:
+            want = np.stack([vis[q, :, :npts[q]].sum(1) for q in range(Nm)])
+            assert np.array_equal(res[1][0], want)
+
+
 @pytest.mark.parametrize("eps,ms", [(0.2, 5), (0.1, 5), (0.1, 3), (0.05, 5)])
 def test_hamming_dbscan_vs_oracle(eps, ms):
     import ctypes as C

@@ -88,3 +88,16 @@ def test_object_enumeration_drops_the_smallest_label_even_without_background():
     assert list(qf) == [0, 0, 1, 1] and list(ql) == [2, 5, 4, 7] and lut[(1, 7)] == 3
     for t in range(2):
         assert np.array_equal(ids[t], torch.unique(torch.from_numpy(labels[t].astype(np.int64)))[1:].numpy())
+
+
+def test_pack_vis_bits_layout():
+    """wire format of S2D_DESC_VIS_BITS: bit p % 32 of int32 word p // 32 is flag p (little-endian bit order)."""
+    import torch
+    from s2d_b200.pipeline import pack_vis_bits
+    rng = np.random.default_rng(3)
+    for P in (1, 31, 32, 33, 100, 4096):
+        vis = (rng.random((3, 4, P)) < 0.5).astype(np.uint8)
+        w = pack_vis_bits(torch.from_numpy(vis)).numpy()
+        assert w.dtype == np.int32 and w.shape == (3, 4, (P + 31) // 32)
+        ref = np.packbits(np.pad(vis, ((0, 0), (0, 0), (0, (-P) % 32))), axis=2, bitorder="little")
+        assert np.array_equal(w.view(np.uint8).reshape(3, 4, -1), ref)
