@@ -30,6 +30,11 @@ WORKLOADS = {
     "target": (64, 36, 480, 854, 20, 4096, "480p videos, 20 masks/frame, 4k tracks (north_star target shape)"),
     "tiny": (4, 12, 120, 160, 6, 256, "tiny self-test shape"),
 }
+LIST_WORKLOADS = {
+    "c3": "SA-V-shaped long videos: 16 videos x 300 frames 1080p, 30 masks/frame, 8k tracks, windowed overlap (<= 64 frames per query)",
+    "c4": "MOSE+VIPSeg mixture: 512 videos (480p-1080p, 20-120 frames, 5-30 masks/frame, 1k tracks) partitioned by video across the GPUs",
+    "c5": "stress sweep: masks/frame 10-100 x tracks 1k-16k x window 8-64 frames (480x854), every point vs the CPU baseline",
+}
 METRIC = "keymask_discovery_frames_per_sec"
 UNIT = "frames/s"
 
@@ -194,7 +199,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS) + list(LIST_WORKLOADS))
+    ap.add_argument("--list-videos", type=int, default=0, help="c3 / c4: number of videos in the list (default 16 / 512)")
+    ap.add_argument("--list-scale", type=float, default=1.0, help="c3 / c4 / c5: scale frame size by this factor (smoke runs)")
+    ap.add_argument("--hbm-budget-gb", type=float, default=110.0, help="c3 / c4 / c5: HBM per chunk of videos")
+    ap.add_argument("--digest-file", default="", help="c3 / c4: JSON file with the digest of a reference run (any GPU count) to compare with")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-queries", type=int, default=8, help="queries per step of the reference arm")
     ap.add_argument("--cpu-queries", type=int, default=48, help="queries in the cpu_baseline sample")
@@ -213,6 +222,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.workload in LIST_WORKLOADS:
+        return list_workload(args)
     if args.videos > 0:
         w = WORKLOADS[args.workload]
         WORKLOADS[args.workload] = (args.videos,) + w[1:]
@@ -366,6 +377,279 @@ def main():
         dist.destroy_process_group()
 
 
+def list_specs(args):
+    """the video list of a list workload (identical on every rank)"""
+    from dataclasses import replace
+    from s2d_b200 import workloads as wl
+    if args.workload == "c3":
+        specs = wl.c3_specs(args.list_videos or 16)
+    elif args.workload == "c4":
+        specs = wl.c4_specs(args.list_videos or 512)
+    else:
+        raise ValueError(args.workload)
+    if args.list_scale != 1.0:
+        f = args.list_scale
+        specs = [replace(s, H=max(32, int(s.H * f) // 2 * 2), W=max(32, int(s.W * f) // 2 * 2)) for s in specs]
+    return specs
+
+
+def cpu_sample_spec(spec, nq, threads, device):
+    """dense torch-CPU port on `nq` queries of one generated video of `spec` (windowed specs: over the stored window)."""
+    import numpy as np
+    import torch
+    from oracle import dense_port
+    from s2d_b200.synth import make_scene_device
+    from s2d_b200.workloads import window_starts
+    torch.set_num_threads(threads)
+    sc = make_scene_device(spec.seed, spec.T, spec.H, spec.W, spec.M, spec.P, device, window=spec.window, vis_bits=spec.vis_bits)
+    Nm = sc["tracks"].shape[0]
+    qs = [int(q) for q in np.linspace(0, Nm - 1, nq).astype(int)]
+    lab = sc["labels"].cpu().long()[..., None]
+    T = spec.T
+    if spec.window > 0:
+        ri = torch.zeros((Nm, 4), dtype=torch.int32, device=sc["query_frame"].device)
+        ri[:, 3] = T - 1
+        ts = window_starts(sc["query_frame"], ri, T, spec.window)
+        sc["fill_window"](ts)
+    t0 = time.perf_counter()
+    npairs = 0
+    for q in qs:
+        if spec.window > 0:
+            a = int(ts[q])
+            full = torch.full((T, spec.P, 2), float("nan"))
+            full[a:a + spec.window] = sc["tracks"][q].cpu()
+            v0, v1 = a, a + spec.window - 1
+        else:
+            full, v0, v1 = sc["tracks"][q].cpu(), 0, T - 1
+        m, c, o = dense_port.match_query_dense(lab, full, v0, v1, spec.H, spec.W, 0.5)
+        npairs += len(c)
+    dt = time.perf_counter() - t0
+    return T / (dt / len(qs) * Nm), dt, npairs, len(qs), Nm
+
+
+def list_workload(args):
+    """--workload c3 | c4 | c5: a LIST of videos (mixed shapes / long windowed videos / the sweep's points) instead of one
+    homogeneous batch per GPU. The list is the same on every rank; s2d_b200.partition assigns videos to ranks (LPT over
+    the byte cost), every rank runs its share through the device pipeline in HBM-sized chunks (device-timed), rank 0
+    gathers the per-video results (timed) and hashes them: the digest must not depend on the number of GPUs.
+    Strong scaling: the total work is fixed."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from s2d_b200 import hostmem, partition
+    from s2d_b200 import workloads as wl
+    from s2d_b200.pipeline import Params
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ncores = host_threads()
+        for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[k] = str(ncores)
+        dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
+        if args.workload == "c5":
+            specs = [wl.c5_specs(M, P, Tw)[0] for (M, P, Tw) in wl.c5_points()[:: max(1, 48 // max(1, args.ref_queries))]]
+        else:
+            specs = list_specs(args)
+            specs = [specs[i] for i in np.linspace(0, len(specs) - 1, min(len(specs), 3)).astype(int)]
+        vals, secs = [], []
+        for _ in range(max(1, args.steps)):
+            fr, tt, meas = 0.0, 0.0, 0.0
+            for sp in specs:
+                fps, dt, npairs, n, Nm = cpu_sample_spec(sp, 1, ncores, dev)
+                fr += sp.T; tt += sp.T / fps; meas += dt
+            vals.append(fr / tt); secs.append(meas)
+        v = sum(vals) / len(vals)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1000 * sum(secs) / len(secs), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "int64/u8 (torch CPU)", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {LIST_WORKLOADS[args.workload]}", "point_order": args.point_order},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncores, "kind": "port",
+                                 "sample": f"1 query of each of {len(specs)} videos spread over the list, dense torch-CPU port, "
+                                           f"frames/s extrapolated linearly in queries and averaged by frames"},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    all_cores = os.sched_getaffinity(0)
+    binding = hostmem.bind_to_gpu(local_rank, local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    runner = wl.DeviceRunner(dev, Params(), budget_bytes=args.hbm_budget_gb * 1e9, point_order=args.point_order)
+    peak, peak_src = _peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clocks = ClockSampler(local_rank)
+    if args.workload == "c5":
+        return c5_sweep(args, runner, rank, world, dev, barrier, max_over_ranks, clocks, peak, peak_src, all_cores)
+
+    specs = list_specs(args)
+    costs = [s.cost() for s in specs]
+    # warm-up: W small videos through every kernel of the path (attribute opt-ins, allocator, clocks)
+    warm = [wl.VideoSpec(f"warm{i}", 7 + i, 24, 240, 426, 8, specs[0].P, window=min(specs[0].window, 16), vis_bits=specs[0].vis_bits)
+            for i in range(max(3, args.warmup))]
+    runner.run_list(warm)
+    barrier()
+    clocks.start()
+    local_stats = {}
+
+    def worker(idx):
+        res, st, _ = runner.run_list([specs[i] for i in idx])
+        local_stats.update(st)
+        return res
+
+    # the gather is timed on its own, after a barrier, so that it measures the exchange and not the ranks' drift
+    parts = partition.lpt_partition(costs, world)
+    t_part0 = time.perf_counter()
+    mine = partition.lpt_partition(costs, world)[rank]
+    t_part = time.perf_counter() - t_part0
+    local = worker(mine)
+    barrier()
+    clk = clocks.stop()
+    tg0 = time.perf_counter()
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(list(zip(mine, local)), gathered, dst=0)
+        merged = sorted((p for part in gathered for p in part), key=lambda x: x[0]) if rank == 0 else None
+    else:
+        merged = sorted(zip(mine, local), key=lambda x: x[0])
+    t_gather = time.perf_counter() - tg0
+    dev_ms = max_over_ranks(local_stats["device_ms"])
+    sum_ms = torch.tensor([local_stats["device_ms"], local_stats["k2_ms"], float(local_stats["k2_bytes"]), float(local_stats["k2_tiles"]),
+                           float(local_stats["launches"]), local_stats["vis_ms"], float(local_stats["vis_bytes"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(sum_ms)
+    tot = sum_ms.tolist()
+    if rank == 0:
+        results = [r for _, r in merged]
+        assert [i for i, _ in merged] == list(range(len(specs)))
+        digest = wl.list_digest(results)
+        frames = sum(r["frames"] for r in results)
+        total_s = dev_ms / 1000.0 + t_gather + t_part
+        ref_digest, equal = None, None
+        dpath = args.digest_file or os.path.join(ROOT, "profiles", f"{args.workload}_digest.json")
+        if os.path.exists(dpath):
+            dj = json.load(open(dpath))
+            key = f"{args.workload}/{len(specs)}/{args.list_scale}/{args.point_order}"
+            if key in dj:
+                ref_digest, equal = dj[key]["digest"], dj[key]["digest"] == digest
+        loads = [sum(costs[i] for i in p) for p in parts]
+        k2_gbs = tot[2] / (tot[1] / 1000.0) / 1e9 if tot[1] > 0 else 0.0
+        line = {"metric": METRIC, "value": frames / total_s, "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": len(warm),
+                "ms_per_step": 1000 * total_s, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u8/int32 (f32 tracks, f64 scores)", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {LIST_WORKLOADS[args.workload]}", "videos": len(specs),
+                           "frames": frames, "queries": sum(r["queries"] for r in results), "list_scale": args.list_scale,
+                           "point_order": args.point_order, "hbm_budget_gb": args.hbm_budget_gb,
+                           "partition": f"LPT by video over {world} GPU(s), host gather of per-video results (gather_object)",
+                           "cache": "every chunk's inputs >> 126 MB L2, no flush needed"},
+                "timed_region": {"device_ms_max_over_ranks": dev_ms, "gather_ms": 1000 * t_gather, "partition_ms": 1000 * t_part,
+                                 "note": "device_ms = CUDA-event time of every chunk's kernels + result read-back, summed per rank, max over "
+                                         "ranks; generation of the synthetic inputs (upstream producers) is outside; gather timed after a barrier"},
+                "balance": {"max_over_mean_cost": max(loads) / (sum(loads) / len(loads)), "device_ms_sum_over_ranks": tot[0]},
+                "clocks": clk, "gpu_launches": int(tot[4]),
+                "roofline": {"kernel": "point_votes_tab_kernel (all chunks of all ranks)", "bound": "hbm", "achieved": k2_gbs, "peak": peak,
+                             "unit": "GB/s", "frac": k2_gbs / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes": tot[2], "ms_sum_over_ranks": tot[1], "tiles": int(tot[3]),
+                             "vis_reduce": {"achieved": tot[6] / (tot[5] / 1000.0) / 1e9 if tot[5] > 0 else None, "algorithmic_bytes": tot[6], "ms": tot[5]}},
+                "results": {"digest": digest, "reference_digest": ref_digest, "results_equal": equal,
+                            "videos_ok": sum(1 for r in results if r["status"] == 1), "keymasks": sum(r["keymasks"] for r in results),
+                            "candidates": sum(r["candidates"] for r in results)},
+                "e2e": None, "cpu_binding": binding}
+        if world == 1 and not args.no_cpu:
+            os.sched_setaffinity(0, all_cores)
+            sp = specs[len(specs) // 2]
+            fps, dt, npairs, n, Nm = cpu_sample_spec(sp, 1, host_threads(), dev)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": host_threads(), "kind": "port",
+                                    "sample": f"1 of {Nm} queries of video {sp.name} ({sp.T} x {sp.H}x{sp.W}, window {sp.window or sp.T}), "
+                                              f"{npairs} pairs in {dt:.1f} s, extrapolated linearly in queries"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def c5_sweep(args, runner, rank, world, dev, barrier, max_over_ranks, clocks, peak, peak_src, all_cores):
+    """the 48 points of the sweep are dealt to the ranks round-robin by cost; per point: frames/s of the device path, the
+    K2 roofline fraction, and the CPU port on one query of the same video (all host cores / ranks per rank)."""
+    import torch
+    import torch.distributed as dist
+    from s2d_b200 import partition
+    from s2d_b200 import workloads as wl
+    pts = wl.c5_points()
+    plists = [wl.c5_specs(M, P, Tw) for (M, P, Tw) in pts]
+    if args.list_scale != 1.0:
+        from dataclasses import replace
+        f = args.list_scale
+        plists = [[replace(s, H=max(32, int(s.H * f) // 2 * 2), W=max(32, int(s.W * f) // 2 * 2)) for s in pl] for pl in plists]
+    costs = [sum(s.cost() for s in pl) for pl in plists]
+    mine = partition.lpt_partition(costs, world)[rank]
+    runner.run_list([wl.VideoSpec(f"warm{i}", 7 + i, 16, 240, 426, 8, 1024) for i in range(3)])
+    barrier()
+    clocks.start()
+    out = []
+    dev_ms = 0.0
+    threads = max(1, len(all_cores) // world)
+    for pi in mine:
+        M, P, Tw = pts[pi]
+        res, st, _ = runner.run_list(plists[pi], reps=2)      # second repetition is the one reported (first warms the shape)
+        dev_ms += st["device_ms"]
+        k2 = st["k2_bytes"] / (st["k2_ms"] / 1000.0) / 1e9 if st["k2_ms"] > 0 else 0.0
+        rec = {"masks_per_frame": M, "tracks": P, "window": Tw, "videos": len(plists[pi]), "frames": st["frames"],
+               "frames_per_s": st["frames"] / (st["device_ms"] / 1000.0), "device_ms": st["device_ms"],
+               "k2_gbs": k2, "k2_frac": k2 / peak, "k2_ms": st["k2_ms"], "videos_ok": sum(1 for r in res if r["status"] == 1),
+               "digest": wl.list_digest(res)}
+        if not args.no_cpu:
+            fps, dt, npairs, n, Nm = cpu_sample_spec(plists[pi][0], 1, threads, dev)
+            rec["cpu_frames_per_s"] = fps
+            rec["cpu_sample"] = f"1 of {Nm} queries, {npairs} pairs in {dt:.2f} s on {threads} threads"
+        out.append((pi, rec))
+    barrier()
+    clk = clocks.stop()
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(out, gathered, dst=0)
+        merged = sorted((p for part in gathered for p in part), key=lambda x: x[0]) if rank == 0 else None
+    else:
+        merged = sorted(out, key=lambda x: x[0])
+    t_max = max_over_ranks(dev_ms)
+    if rank == 0:
+        recs = [r for _, r in merged]
+        frames = sum(r["frames"] for r in recs)
+        fr = [r["k2_frac"] for r in recs]
+        line = {"metric": METRIC, "value": frames / (t_max / 1000.0), "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": 3,
+                "ms_per_step": t_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u8/int32 (f32 tracks, f64 scores)", "data": "synthetic",
+                "config": {"workload": f"c5: {LIST_WORKLOADS['c5']}", "points": len(recs), "list_scale": args.list_scale,
+                           "partition": f"LPT by sweep point over {world} GPU(s)", "cache": "inputs per point >> 126 MB L2"},
+                "clocks": clk, "roofline": {"kernel": "point_votes_tab_kernel", "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+                                           "frac_min": min(fr), "frac_median": sorted(fr)[len(fr) // 2], "frac_max": max(fr),
+                                           "achieved": sorted(r["k2_gbs"] for r in recs)[len(recs) // 2], "frac": sorted(fr)[len(fr) // 2], "traffic": None},
+                "cpu_baseline": None if args.no_cpu else {
+                    "value": frames / sum(r["frames"] / r["cpu_frames_per_s"] for r in recs), "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": "1 query of the first video of every sweep point, dense torch-CPU port, extrapolated linearly in queries; frames-weighted"},
+                "sweep": recs, "e2e": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_k1(vids, batch, L):
     """Cross-frame mask-overlap matrix of a video (all (frame,label) masks against each other) as an int8
     contraction on the tensor cores, operands synthesised on-chip from the label maps. Reports achieved
@@ -489,7 +773,7 @@ def run_e2e(args, vids, dev, world, params, barrier, binding):
         pool_desc = {"kind": "cudaHostAlloc (torch pin_memory)"}
     del src
     hv = [HostVideo(host[3 * i], host[3 * i + 1], host[3 * i + 2], vis_bits=bits, max_label=M) for i in range(npool)]
-    pipe = HostPipeline(hv[:chunk], dev, params)
+    pipe = HostPipeline(hv[:2 * chunk] if npool >= 2 * chunk else hv[:chunk], dev, params, chunk=chunk)
     steps = max(2, min(args.steps, 5))
     order = [hv[i % npool] for i in range(nvid)]
 

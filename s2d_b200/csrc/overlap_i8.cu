@@ -264,7 +264,7 @@ gram_labels_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npi
             const int rl = isA ? tid : tid - GM_BLOCK_M;                 // row inside the A or B tile
             const int r = (isA ? m0 : n0) + rl;
             const bool rvalid = r < R;
-            const int f = rvalid ? r / L : 0;
+            const int f = rvalid ? r / L : (isA ? fa0 : fb0);        // padding rows: any frame slot of their operand (output is zero)
             const uint32_t sp = rvalid ? (uint32_t)(r - f * L) * 0x01010101u : 0xFEFEFEFEu;   // 0xFE never matches (L <= 254)
             const int lab_off = (isA ? (f - fa0) : nfa + (f - fb0)) * 128;
             const int row_off = (isA ? 0 : A_BYTES) + rl * 128;
@@ -458,7 +458,7 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
             // ---- operand producers: thread t of a group builds A row t and B row t; group g takes k-blocks g, g+2, ... ----
             const int rA = m0 + tid, rB = n0 + tid;
             const bool vA = rA < R && !diag, vB = rB < R;
-            const int fA = rA < R ? rA / L : 0, fB = vB ? rB / L : 0;
+            const int fA = rA < R ? rA / L : fa0, fB = vB ? rB / L : fb0;    // padding rows: frame slot 0 of their operand (output is zero)
             const uint32_t spA = vA ? (uint32_t)(rA - fA * L) * 0x01010101u : 0xFEFEFEFEu;   // 0xFE never matches (L <= 254)
             const uint32_t spB = vB ? (uint32_t)(rB - fB * L) * 0x01010101u : 0xFEFEFEFEu;
             const int frA = diag ? 0 : fA - fa0, frB = nfa + (fB - fb0);                      // frame slots in the label ring

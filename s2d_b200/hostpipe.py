@@ -35,23 +35,26 @@ class HostVideo:
 
 
 class HostPipeline:
-    """Staging sets + batches for chunks of `chunk` videos shaped like `like` (one entry per slot of a chunk). The
-    allocation happens here, once; run() only enqueues copies and kernels."""
+    """Two staging sets + batches for chunks of `chunk` videos. `like` gives the shapes of the slots: `chunk` entries
+    (both sets alike) or 2 * `chunk` entries (even chunks land in the first half's shapes, odd chunks in the second
+    half's). The allocation happens here, once; run() only enqueues copies and kernels."""
 
     RESULT_TABLES = ("vidinfo", "clusterinfo", "rowinfo", "glabel", "one2x")
 
-    def __init__(self, like: Sequence[HostVideo], device, params: Params = Params()):
+    def __init__(self, like: Sequence[HostVideo], device, params: Params = Params(), chunk: Optional[int] = None):
         self.device = torch.device(device)
         self.params = params
-        self.chunk = len(like)
-        self.sigs = [v.signature() for v in like]
+        self.chunk = int(chunk) if chunk else len(like)
+        assert len(like) in (self.chunk, 2 * self.chunk)
+        halves = [list(like[:self.chunk]), list(like[-self.chunk:])]
+        self.sigs = [[v.signature() for v in h] for h in halves]
         self.sets = []
         with torch.cuda.device(self.device):
-            for _ in range(2):
+            for h in halves:
                 dv = [VideoInput(torch.empty(v.labels.shape, dtype=torch.uint8, device=self.device),
                                  torch.empty(v.tracks.shape, dtype=torch.float32, device=self.device),
                                  torch.empty(v.vis.shape, dtype=v.vis.dtype, device=self.device),
-                                 vis_bits=v.vis_bits, max_label=v.max_label) for v in like]
+                                 vis_bits=v.vis_bits, max_label=v.max_label) for v in h]
                 b = Batch(dv, device=self.device)
                 self.sets.append((dv, b))
             self.copy_streams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
@@ -66,8 +69,8 @@ class HostPipeline:
         overwritten by the next run). Synchronises the device once, at the end."""
         assert len(videos) % self.chunk == 0, "the list must be a whole number of chunks"
         nchunks = len(videos) // self.chunk
-        b0 = self.sets[0][1]
         while len(self.host_results) < nchunks:      # first call only: pinned result tables for every chunk
+            b0 = self.sets[len(self.host_results) % 2][1]
             self.host_results.append({k: torch.empty(getattr(b0, k).shape, dtype=getattr(b0, k).dtype, pin_memory=True)
                                       for k in self.RESULT_TABLES})
         done = [None, None]
@@ -81,7 +84,7 @@ class HostPipeline:
                 with torch.cuda.stream(self.copy_streams[s]):
                     for j in range(self.chunk):
                         hv = videos[c * self.chunk + j]
-                        assert hv.signature() == self.sigs[j], "video does not fit the staging slot it lands in"
+                        assert hv.signature() == self.sigs[s][j], "video does not fit the staging slot it lands in"
                         dv[j].labels.copy_(hv.labels, non_blocking=True)
                         dv[j].tracks.copy_(hv.tracks, non_blocking=True)
                         dv[j].vis.copy_(hv.vis, non_blocking=True)

@@ -367,6 +367,10 @@ class Batch:
                 if want_comps:
                     hits = h["hits"][d.hits_off:d.hits_off + Nm * T * L].reshape(Nm, T, L)
                     uniq = h["uniq"][d.vt_off:d.vt_off + Nm * T].reshape(Nm, T)
+                    # windowed track storage: frames without stored tracks were not voted on (their hits / uniq are
+                    # whatever the buffers held); they count as intersection 0 / union 0, like in s2d_select
+                    tsv = self.videos[vi].tstart
+                    ts_h = tsv.cpu().numpy().astype(np.int64) if tsv is not None else None
                 queries = []
                 for c in range(k):
                     rows = np.nonzero((ri[:, 0] == c) & (ri[:, 1] >= 0))[0]
@@ -384,8 +388,9 @@ class Batch:
                             comps = []
                             for t in range(v0, v1 + 1):
                                 gids = gid_of[f0 + t]
+                                stored = ts_h is None or ts_h[g] <= t < ts_h[g] + d.Ttr
                                 for o in np.nonzero(gids >= 0)[0]:
-                                    I, U = int(hits[g, t, o]), int(uniq[g, t])
+                                    I, U = (int(hits[g, t, o]), int(uniq[g, t])) if stored else (0, 0)
                                     comps.append((t, int(o), int(gids[o]), I, U, 0.0 if U == 0 else I / U))
                             q["comps"] = comps
                         queries.append(q)
