@@ -598,10 +598,23 @@ point_votes_tma_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
 constexpr int PV_MAX_BANDS = 6;
 constexpr uint32_t PV_PK_INVALID = 0xFFFFFFFFu;
 
-__host__ __device__ constexpr int pv_buf_bytes(int threads, int ppt, int ctas) {
-    // 228 KB per SM, 1 KB reserved per CTA, <= 2 KB static shared memory, 64 B slack behind the table
-    const int cap = ((233472 / ctas - 1024 - 2048 - 64) / 128) * 128;
-    return cap < threads * ppt * 8 ? threads * ppt * 8 : cap;
+// Shared memory of the label-table kernel, all of it dynamic and carved by hand so that phase B can address it as
+// (one base register | compile-time offset):
+//   [0, 1024)            vote histogram, 256 int32 - the base is 1 KB aligned, so a bin's address is (4 * label) | base
+//   [1024, 1152)         dummy words (all ones): target of points outside the band
+//   [1152, 1664)         PvCtl: mbarriers, tile records, scheduler state, per-warp bounding boxes
+//   [1664, +TRK)         SPLIT only: the tile's tracks (their own region: the next tile's tracks are fetched as soon as
+//                        phase A has read this tile's, i.e. during the table fetch and phase B)
+//   [.., +BUF + 64)      the buffer: the tile's tracks (not SPLIT), then its label table (+ 64 B slack for row copies)
+constexpr int PV_FIXED_BYTES = 1664;
+__host__ __device__ constexpr int pv_buf_bytes(int threads, int ppt, int ctas, bool split) {
+    // 228 KB per SM, 1 KB reserved by the system per CTA
+    const int avail = 233472 / ctas - 1024 - PV_FIXED_BYTES - 64 - (split ? threads * ppt * 8 : 0);
+    const int cap = (avail / 128) * 128;
+    return (!split && cap < threads * ppt * 8) ? threads * ppt * 8 : cap;
+}
+__host__ __device__ constexpr int pv_smem_bytes(int threads, int ppt, int ctas, bool split) {
+    return PV_FIXED_BYTES + (split ? threads * ppt * 8 : 0) + pv_buf_bytes(threads, ppt, ctas, split) + 64;
 }
 
 // (iy << 16 | ix) of a point that lands inside the frame, PV_PK_INVALID otherwise (W, H <= 65535)
@@ -709,13 +722,26 @@ __device__ __forceinline__ bool pv_plan_next(PvPlan& pl, PvTile* rec, int lane, 
     return true;
 }
 
-template <int THREADS, int PPT, int CTAS>
+struct PvCtl {
+    uint2 wred[16];                  // per-warp packed (min, max + 1) of (iy, ix)
+    uint64_t full, full2, tabbar;    // tracks arrive in two halves: phase A starts on the first
+    PvTile tinfo[2];                 // current tile, next tile (planned during the current one)
+    PvPlan plan;                     // scheduler state (kept out of the registers)
+    const float* nsrc;               // tracks of the planned tile
+    int more;
+};
+static_assert(sizeof(PvCtl) <= 512, "PvCtl must fit its slot of the shared-memory layout");
+
+template <int THREADS, int PPT, int CTAS, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, CTAS)
 point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __restrict__ rowplan,
                        int total_rows, int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
                        int32_t* __restrict__ uniq, const uint8_t* __restrict__ tmaps) {
-    constexpr int BUF_BYTES = pv_buf_bytes(THREADS, PPT, CTAS);
+    constexpr int BUF_BYTES = pv_buf_bytes(THREADS, PPT, CTAS, SPLIT);
+    constexpr int TRK_BYTES = SPLIT ? THREADS * PPT * 8 : 0;
     constexpr int NWARPS = THREADS / 32;
+    static_assert(NWARPS <= 16, "PvCtl::wred");
+    static_assert(BUF_BYTES >= 8192, "label table buffer too small");
     // the fallback bitmap lives in the buffer: the largest power of two of words that fits (at most 2^13 = 32 KB)
     constexpr int FB_LOGW = BUF_BYTES >= 32768 ? 13 : (BUF_BYTES >= 16384 ? 12 : 11);
     constexpr int FB_WORDS = 1 << FB_LOGW;
@@ -723,15 +749,21 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     static_assert(BUF_BYTES >= FB_WORDS * 4, "the fallback bitmap lives in the buffer");
     static_assert(S2D_MAX_LABELS % THREADS == 0 || THREADS % S2D_MAX_LABELS == 0, "output phase: whole warps per pass");
     static_assert(PPT % 4 == 0, "points are read two at a time, in two halves");
-    extern __shared__ __align__(128) uint8_t buf[];   // tracks of the tile, then its label table
-    __shared__ int hist[S2D_MAX_LABELS];
-    __shared__ __align__(8) uint2 wred[NWARPS];        // per-warp packed (min, max + 1) of (iy, ix)
-    __shared__ uint32_t dummy[32];                     // all ones: target of points outside the band
-    __shared__ __align__(8) uint64_t full, full2, tabbar;   // tracks arrive in two halves: phase A starts on the first
-    __shared__ PvTile tinfo[2];                        // current tile, next tile (planned during the current one)
-    __shared__ PvPlan plan_s;                          // scheduler state (kept out of the registers)
-    __shared__ const float* nsrc_s;                    // tracks of the planned tile
-    __shared__ int more_s;
+    // the address of a static __shared__ variable costs ptxas seven uniform instructions (S2UR SR_CgaCtaId, UMOV, ULEA ...)
+    // and it re-materialised them in every group of four points (ncu: 6 % of the kernel's instructions): everything
+    // lives in dynamic shared memory at compile-time offsets from one base register (layout: pv_buf_bytes above)
+    extern __shared__ __align__(1024) uint8_t dsm[];
+    int* const hist = reinterpret_cast<int*>(dsm);
+    uint32_t* const dummy = reinterpret_cast<uint32_t*>(dsm + 1024);
+    PvCtl& ctl = *reinterpret_cast<PvCtl*>(dsm + 1152);
+    uint8_t* const trk = dsm + PV_FIXED_BYTES;                  // landing zone of the tile's tracks
+    uint8_t* const buf = dsm + PV_FIXED_BYTES + TRK_BYTES;      // label table (not SPLIT: the same bytes as trk)
+    uint2* const wred = ctl.wred;
+    uint64_t& full = ctl.full; uint64_t& full2 = ctl.full2; uint64_t& tabbar = ctl.tabbar;
+    PvTile* const tinfo = ctl.tinfo;
+    PvPlan& plan_s = ctl.plan;
+    const float*& nsrc_s = ctl.nsrc;
+    int& more_s = ctl.more;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total = ctrl[1];
@@ -762,9 +794,9 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         const uint32_t b1 = min(bytes, (uint32_t)(THREADS * PPT * 4));
         const uint64_t pol = l2_policy_evict_first();
         mbar_expect_tx(&full, b1);
-        bulk_g2s_hint(buf, nsrc_s, b1, &full, pol);
+        bulk_g2s_hint(trk, nsrc_s, b1, &full, pol);
         mbar_expect_tx(&full2, bytes - b1);
-        if (bytes > b1) bulk_g2s_hint(buf + b1, reinterpret_cast<const uint8_t*>(nsrc_s) + b1, bytes - b1, &full2, pol);
+        if (bytes > b1) bulk_g2s_hint(trk + b1, reinterpret_cast<const uint8_t*>(nsrc_s) + b1, bytes - b1, &full2, pol);
     };
     if (warp == 0) {
         plan(&tinfo[0]);
@@ -773,8 +805,11 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     }
     __syncthreads();
 
-    const uint32_t tab_s = smem_u32(buf);
-    const uint32_t dummy_s = smem_u32(&dummy[lane]);
+    // the shuffle makes the base an ordinary register value that ptxas cannot re-derive from SR_CgaCtaId at every use
+    const uint32_t hist_s = __shfl_sync(0xffffffffu, smem_u32(dsm), 0);
+    if (hist_s & 1023u) __trap();                     // a bin's address is formed as (4 * label) | hist_s
+    const uint32_t tab_s = hist_s + (uint32_t)(PV_FIXED_BYTES + TRK_BYTES);
+    const uint32_t dummy_s = hist_s + 1024u + 4u * (uint32_t)lane;
     uint32_t tabphase = 0;
     int scur = 0, snxt = 1;                           // slots of tile j and of tile j + 1 (planned during tile j)
     for (int j = 0;; ++j) {
@@ -789,7 +824,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         // ---- phase A: buffer -> registers, round / bounds / pack, bounding box ----------------
         uint32_t pk[PPT];
         uint32_t mn = 0xFFFFFFFFu, mx = 0;
-        const float4* sp = reinterpret_cast<const float4*>(buf);
+        const float4* sp = reinterpret_cast<const float4*>(trk);
         auto point_pair = [&](int k) -> float4 { return sp[k * THREADS + tid]; };
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -898,6 +933,10 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                     if (warp == 0 && !planned) {      // overlap the plan's dependent loads with the table's flight
                         plan(&tinfo[snxt]);
                         planned = true;
+                        if (SPLIT) {                  // the tracks region is free since S1: the next tile's tracks fly from here on
+                            __syncwarp();
+                            if (lane == 0 && more_s) issue_tracks(tinfo[snxt].pad);
+                        }
                     }
                     if (warp == 0) mbar_wait(&tabbar, tabphase);
                     __syncthreads();
@@ -916,7 +955,6 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                     // the lanes of a warp that hit the same bin are merged); bin 255 collects the
                     // points that were not first and is dropped in the output phase (L <= 255 here).
                     constexpr int G = (PPT < 8 || CTAS >= 5) ? 4 : 8;
-                    const uint32_t hist_s = smem_u32(hist);
                     const bool banded = bh > R;        // several bands: most groups of a pass are outside its band
 #pragma unroll
                     for (int g = 0; g < PPT; g += G) {
@@ -931,17 +969,19 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                         for (int k = 0; k < G; ++k) {
                             const uint32_t e = pk[g + k] - pk0;
                             const uint32_t off = (e >> 16) * negc + e + tabc;      // table + dy * pitch + dx + a15
-                            sh[k] = off << 3;                                      // used modulo 32 (wrapping shifts)
+                            sh[k] = (off << 3) - 2u;                               // rotation counts, used modulo 32
                             const uint32_t addr = (e < lim) ? (off & ~3u) : dummy_s;
 #ifdef S2D_PV_BOUNDS_CHECK      // debug build (make check): every claimed byte lies inside the fetched table
                             if (e < lim && (off - tab_s >= (uint32_t)BUF_BYTES || off - tabc >= rows * pitch)) __trap();
 #endif
-                            asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old[k]) : "r"(addr), "r"(__funnelshift_l(0u, 0xFFu, sh[k])));
+                            // 0xFF in byte (off & 3) = 0x3FC rotated left by 8 * (off & 3) - 2
+                            asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old[k]) : "r"(addr), "r"(__funnelshift_l(0x3FCu, 0x3FCu, sh[k])));
                         }
 #pragma unroll
                         for (int k = 0; k < G; ++k) {
-                            const uint32_t lab = __funnelshift_r(old[k], 0u, sh[k]) & 0xFFu;   // 0xFF: not first / not in band
-                            asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(hist_s + lab * 4u) : "memory");
+                            // 4 * label = the byte rotated down to bits 2..9 (label 0xFF: not first / not in band)
+                            const uint32_t bin = (__funnelshift_r(old[k], old[k], sh[k]) & 0x3FCu) | hist_s;     // one LOP3
+                            asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(bin) : "memory");
                         }
                     }
                     if (b0 + R < bh) {                 // the next band's copies overwrite the table
@@ -968,10 +1008,16 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                 }
             }
         }
-        if (warp == 0 && !planned) plan(&tinfo[snxt]);
+        if (warp == 0 && !planned) {
+            plan(&tinfo[snxt]);
+            if (SPLIT) {
+                __syncwarp();
+                if (lane == 0 && more_s) issue_tracks(tinfo[snxt].pad);
+            }
+        }
         fence_proxy_async();                          // buffer atomics before the next tile's bulk copy
         __syncthreads();                              // S2: histogram complete, buffer free, next record visible
-        if (tid == 0 && more_s) {                     // the next tile's tracks fly during the output phase
+        if (!SPLIT && tid == 0 && more_s) {           // the next tile's tracks fly during the output phase
             issue_tracks(tinfo[snxt].pad);
         }
 #pragma unroll
@@ -988,11 +1034,11 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     }
 }
 
-template <int THREADS, int PPT, int CTAS>
+template <int THREADS, int PPT, int CTAS, bool SPLIT = false>
 static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, const int4* rowplan,
                          int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq, const uint8_t* tmaps) {
-    const int smem = pv_buf_bytes(THREADS, PPT, CTAS) + 64;
-    auto kfn = point_votes_tab_kernel<THREADS, PPT, CTAS>;
+    const int smem = pv_smem_bytes(THREADS, PPT, CTAS, SPLIT);
+    auto kfn = point_votes_tab_kernel<THREADS, PPT, CTAS, SPLIT>;
     static bool configured[S2D_MAX_DEVICES] = {};
     {
         cudaError_t e = opt_in_smem(kfn, smem, configured);
@@ -1137,7 +1183,17 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
         S2D_CHECK_LAUNCH("pv_scan_kernel");
         const int tr = (int)total_rows;
         if (variant == 0) {      // label-table kernels
-            if (max_P <= 128 * 8) return launch_pv_tab<128, 8, 6>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+#ifdef S2D_EXPERIMENTS   // 8 KB tiles: CTAs per SM / split tracks region (A/B runs)
+            if (max_P <= 128 * 8 && getenv("S2D_PV_SMALL")) {
+                const int v = atoi(getenv("S2D_PV_SMALL"));
+                if (v == 60) return launch_pv_tab<128, 8, 6, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                if (v == 6) return launch_pv_tab<128, 8, 6, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                if (v == 7) return launch_pv_tab<128, 8, 7, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                if (v == 8) return launch_pv_tab<128, 8, 8, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                if (v == 9) return launch_pv_tab<128, 8, 9, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+            }
+#endif
+            if (max_P <= 128 * 8) return launch_pv_tab<128, 8, 7, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
             if (max_P <= 128 * 16) return launch_pv_tab<128, 16, 6>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
 #ifdef S2D_EXPERIMENTS   // CTAs per SM of the 4096-point configuration (A/B runs; 6 x 128 threads is the measured best)
             if (max_P <= 256 * 16) {

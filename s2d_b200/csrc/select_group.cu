@@ -60,7 +60,7 @@ select_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __restric
             const int gid = g0[tt * S2D_MAX_LABELS + l];
             int I = h0[j], U = u0[tt];                    // unconditional: the three loads of all unrolled steps fly together
             if (t0 + tt < ts0 || t0 + tt >= ts1) { I = 0; U = 0; }
-            if (gid >= 0) {
+            if (gid >= 0 && gid < d.Nm) {          // (a label map that enumerates more objects than the caller's Nm rows: ignored, decode() reports it)
                 // iou = intersection / union as python floats, 0.0 when union == 0 (matching.py:659-662).
                 // The comparison iou > thr is decided without the division whenever I - thr * U is clearly
                 // away from zero (one FMA; a gap of 1e-12 * U is thousands of ulps of the quotient), and by
@@ -73,7 +73,7 @@ select_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __restric
                     m1 = dm > tol ? true : (dm < -tol ? false : (fI / fU > match_thr));
                     m2 = d2 > tol ? true : (d2 < -tol ? false : (fI / fU > one2x_iou));
                 }
-                S2D_DEV_ASSERT(gid < d.Nm && tt <= t1 - t0);
+                S2D_DEV_ASSERT((gid >> 5) < d.NW && tt <= t1 - t0);
                 if (m1) {
                     atomicOr(&mrow[gid >> 5], 1u << (gid & 31));
                     ++nm;
