@@ -273,6 +273,16 @@ int s2d_overlap_gram_executed_ops(int nframes, int nlab, int64_t npix, double* o
 int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int nlab, int64_t npix, int32_t* work,
                             int32_t* G, void* stream);
 
+/* Banded form of the Gram overlap ("all mask pairs within a frame window", BASELINE.json north_star kernel 1): only pairs
+ * of rows whose frames are at most band_frames apart. Gband: int32 [R][(2 * band_frames + 1) * nlab],
+ * Gband[f * nlab + l][(d + band_frames) * nlab + l2] = |mask(f, l) AND mask(f + d, l2)| for -band <= d <= band, 0 when frame
+ * f + d does not exist. Only the 256 x 256 blocks of the symmetric matrix that touch the band are executed (long videos:
+ * 300 frames x 30 labels, band 64 -> a third of the upper triangle), each block's pixel range split to fill whole waves.
+ * Needs the 256 x 256 tiling (s2d_overlap_gram_tiling == 2). work: s2d_overlap_gram_band_work_ints() int32. */
+int s2d_overlap_gram_band_work_ints(int nframes, int nlab, int64_t npix, int band_frames, int64_t* out);
+int s2d_overlap_gram_labels_banded(const uint8_t* labels, int nframes, int nlab, int64_t npix, int band_frames,
+                                   int32_t* work, int32_t* Gband, void* stream);
+
 /* Rasterise tracks of one query into a u8 plane per frame (pred_tracks_to_binary_masks,
  * return_mask=False, cotracker_matching.py:453-503) - the dense A operand of K1. */
 int s2d_rasterise_tracks(const float* tracks, int T, int P, int H, int W, uint8_t* planes,

@@ -67,6 +67,8 @@ SIGNATURES = {
     "s2d_overlap_i8": [_P, _I, _P, _I, _L, _P, _P],
     "s2d_overlap_gram_work_ints": [_I, _I, _L, C.POINTER(C.c_int64)],
     "s2d_overlap_gram_tiling": [_I, _I, C.POINTER(C.c_int)],
+    "s2d_overlap_gram_band_work_ints": [_I, _I, _L, _I, C.POINTER(C.c_int64)],
+    "s2d_overlap_gram_labels_banded": [_P, _I, _I, _L, _I, _P, _P, _P],
     "s2d_overlap_gram_executed_ops": [_I, _I, _L, C.POINTER(C.c_double)],
     "s2d_overlap_gram_labels": [_P, _I, _I, _L, _P, _P, _P],
     "s2d_color_to_labels_work_ints": [_I, C.POINTER(C.c_int64)],

@@ -99,48 +99,89 @@ label_hist_kernel(const s2d_video_desc* __restrict__ descs, int32_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// K0b: object enumeration. One CTA (256 threads = one per label) per video, frames in order.
+// K0b: object enumeration. One CTA (8 warps) per video. The only sequential quantity is the first global id of a
+// frame (a prefix sum of the frames' object counts): pass 1 counts the objects of every frame (a warp per frame,
+// lane = 8 labels, eight ballots), a block scan turns the counts into first ids, pass 2 writes the tables - the
+// frames' loads are independent, so the kernel costs a few global-memory latencies instead of one per frame.
 // ------------------------------------------------------------------------------------------
+constexpr int FT_MAX_T = 1024;            // frames per video (s2d_windows has the same limit)
+
+__device__ __forceinline__ void ft_presence(const int32_t* __restrict__ arow, int lane, uint32_t (&pres)[8]) {
+    int a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = arow[k * 32 + lane];          // label k * 32 + lane
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pres[k] = __ballot_sync(0xffffffffu, a[k] > 0);
+}
+
 __global__ void __launch_bounds__(S2D_MAX_LABELS)
 frame_tables_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __restrict__ area,
                     int32_t* __restrict__ gid_of, int32_t* __restrict__ frameinfo,
                     int32_t* __restrict__ qframe, int32_t* __restrict__ qlabel,
                     int32_t* __restrict__ vidinfo) {
     const s2d_video_desc d = descs[blockIdx.x];
-    __shared__ uint32_t pres[8];
-    const int l = threadIdx.x, w = l >> 5, lane = l & 31;
-    int gid_base = 0;
-    for (int t = 0; t < d.T; ++t) {
+    __shared__ int first[FT_MAX_T + 1];
+    __shared__ int wsum[8];
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int T = min(d.T, FT_MAX_T);
+    // pass 1: objects per frame (present labels minus the smallest one)
+    for (int t = w; t < T; t += 8) {
+        uint32_t pres[8];
+        ft_presence(area + (d.frame0 + t) * S2D_MAX_LABELS, lane, pres);
+        int total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) total += __popc(pres[k]);
+        if (lane == 0) first[t] = total > 0 ? total - 1 : 0;
+    }
+    __syncthreads();
+    // exclusive scan of first[0..T) (T <= 1024: four values per thread)
+    int v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int t = tid * 4 + k; v[k] = t < T ? first[t] : 0; s += v[k]; }
+    int x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    int before = 0, total_obj = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const int t = wsum[k]; if (k < w) before += t; total_obj += t; }
+    int run = before + x - s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int t = tid * 4 + k; if (t < T) first[t] = run; run += v[k]; }
+    __syncthreads();
+    // pass 2: tables
+    for (int t = w; t < T; t += 8) {
         const int64_t f = d.frame0 + t;
-        const bool p = area[f * S2D_MAX_LABELS + l] > 0;
-        const uint32_t b = __ballot_sync(0xffffffffu, p);
-        if (lane == 0) pres[w] = b;
-        __syncthreads();
-        int below = 0, total = 0, minlab = -1;
+        uint32_t pres[8];
+        ft_presence(area + f * S2D_MAX_LABELS, lane, pres);
+        int total = 0, minlab = -1;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const uint32_t m = pres[k];
-            total += __popc(m);
-            if (k < w) below += __popc(m);
-            if (minlab < 0 && m) minlab = k * 32 + __ffs(m) - 1;
+            if (minlab < 0 && pres[k]) minlab = k * 32 + __ffs(pres[k]) - 1;
+            total += __popc(pres[k]);
         }
-        below += __popc(b & ((1u << lane) - 1u));
-        int gid = -1;
-        if (p && l != minlab) {
-            gid = gid_base + below - 1;
-            S2D_DEV_ASSERT(gid >= 0);
-            if (gid < d.Nm) {
-                qframe[d.row0 + gid] = t;
-                qlabel[d.row0 + gid] = l;
+        const int gid_base = first[t];
+        int below = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int l = k * 32 + lane;
+            const bool p = (pres[k] >> lane) & 1u;
+            int gid = -1;
+            if (p && l != minlab) {
+                gid = gid_base + below + __popc(pres[k] & ((1u << lane) - 1u)) - 1;
+                S2D_DEV_ASSERT(gid >= 0);
+                if (gid < d.Nm) {
+                    qframe[d.row0 + gid] = t;
+                    qlabel[d.row0 + gid] = l;
+                }
             }
+            gid_of[f * S2D_MAX_LABELS + l] = gid;
+            below += __popc(pres[k]);
         }
-        gid_of[f * S2D_MAX_LABELS + l] = gid;
-        const int nobj = total > 0 ? total - 1 : 0;
-        if (l == 0) reinterpret_cast<int4*>(frameinfo)[f] = make_int4(nobj, gid_base, minlab, total);
-        gid_base += nobj;
-        __syncthreads();
+        if (lane == 0) reinterpret_cast<int4*>(frameinfo)[f] = make_int4(total > 0 ? total - 1 : 0, gid_base, minlab, total);
     }
-    if (l == 0) vidinfo[blockIdx.x * S2D_VIDINFO_WORDS + 5] = gid_base;
+    if (tid == 0) vidinfo[blockIdx.x * S2D_VIDINFO_WORDS + 5] = total_obj;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -230,8 +271,8 @@ extern "C" int s2d_label_stats(const s2d_video_desc* descs, int nvideos, int max
     S2D_ENTER(stream);
     S2D_CHECK_ARG(descs && area && gid_of && frameinfo && qframe && qlabel && vidinfo,
                   "s2d_label_stats: null pointer");
-    S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_T > 0 && max_T <= 65535 && max_npix > 0,
-                  "s2d_label_stats: bad sizes nvideos=%d max_T=%d", nvideos, max_T);
+    S2D_CHECK_ARG(nvideos > 0 && nvideos <= 65535 && max_T > 0 && max_T <= FT_MAX_T && max_npix > 0,
+                  "s2d_label_stats: bad sizes nvideos=%d max_T=%d (videos of up to %d frames)", nvideos, max_T, FT_MAX_T);
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(area, 0, (size_t)total_frames * S2D_MAX_LABELS * sizeof(int32_t), st);
     dim3 grid((unsigned)((max_npix + LH_BYTES_PER_CTA - 1) / LH_BYTES_PER_CTA), max_T, nvideos);

@@ -402,11 +402,11 @@ constexpr int G2_GROUPS = 2;             // producer groups working on alternate
 constexpr int G2_GTHREADS = 256;         // threads per group: thread t builds A row t and B row t
 constexpr int G2_PRODUCERS = G2_GROUPS * G2_GTHREADS;
 
+template <int STAGES>     // 3 operand stages; 2 when the label ring of a shape with few labels per frame needs the room
 __global__ void __launch_bounds__(G2_PRODUCERS + 32, 1)
 gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t npix, int kblocks_total,
                     int nt, int s_off, int s_diag, int per_off, int per_diag, int nfr_max, int Rp,
-                    int32_t* __restrict__ part, int64_t part_ints) {
-    constexpr int STAGES = G2_STAGES;
+                    int32_t* __restrict__ part, int64_t part_ints, const int2* __restrict__ blist) {
     constexpr int GT = G2_GTHREADS;
     constexpr int A_BYTES = G2_AM * GM_BLOCK_K;
     constexpr int B_BYTES = G2_BN * GM_BLOCK_K;
@@ -425,12 +425,19 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
     const int tid = threadIdx.x % GT, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // tid: index inside the group
     // symmetric: block column nj holds the block rows 0 .. nj (256 x 256 blocks). A diagonal block's A rows ARE its
     // B rows: it synthesises the B tile only and points both A descriptors into it.
+    // banded form (blist != nullptr): an explicit list of blocks (only those whose frames lie within the band), every block
+    // split s_off times; its partial tiles are stored tile by tile ([cta][256][256]) instead of in the dense [split][R][Rp]
     int x = blockIdx.x, mi = 0, nj = 0;
-    for (;;) {
-        const int cnt = (mi == nj) ? s_diag : s_off;
-        if (x < cnt) break;
-        x -= cnt;
-        if (++mi > nj) { mi = 0; ++nj; }
+    if (blist) {
+        const int2 b = blist[x / s_off];
+        mi = b.x; nj = b.y; x = x % s_off;
+    } else {
+        for (;;) {
+            const int cnt = (mi == nj) ? s_diag : s_off;
+            if (x < cnt) break;
+            x -= cnt;
+            if (++mi > nj) { mi = 0; ++nj; }
+        }
     }
     const bool diag = mi == nj;
     const int split = x, kblocks_per_split = diag ? per_diag : per_off;
@@ -541,23 +548,26 @@ gram_labels2_kernel(const uint8_t* __restrict__ labels, int F, int L, int64_t np
                 __syncwarp();
                 if (lane == 0) bar_arrive(&full[s]);                           // one arrival per producer warp of the group
             }
-            // ---- epilogue: warps 0-3 own the four TMEM lane quarters; two accumulators (A rows 0-127 and 128-255) ----
-            if (warp < 4) {
+            // ---- epilogue: all 16 producer warps drain TMEM. A warp may only touch the lane quarter (warp % 4); the four
+            // warps of a quarter take every fourth 32-column block. Two accumulators (A rows 0-127 and 128-255) ----
+            {
+                const int qd = warp & 3, cgrp = warp >> 2;                 // warps 0-15: both producer groups
                 bar_wait(&accum_full, 0);
                 tc_fence_after();
 #pragma unroll 1
                 for (int acc = 0; acc < 2; ++acc) {
-                    const int row = m0 + acc * GM_BLOCK_M + warp * 32 + lane;
-                    int32_t* prow = part + ((int64_t)split * R + row) * Rp;
+                    const int row = m0 + acc * GM_BLOCK_M + qd * 32 + lane;
+                    int32_t* prow = blist ? part + ((int64_t)blockIdx.x * G2_AM + (row - m0)) * G2_BN - n0      // tile-addressed
+                                          : part + ((int64_t)split * R + row) * Rp;
 #pragma unroll 1
-                    for (int c0 = 0; c0 < G2_BN; c0 += 32) {
+                    for (int c0 = cgrp * 32; c0 < G2_BN; c0 += 32 * (G2_PRODUCERS / 128)) {
                         uint32_t v[32];
-                        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + acc * G2_BN + c0, v);
+                        tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + acc * G2_BN + c0, v);
                         if (row < R) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const int col = n0 + c0 + j;
-                                S2D_DEV_ASSERT(col >= Rp || (((int64_t)split * R + row) * Rp + col + 4 <= part_ints));
+                                S2D_DEV_ASSERT(col >= Rp || (prow + col >= part && prow + col + 4 <= part + part_ints));
                                 if (col < Rp) *reinterpret_cast<uint4*>(prow + col) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                             }
                         }
@@ -603,6 +613,67 @@ __global__ void gram_reduce_kernel(const int32_t* __restrict__ part, int splits,
     S2D_DEV_ASSERT(cc < Rp);
     for (int s = 0; s < ns; ++s) acc += part[((int64_t)s * R + rr) * Rp + cc];
     G[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Banded form: only pairs of rows whose frames are at most `band` apart ("all mask pairs within a frame window").
+// Blocks (mi <= nj) of 256 x 256 rows are kept when the closest frames of their row / column ranges are within the band.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline bool gram_band_block(int mi, int nj, int R, int L, int band) {
+    const int fa1 = (min(R - 1, mi * G2_AM + G2_AM - 1)) / L;      // last frame of the block's rows
+    const int fb0 = (nj * G2_BN) / L;                               // first frame of its columns (nj >= mi)
+    return fb0 - fa1 <= band;
+}
+
+// index[mi * nt + nj] = position of block (mi, nj) in blist, -1 when it is outside the band; one thread (<= a few thousand blocks)
+__global__ void gram_band_plan_kernel(int nt, int R, int L, int band, int32_t* __restrict__ index, int2* __restrict__ blist) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int n = 0;
+    for (int nj = 0; nj < nt; ++nj)
+        for (int mi = 0; mi < nt; ++mi) {
+            int v = -1;
+            if (mi <= nj && gram_band_block(mi, nj, R, L, band)) { blist[n] = make_int2(mi, nj); v = n++; }
+            index[mi * nt + nj] = v;
+        }
+}
+
+// Gband[r][(d + band) * L + l2] = overlap of row r = (f, l) with row (f + d, l2), 0 when frame f + d does not exist
+__global__ void gram_band_reduce_kernel(const int32_t* __restrict__ part, const int32_t* __restrict__ index, int nt, int splits,
+                                        int F, int L, int band, int32_t* __restrict__ Gband) {
+    const int Wb = (2 * band + 1) * L;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)F * L * Wb) return;
+    const int r = (int)(i / Wb), c = (int)(i - (int64_t)r * Wb);
+    const int f2 = r / L + c / L - band;
+    int acc = 0;
+    if (f2 >= 0 && f2 < F) {
+        const int r2 = f2 * L + c % L;
+        const int rr = min(r, r2), cc = max(r, r2);
+        const int bi = index[(rr >> 8) * nt + (cc >> 8)];
+        S2D_DEV_ASSERT(bi >= 0);
+        if (bi >= 0)
+            for (int s = 0; s < splits; ++s) acc += part[(((int64_t)bi * splits + s) * G2_AM + (rr & 255)) * G2_BN + (cc & 255)];
+    }
+    Gband[i] = acc;
+}
+
+static int gram_band_blocks(int R, int L, int band) {
+    const int nt = (R + G2_BN - 1) / G2_BN;
+    int n = 0;
+    for (int nj = 0; nj < nt; ++nj)
+        for (int mi = 0; mi <= nj; ++mi) n += gram_band_block(mi, nj, R, L, band) ? 1 : 0;
+    return n;
+}
+
+// splits of the pixel range per block: the count (<= 8) that fills whole waves of 148 CTAs best
+static int gram_band_splits(int nblk, int kblocks) {
+    int best = 1; double beff = -1.0;
+    for (int sp = 1; sp <= 8 && sp <= kblocks; ++sp) {
+        const double waves = (double)nblk * sp / 148.0;
+        const double eff = waves / (double)((int64_t)(waves + 0.999999));
+        if (eff > beff + 1e-9) { beff = eff; best = sp; }
+    }
+    return best;
 }
 
 static int gram_tiles(int mt, int nt, int BN) {        // tiles that touch the upper triangle (see gram_labels_kernel)
@@ -656,26 +727,37 @@ static bool gram_use_v2(int R) {
 }
 
 // shared memory of the two-m-tile kernel: the label ring grows with the frames a 256-row tile touches (256 / L + 2)
-static int gram2_smem(int F, int L, int* nfr_max_out) {
+static int gram2_smem(int F, int L, int stages, int* nfr_max_out) {
     const int per_tile = G2_AM / L + 2;
     const int nfr_max = 2 * (F < per_tile ? F : per_tile);
     if (nfr_max_out) *nfr_max_out = nfr_max;
-    return G2_STAGES * (G2_AM + G2_BN) * GM_BLOCK_K + G2_GROUPS * ((GR_PF + 1) * nfr_max * 128 + 2 * nfr_max * 8) + 1024;
+    return stages * (G2_AM + G2_BN) * GM_BLOCK_K + G2_GROUPS * ((GR_PF + 1) * nfr_max * 128 + 2 * nfr_max * 8) + 1024;
+}
+// operand stages of the 256 x 256 kernel for this shape: 3 if the label ring fits beside them, else 2, else 0 (narrower tilings)
+static int gram2_stages(int F, int L) {
+    constexpr int SMEM_MAX = 227 * 1024;
+#ifdef S2D_EXPERIMENTS
+    if (getenv("S2D_GRAM_STAGES") && atoi(getenv("S2D_GRAM_STAGES")) == 2) return gram2_smem(F, L, 2, nullptr) <= SMEM_MAX ? 2 : 0;
+#endif
+    if (gram2_smem(F, L, G2_STAGES, nullptr) <= SMEM_MAX) return G2_STAGES;
+    if (gram2_smem(F, L, 2, nullptr) <= SMEM_MAX) return 2;
+    return 0;
 }
 
+template <int STAGES>
 static int launch_gram2(const uint8_t* labels, int F, int L, int64_t npix, int32_t* work, int32_t* G, cudaStream_t st) {
     const int R = F * L;
     int nfr_max;
-    const int smem = gram2_smem(F, L, &nfr_max);
+    const int smem = gram2_smem(F, L, STAGES, &nfr_max);
     if (smem > 227 * 1024) { set_error("s2d_overlap_gram_labels: nlab=%d is too small for the label ring (needs %d B of shared memory)", L, smem); return -1; }
-    cudaError_t e = cudaFuncSetAttribute(gram_labels2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(gram_labels2_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("gram_labels2_kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return -2; }
     int nt, kblocks, s_off, s_diag, per_off, per_diag, Rp;
     gram2_plan(R, npix, &nt, &kblocks, &s_off, &s_diag, &per_off, &per_diag, &Rp);
     const int nctas = nt * s_diag + nt * (nt - 1) / 2 * s_off;
-    gram_labels2_kernel<<<nctas, G2_PRODUCERS + 32, smem, st>>>(labels, F, L, npix, kblocks, nt, s_off, s_diag, per_off, per_diag,
+    gram_labels2_kernel<STAGES><<<nctas, G2_PRODUCERS + 32, smem, st>>>(labels, F, L, npix, kblocks, nt, s_off, s_diag, per_off, per_diag,
                                                               nfr_max, Rp, work,
-                                                              (int64_t)(s_off > s_diag ? s_off : s_diag) * R * Rp);
+                                                              (int64_t)(s_off > s_diag ? s_off : s_diag) * R * Rp, nullptr);
     S2D_CHECK_LAUNCH("gram_labels2_kernel");
     gram_reduce_kernel<<<(unsigned)(((int64_t)R * R + 255) / 256), 256, 0, st>>>(work, s_off, s_diag, R, Rp, G);
     S2D_CHECK_LAUNCH("gram_reduce_kernel");
@@ -810,9 +892,66 @@ extern "C" int s2d_overlap_gram_labels(const uint8_t* labels, int nframes, int n
     const int R = nframes * nlab;
     int tiling = 0;
     s2d_overlap_gram_tiling(nframes, nlab, &tiling);
-    if (tiling == 2) return launch_gram2(labels, nframes, nlab, npix, work, G, st);
+    if (tiling == 2) return gram2_stages(nframes, nlab) == 2 ? launch_gram2<2>(labels, nframes, nlab, npix, work, G, st)
+                                                             : launch_gram2<G2_STAGES>(labels, nframes, nlab, npix, work, G, st);
     if (tiling == 1) return launch_gram<256>(labels, nframes, nlab, npix, work, G, st);
     return launch_gram<128>(labels, nframes, nlab, npix, work, G, st);
+}
+
+extern "C" int s2d_overlap_gram_band_work_ints(int nframes, int nlab, int64_t npix, int band_frames, int64_t* out) {
+    if (!out || nframes <= 0 || nlab <= 0 || npix <= 0 || band_frames < 0) return -1;
+    const int R = nframes * nlab, nt = (R + G2_BN - 1) / G2_BN;
+    const int nblk = gram_band_blocks(R, nlab, band_frames);
+    const int kblocks = (int)((npix + GM_BLOCK_K - 1) / GM_BLOCK_K);
+    *out = (int64_t)nt * nt + 2 * (int64_t)nblk + 4 + (int64_t)nblk * gram_band_splits(nblk, kblocks) * G2_AM * G2_BN;
+    return 0;
+}
+
+extern "C" int s2d_overlap_gram_labels_banded(const uint8_t* labels, int nframes, int nlab, int64_t npix, int band_frames,
+                                              int32_t* work, int32_t* Gband, void* stream) {
+    S2D_ENTER(stream);
+    S2D_CHECK_ARG(labels && Gband && work && nframes > 0 && nlab > 0 && nlab <= 254 && npix > 0 && band_frames >= 0,
+                  "s2d_overlap_gram_labels_banded: bad arguments");
+    S2D_CHECK_ARG(npix % 16 == 0 && (((uintptr_t)labels) & 15) == 0 && (((uintptr_t)work) & 15) == 0,
+                  "s2d_overlap_gram_labels_banded: label maps / work must be 16-byte aligned with a pixel count that is a multiple of 16");
+    S2D_CHECK_ARG((int64_t)nframes * nlab <= 46340, "s2d_overlap_gram_labels_banded: too many rows");
+    const int stages = gram2_stages(nframes, nlab);
+    S2D_CHECK_ARG(stages > 0, "s2d_overlap_gram_labels_banded: nlab=%d is too small for the label ring of the 256 x 256 tiling", nlab);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = nframes * nlab, nt = (R + G2_BN - 1) / G2_BN;
+    const int nblk = gram_band_blocks(R, nlab, band_frames);
+    const int kblocks = (int)((npix + GM_BLOCK_K - 1) / GM_BLOCK_K);
+    int splits = gram_band_splits(nblk, kblocks);
+    const int per = (kblocks + splits - 1) / splits;
+    splits = (kblocks + per - 1) / per;                                   // no empty splits
+    int32_t* index = work;
+    int64_t off = (int64_t)nt * nt;
+    off += off & 1;
+    int2* blist = reinterpret_cast<int2*>(work + off);
+    off += 2 * (int64_t)nblk;
+    off = (off + 3) & ~(int64_t)3;
+    int32_t* part = work + off;
+    gram_band_plan_kernel<<<1, 32, 0, st>>>(nt, R, nlab, band_frames, index, blist);
+    S2D_CHECK_LAUNCH("gram_band_plan_kernel");
+    int nfr_max;
+    const int smem = gram2_smem(nframes, nlab, stages, &nfr_max);
+    const int64_t part_ints = (int64_t)nblk * splits * G2_AM * G2_BN;
+    if (stages == 2) {
+        cudaError_t e = cudaFuncSetAttribute(gram_labels2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { set_error("gram_labels2_kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return -2; }
+        gram_labels2_kernel<2><<<nblk * splits, G2_PRODUCERS + 32, smem, st>>>(labels, nframes, nlab, npix, kblocks, nt, splits, splits, per, per,
+                                                                           nfr_max, G2_BN * nt, part, part_ints, blist);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(gram_labels2_kernel<G2_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { set_error("gram_labels2_kernel: shared memory opt-in failed: %s", cudaGetErrorString(e)); return -2; }
+        gram_labels2_kernel<G2_STAGES><<<nblk * splits, G2_PRODUCERS + 32, smem, st>>>(labels, nframes, nlab, npix, kblocks, nt, splits, splits, per, per,
+                                                                                   nfr_max, G2_BN * nt, part, part_ints, blist);
+    }
+    S2D_CHECK_LAUNCH("gram_labels2_kernel (banded)");
+    const int64_t nout = (int64_t)R * (2 * band_frames + 1) * nlab;
+    gram_band_reduce_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(part, index, nt, splits, nframes, nlab, band_frames, Gband);
+    S2D_CHECK_LAUNCH("gram_band_reduce_kernel");
+    return 0;
 }
 
 extern "C" int s2d_overlap_gram_executed_ops(int nframes, int nlab, int64_t npix, double* out) {
@@ -840,7 +979,7 @@ extern "C" int s2d_overlap_gram_tiling(int nframes, int nlab, int* out) {
     // few labels per frame = many frames per operand tile = a bigger label ring: fall back to the narrower tilings
     // (256 x 256 two-m-tile -> 128 x 256 -> 128 x 128) until the ring fits beside the operand stages
     constexpr int SMEM_MAX = 227 * 1024;
-    if (gram_use_v2(R) && gram2_smem(nframes, nlab, nullptr) <= SMEM_MAX) *out = 2;
+    if (gram_use_v2(R) && gram2_stages(nframes, nlab) > 0) *out = 2;
     else if (gram1_smem(256, nframes, nlab, nullptr) <= SMEM_MAX) *out = 1;
     return 0;
 }

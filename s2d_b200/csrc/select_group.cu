@@ -14,9 +14,13 @@ namespace s2d {
 // select: one warp per candidate query
 // ------------------------------------------------------------------------------------------
 constexpr int SEL_WARPS = 4;
-constexpr int SEL_MAX_T = 1024;          // frames per video (s2d_windows has the same limit)
 
-__global__ void __launch_bounds__(SEL_WARPS * 32, 10)
+// One warp per candidate query, lane = label: for every frame of the window the lanes load the frame's hit counts
+// (one coalesced row of hits[q, t, :]) and global ids, the union count is a broadcast load. The number of masks with
+// iou > one2x_iou in a frame is a ballot + popcount (no shared memory, no atomics), match bits are rare atomicOr's
+// into the query's bit row. Four frames are in flight per step (independent loads). Frames for which no tracks are
+// stored (windowed storage) count as intersection 0 / union 0.
+__global__ void __launch_bounds__(SEL_WARPS * 32)
 select_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __restrict__ hits,
               const int32_t* __restrict__ uniq, const int32_t* __restrict__ gid_of,
               const int32_t* __restrict__ rowinfo, double match_thr, double one2x_iou,
@@ -34,59 +38,66 @@ select_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __restric
         return;
     }
     uint32_t* mrow = mbits + d.mbits_off + (int64_t)q * d.NW;
-    int warn = 0, nm = 0, maxg = -1;
-    // The (frame, label) cells of the query's window are one contiguous run of hits[q]: the lanes walk
-    // it 32 cells at a time with every load independent (a loop over frames with a warp reduction per
-    // frame is a chain of global-memory latencies). Cells with iou > one2x_iou are rare: they bump a
-    // per-frame counter in shared memory, and the frames with more than one are counted at the end.
-    __shared__ int c25s[SEL_WARPS][SEL_MAX_T];
-    int* c25 = c25s[threadIdx.x >> 5];
     const int L = d.L;
-    // windowed track storage: only frames [ts0, ts0 + Ttr) of the query were voted on (s2d_point_votes clips its
-    // tiles to them and leaves the rest of hits / uniq untouched); every other frame of [v0, v1] counts as "no
-    // tracked point landed in the frame": intersection 0, union 0, iou 0.0
-    const int ts0 = d.tstart ? d.tstart[q] : 0, ts1 = ts0 + d.Ttr;
-    for (int t0 = max(ri.z, 0); t0 <= min(ri.w, d.T - 1); t0 += SEL_MAX_T) {      // one segment unless the window is huge
-        const int t1 = min(min(ri.w, d.T - 1), t0 + SEL_MAX_T - 1);
-        for (int t = t0 + lane; t <= t1; t += 32) c25[t - t0] = 0;
-        __syncwarp();
-        const int ncell = (t1 - t0 + 1) * L;
-        const int32_t* h0 = hits + d.hits_off + ((int64_t)q * d.T + t0) * L;
-        const int32_t* u0 = uniq + d.vt_off + (int64_t)q * d.T + t0;
-        const int32_t* g0 = gid_of + (d.frame0 + t0) * S2D_MAX_LABELS;
-        int tt = lane / L, l = lane - tt * L;              // cell j = tt * L + l, advanced by 32 per step without dividing
-#pragma unroll 8
-        for (int j = lane; j < ncell; j += 32) {
-            const int gid = g0[tt * S2D_MAX_LABELS + l];
-            int I = h0[j], U = u0[tt];                    // unconditional: the three loads of all unrolled steps fly together
-            if (t0 + tt < ts0 || t0 + tt >= ts1) { I = 0; U = 0; }
-            if (gid >= 0 && gid < d.Nm) {          // (a label map that enumerates more objects than the caller's Nm rows: ignored, decode() reports it)
-                // iou = intersection / union as python floats, 0.0 when union == 0 (matching.py:659-662).
-                // The comparison iou > thr is decided without the division whenever I - thr * U is clearly
-                // away from zero (one FMA; a gap of 1e-12 * U is thousands of ulps of the quotient), and by
-                // the reference's own expression otherwise.
-                const double fI = (double)I, fU = (double)U, tol = 1e-12 * fU;
-                const double dm = fma(-match_thr, fU, fI), d2 = fma(-one2x_iou, fU, fI);
-                bool m1, m2;
-                if (U == 0) { m1 = 0.0 > match_thr; m2 = 0.0 > one2x_iou; }
-                else {
-                    m1 = dm > tol ? true : (dm < -tol ? false : (fI / fU > match_thr));
-                    m2 = d2 > tol ? true : (d2 < -tol ? false : (fI / fU > one2x_iou));
-                }
-                S2D_DEV_ASSERT((gid >> 5) < d.NW && tt <= t1 - t0);
-                if (m1) {
-                    atomicOr(&mrow[gid >> 5], 1u << (gid & 31));
-                    ++nm;
-                    maxg = max(maxg, gid);
-                }
-                if (m2) atomicAdd(&c25[tt], 1);
-            }
-            l += 32;
-            while (l >= L) { l -= L; ++tt; }
+    const int ts0 = d.tstart ? d.tstart[q] : 0, ts1 = ts0 + d.Ttr;        // frames that carry votes
+    const int t0 = max(ri.z, 0), t1 = min(ri.w, d.T - 1);
+    const int32_t* hq = hits + d.hits_off + (int64_t)q * d.T * L;
+    const int32_t* uq = uniq + d.vt_off + (int64_t)q * d.T;
+    const int32_t* gq = gid_of + d.frame0 * S2D_MAX_LABELS;
+    int warn = 0, nm = 0, maxg = -1;
+    // iou = intersection / union as python floats, 0.0 when union == 0 (matching.py:659-662). The comparison iou > thr
+    // is decided without the division whenever I - thr * U is clearly away from zero (one FMA; a gap of 1e-12 * U is
+    // thousands of ulps of the quotient), and by the reference's own expression otherwise.
+    auto score = [&](int I, int U, int gid, int& c25) {
+        if (gid < 0 || gid >= d.Nm) return;       // not an object (or a label map that enumerates more objects than Nm rows)
+        const double fI = (double)I, fU = (double)U, tol = 1e-12 * fU;
+        const double dm = fma(-match_thr, fU, fI), d2 = fma(-one2x_iou, fU, fI);
+        bool m1, m2;
+        if (U == 0) { m1 = 0.0 > match_thr; m2 = 0.0 > one2x_iou; }
+        else {
+            m1 = dm > tol ? true : (dm < -tol ? false : (fI / fU > match_thr));
+            m2 = d2 > tol ? true : (d2 < -tol ? false : (fI / fU > one2x_iou));
         }
-        __syncwarp();
-        for (int t = t0 + lane; t <= t1; t += 32) warn += c25[t - t0] > 1 ? 1 : 0;
-        __syncwarp();
+        if (m1) {
+            S2D_DEV_ASSERT((gid >> 5) < d.NW);
+            atomicOr(&mrow[gid >> 5], 1u << (gid & 31));
+            ++nm;
+            maxg = max(maxg, gid);
+        }
+        c25 += m2 ? 1 : 0;
+    };
+    if (L <= 32) {
+        constexpr int FR = 4;                      // frames in flight
+        for (int tb = t0; tb <= t1; tb += FR) {
+            int I[FR], U[FR], g[FR];
+#pragma unroll
+            for (int k = 0; k < FR; ++k) {         // all loads of the step first (clamped: always inside the query's rows)
+                const int t = min(tb + k, t1);
+                I[k] = lane < L ? hq[(int64_t)t * L + lane] : 0;
+                g[k] = lane < L ? gq[(int64_t)t * S2D_MAX_LABELS + lane] : -1;
+                U[k] = uq[t];
+            }
+#pragma unroll
+            for (int k = 0; k < FR; ++k) {
+                const int t = tb + k;
+                if (t > t1) break;                 // warp-uniform
+                if (t < ts0 || t >= ts1) { I[k] = 0; U[k] = 0; }
+                int c25 = 0;
+                score(I[k], U[k], g[k], c25);
+                warn += (__popc(__ballot_sync(0xffffffffu, c25 != 0)) > 1) ? 1 : 0;     // same value in every lane
+            }
+        }
+        warn *= (lane == 0) ? 1 : 0;               // counted once
+    } else {
+        for (int t = t0; t <= t1; ++t) {
+            const bool stored = t >= ts0 && t < ts1;
+            const int U = stored ? uq[t] : 0;
+            int c25 = 0;
+            for (int l = lane; l < L; l += 32)
+                score(stored ? hq[(int64_t)t * L + l] : 0, U, gq[(int64_t)t * S2D_MAX_LABELS + l], c25);
+            c25 = warp_sum(c25);
+            warn += (lane == 0 && c25 > 1) ? 1 : 0;
+        }
     }
     warn = warp_sum(warn);
     nm = warp_sum(nm);

@@ -60,7 +60,9 @@ def test_gram_tiling_query_is_host_only():
         t = C.c_int(-1)
         _lib.call("s2d_overlap_gram_tiling", F, L, C.byref(t))
         got[(F, L)] = t.value
-    assert got == {(36, 21): 2, (64, 31): 2, (30, 18): 2, (24, 14): 1, (24, 11): 0, (48, 6): 0, (100, 3): 0, (3, 4): 0}
+    # (24, 14), (24, 11), (48, 6): the 256 x 256 kernel with two operand stages instead of three, so that the label ring
+    # of shapes with few labels per frame fits (round 1 fell back to 128-row tiles there: the C1 shape ran at 18 %)
+    assert got == {(36, 21): 2, (64, 31): 2, (30, 18): 2, (24, 14): 2, (24, 11): 2, (48, 6): 2, (100, 3): 0, (3, 4): 0}
     n = C.c_int64()
     for F, L in got:                       # the scratch size covers whichever tiling is chosen
         _lib.call("s2d_overlap_gram_work_ints", F, L, 64 * 48, C.byref(n))

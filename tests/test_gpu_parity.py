@@ -336,6 +336,37 @@ def test_gram_labels_tensor_core_vs_oracle(F, L, H, W):
     assert np.array_equal(G.cpu().numpy().reshape(R, R), X @ X.T)
 
 
+@pytest.mark.parametrize("F,L,H,W,band", [(40, 21, 48, 64, 5), (64, 30, 32, 64, 8), (30, 18, 32, 48, 0), (36, 21, 96, 128, 40), (50, 11, 32, 64, 3)])
+def test_gram_labels_banded_vs_oracle(F, L, H, W, band):
+    """north_star kernel 1, "all mask pairs within a frame window": the banded Gram form computes only the 256 x 256 blocks
+    whose frames lie within `band` of each other and returns the band layout [R][(2 band + 1) L]; every entry against the
+    oracle's dense contraction of the one-hot masks (pairs beyond the band are not part of the output at all)."""
+    import ctypes as C
+    from s2d_b200 import _lib
+    rng = np.random.default_rng(F * L + band)
+    blocks = rng.integers(0, L, size=(F, (H + 7) // 8, (W + 7) // 8)).astype(np.uint8)
+    labels = np.repeat(np.repeat(blocks, 8, axis=1), 8, axis=2)[:, :H, :W].copy()
+    labels[:, 0, :L] = np.arange(L, dtype=np.uint8)
+    R, Wb = F * L, (2 * band + 1) * L
+    d = _dev()
+    nw = C.c_int64()
+    _lib.call("s2d_overlap_gram_band_work_ints", F, L, H * W, band, C.byref(nw))
+    work = torch.empty(nw.value, dtype=torch.int32, device=d)
+    Gb = torch.full((R * Wb,), -1, dtype=torch.int32, device=d)
+    dlab = torch.from_numpy(labels).to(d)
+    _lib.call("s2d_overlap_gram_labels_banded", dlab.data_ptr(), F, L, H * W, band, work.data_ptr(), Gb.data_ptr(),
+              torch.cuda.current_stream(d).cuda_stream)
+    torch.cuda.synchronize()
+    X = (labels.reshape(F, 1, -1) == np.arange(L, dtype=np.uint8)[None, :, None]).reshape(R, -1)
+    full, _, _ = ko.overlap_counts(X, X)
+    want = np.zeros((R, Wb), np.int64)
+    for f in range(F):
+        for dd in range(-band, band + 1):
+            if 0 <= f + dd < F:
+                want[f * L:(f + 1) * L, (dd + band) * L:(dd + band + 1) * L] = full[f * L:(f + 1) * L, (f + dd) * L:(f + dd + 1) * L]
+    assert np.array_equal(Gb.cpu().numpy().reshape(R, Wb), want)
+
+
 def test_color_to_labels_vs_host_rule():
     """f1: colour PNG frames -> label ids on the GPU == rank of the RGB tuple among the non-black colours."""
     from s2d_b200.keymask_ident import _engine
