@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--list-scale", type=float, default=1.0, help="c3 / c4 / c5: scale frame size by this factor (smoke runs)")
     ap.add_argument("--hbm-budget-gb", type=float, default=110.0, help="c3 / c4 / c5: HBM per chunk of videos")
     ap.add_argument("--digest-file", default="", help="c3 / c4: JSON file with the digest of a reference run (any GPU count) to compare with")
+    ap.add_argument("--write-digest", default="", help="c3 / c4: JSON file that receives this run's digest (merged by workload key)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-queries", type=int, default=8, help="queries per step of the reference arm")
     ap.add_argument("--cpu-queries", type=int, default=48, help="queries in the cpu_baseline sample")
@@ -550,6 +551,13 @@ def list_workload(args):
             key = f"{args.workload}/{len(specs)}/{args.list_scale}/{args.point_order}"
             if key in dj:
                 ref_digest, equal = dj[key]["digest"], dj[key]["digest"] == digest
+        if args.write_digest:
+            dj = json.load(open(args.write_digest)) if os.path.exists(args.write_digest) else {}
+            dj[f"{args.workload}/{len(specs)}/{args.list_scale}/{args.point_order}"] = {
+                "digest": digest, "n_gpus": world, "videos": len(specs), "frames": frames,
+                "videos_ok": sum(1 for r in results if r["status"] == 1), "keymasks": sum(r["keymasks"] for r in results)}
+            with open(args.write_digest, "w") as f:
+                json.dump(dj, f, indent=1, sort_keys=True)
         loads = [sum(costs[i] for i in p) for p in parts]
         k2_gbs = tot[2] / (tot[1] / 1000.0) / 1e9 if tot[1] > 0 else 0.0
         line = {"metric": METRIC, "value": frames / total_s, "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": len(warm),

@@ -11,10 +11,21 @@ namespace s2d {
 constexpr int LH_THREADS = 256;
 constexpr int LH_BYTES_PER_CTA = 64 * 1024;
 
-__device__ __forceinline__ void hist_flush(int* wh, int cur, int cnt) {
-    if (cnt) atomicAdd(&wh[cur], cnt);
+// bit 7 of every byte of x that is non-zero
+__device__ __forceinline__ uint32_t lh_nz7(uint32_t x) { return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
+// number of the 16 bytes of w that equal the byte replicated in s4
+__device__ __forceinline__ int lh_count_eq(const int4 w, uint32_t s4) {
+    const uint32_t m = (lh_nz7((uint32_t)w.x ^ s4) >> 7) | (lh_nz7((uint32_t)w.y ^ s4) >> 6) |
+                       (lh_nz7((uint32_t)w.z ^ s4) >> 5) | (lh_nz7((uint32_t)w.w ^ s4) >> 4);
+    return 16 - __popc(m);
 }
 
+// Label maps are piecewise constant: a 16-byte vector almost always holds one label (a) or two runs (a ... a z ... z), and
+// the 32 vectors a warp reads side by side (512 consecutive pixels) mostly share them. Per warp step, branch-free: every
+// lane counts the bytes equal to its first (a) and to its last (z) byte; the lanes whose a equals lane 0's are summed with
+// one warp reduction and added by lane 0, the others add their own count, z likewise when the vector is not uniform.
+// Only a vector with three or more labels (c_a + c_z < 16, rare) is counted byte by byte. The round-1 kernel kept a
+// per-thread run and took a divergent per-byte path in every warp step that met an object border (ncu: 0.55 of HBM).
 __global__ void __launch_bounds__(LH_THREADS)
 label_hist_kernel(const s2d_video_desc* __restrict__ descs, int32_t* __restrict__ area) {
     const s2d_video_desc d = descs[blockIdx.z];
@@ -29,65 +40,52 @@ label_hist_kernel(const s2d_video_desc* __restrict__ descs, int32_t* __restrict_
     for (int i = threadIdx.x; i < (LH_THREADS / 32) * S2D_MAX_LABELS; i += LH_THREADS) (&wh[0][0])[i] = 0;
     __syncthreads();
     int* mywh = wh[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
 
     const uint8_t* base = d.labels + (int64_t)t * npix;
-    int cur = 0, cnt = 0;
-    // head: bytes until 16-byte alignment (thread 0 of the CTA handles them; at most 15)
+    // head / tail: bytes outside the 16-byte aligned body (thread 0 of the CTA; at most 15 each)
     const uintptr_t addr0 = (uintptr_t)(base + beg);
-    int64_t head = min((int64_t)((16 - (addr0 & 15)) & 15), end - beg);
+    const int64_t head = min((int64_t)((16 - (addr0 & 15)) & 15), end - beg);
     const int64_t vbeg = beg + head;
     const int64_t nvec = (end - vbeg) / 16;
     if (threadIdx.x == 0) {
-        for (int64_t i = beg; i < vbeg; ++i) {
-            int v = base[i];
-            if (v != cur) { hist_flush(mywh, cur, cnt); cur = v; cnt = 0; }
-            ++cnt;
-        }
-        for (int64_t i = vbeg + nvec * 16; i < end; ++i) {
-            int v = base[i];
-            if (v != cur) { hist_flush(mywh, cur, cnt); cur = v; cnt = 0; }
-            ++cnt;
-        }
+        for (int64_t i = beg; i < vbeg; ++i) atomicAdd(&mywh[base[i]], 1);
+        for (int64_t i = vbeg + nvec * 16; i < end; ++i) atomicAdd(&mywh[base[i]], 1);
     }
     const int4* vp = reinterpret_cast<const int4*>(base + vbeg);
-    // a thread's consecutive vectors are 4 KB apart, so the label it carries rarely matches the next vector: test the
-    // vector (then each word) for "one label throughout" against its own first byte, not against `cur`
-    auto eat = [&](const int4 w) {
-        const uint32_t ws[4] = {(uint32_t)w.x, (uint32_t)w.y, (uint32_t)w.z, (uint32_t)w.w};
-        const uint32_t s0 = __byte_perm(ws[0], 0, 0x0000);
-        if ((ws[0] == s0) & (ws[1] == s0) & (ws[2] == s0) & (ws[3] == s0)) {
-            const int v = (int)(s0 & 255u);
-            if (v != cur) { hist_flush(mywh, cur, cnt); cur = v; cnt = 0; }
-            cnt += 16;
-            return;
-        }
+    S2D_DEV_ASSERT(vbeg + nvec * 16 <= end && end <= npix);
+    auto eat = [&](const int4 w, bool valid) {                 // warp-uniform call; `valid` false: the lane has no vector
+        const uint32_t a = (uint32_t)w.x & 255u, z = (uint32_t)w.w >> 24;
+        const int ca = valid ? lh_count_eq(w, a * 0x01010101u) : 0;
+        const int cz = (valid && z != a) ? lh_count_eq(w, z * 0x01010101u) : 0;
+        const uint32_t a0 = __shfl_sync(0xffffffffu, a, 0);
+        const int sa = __reduce_add_sync(0xffffffffu, a == a0 ? ca : 0);
+        if (lane == 0) atomicAdd(&mywh[a0], sa);
+        else if (a != a0 && ca) atomicAdd(&mywh[a], ca);
+        if (cz) atomicAdd(&mywh[z], cz);
+        if (__any_sync(0xffffffffu, valid && ca + cz != 16)) {     // three or more labels in 16 pixels: byte by byte
+            if (valid && ca + cz != 16) {
+                const uint32_t ws[4] = {(uint32_t)w.x, (uint32_t)w.y, (uint32_t)w.z, (uint32_t)w.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t sk = __byte_perm(ws[k], 0, 0x0000);
-            if (ws[k] == sk) {
-                const int v = (int)(sk & 255u);
-                if (v != cur) { hist_flush(mywh, cur, cnt); cur = v; cnt = 0; }
-                cnt += 4;
-                continue;
-            }
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                int v = (ws[k] >> (8 * b)) & 255;
-                if (v != cur) { hist_flush(mywh, cur, cnt); cur = v; cnt = 0; }
-                ++cnt;
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t v = (ws[k >> 2] >> (8 * (k & 3))) & 255u;
+                    if (v != a && v != z) atomicAdd(&mywh[v], 1);
+                }
             }
         }
     };
-    // four independent 128-bit streaming loads in flight per thread, then the (divergent) run-length pass over them
+    // four independent 128-bit streaming loads in flight per thread
+    const int64_t nfull = nvec - nvec % (4 * LH_THREADS);
     int64_t i = threadIdx.x;
-    for (; i + 3 * LH_THREADS < nvec; i += 4 * LH_THREADS) {
+    for (; i < nfull; i += 4 * LH_THREADS) {
         const int4 w0 = ld_stream(vp + i), w1 = ld_stream(vp + i + LH_THREADS);
         const int4 w2 = ld_stream(vp + i + 2 * LH_THREADS), w3 = ld_stream(vp + i + 3 * LH_THREADS);
-        eat(w0); eat(w1); eat(w2); eat(w3);
+        eat(w0, true); eat(w1, true); eat(w2, true); eat(w3, true);
     }
-    S2D_DEV_ASSERT(vbeg + nvec * 16 <= end && end <= npix);
-    for (; i < nvec; i += LH_THREADS) eat(ld_stream(vp + i));
-    hist_flush(mywh, cur, cnt);
+    for (int64_t j = nfull + (threadIdx.x & ~31); j < nvec; j += LH_THREADS) {       // warp-uniform trip count
+        const bool valid = j + lane < nvec;
+        eat(valid ? ld_stream(vp + j + lane) : make_int4(0, 0, 0, 0), valid);
+    }
     __syncthreads();
     int32_t* out = area + (d.frame0 + t) * S2D_MAX_LABELS;
     for (int l = threadIdx.x; l < S2D_MAX_LABELS; l += LH_THREADS) {
