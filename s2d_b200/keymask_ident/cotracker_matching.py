@@ -474,12 +474,20 @@ def temporal_correspondence_match(video_path, mask_path, cluster_mask_path, visi
     pmax = max(int(t.shape[1]) for t in tracks_of.values())
     pmax += pmax % 2
     dev = labels_dev.device
-    tracks = torch.zeros((nm, T, pmax, 2), dtype=torch.float32, device=dev)
+    # windowed storage: only the frames of a query's window [v0, v1] are ever voted on, so only they are kept on the
+    # device (the reference holds one query's full-length tracks at a time; a dense [Nm, T, P, 2] tensor would be tens
+    # of GB for long, crowded videos). Rows that are not candidates own no tile and are never read.
+    ttr = max(int(rowinfo[g, 3] - rowinfo[g, 2] + 1) for g in tracks_of)
+    tstart = np.zeros(nm, np.int32)
+    tracks = torch.empty((nm, ttr, pmax, 2), dtype=torch.float32, device=dev)
     npts = torch.zeros(nm, dtype=torch.int32)
     for g, t in tracks_of.items():
-        tracks[g, :, : t.shape[1]] = t.to(dev, torch.float32)
+        ts = min(int(rowinfo[g, 2]), T - ttr)
+        tstart[g] = ts
+        tracks[g, :, : t.shape[1]] = t[ts:ts + ttr].to(dev, torch.float32)
         npts[g] = t.shape[1]
-    b = Batch([VideoInput(labels=labels_dev, tracks=tracks, npts=npts.to(dev))], stages="LD")
+    b = Batch([VideoInput(labels=labels_dev, tracks=tracks, npts=npts.to(dev), tstart=torch.from_numpy(tstart).to(dev))],
+              stages="LD")
     b.upload_stage_b(rowinfo, len(clusters), 1)
     b.run(Params(matching_threshold=matching_threshold))
     torch.cuda.synchronize(dev)
