@@ -533,7 +533,8 @@ def list_workload(args):
     t_part = time.perf_counter() - t_part0
     local = worker(mine)
     barrier()
-    clk = clocks.stop()
+    if world > 1:
+        dist.barrier(group=host_pg)                   # host-side rendezvous right before the timed exchange
     tg0 = time.perf_counter()
     if world > 1:
         gathered = [None] * world if rank == 0 else None
@@ -542,6 +543,7 @@ def list_workload(args):
     else:
         merged = sorted(zip(mine, local), key=lambda x: x[0])
     t_gather = time.perf_counter() - tg0
+    clk = clocks.stop()
     dev_ms = max_over_ranks(local_stats["device_ms"])
     sum_ms = torch.tensor([local_stats["device_ms"], local_stats["k2_ms"], float(local_stats["k2_bytes"]), float(local_stats["k2_tiles"]),
                            float(local_stats["launches"]), local_stats["vis_ms"], float(local_stats["vis_bytes"])], dtype=torch.float64, device=dev)
@@ -806,10 +808,29 @@ def run_e2e(args, vids, dev, world, params, barrier, binding):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
+    # what the platform gives a bare copy loop at this GPU count: the same pool, cudaMemcpyAsync only, all ranks at once
+    barrier()
+    probe_bytes, tp0 = 0, time.perf_counter()
+    dst = pipe.sets[0][0]
+    with torch.cuda.device(dev):
+        while time.perf_counter() - tp0 < 1.0:
+            for j in range(chunk):
+                dst[j].tracks.copy_(hv[j].tracks, non_blocking=True)
+                probe_bytes += hv[j].tracks.numel() * 4
+            torch.cuda.synchronize(dev)
+    tp = time.perf_counter() - tp0
+    barrier()
+    probe = torch.tensor([probe_bytes / tp / 1e9], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(probe, op=dist.ReduceOp.MIN)
     nchunks = nvid // chunk
     return {"value": nvid * T * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(pipe.h2d_bytes),
             "d2h_bytes_per_step": int(pipe.d2h_bytes), "steps": steps, "ms_per_step": 1000 * dt / steps,
-            "h2d_gbs_per_gpu": pipe.h2d_bytes * steps / dt / 1e9, "gpu_launches_per_step": pipe.launches,
+            "h2d_gbs_per_gpu": pipe.h2d_bytes * steps / dt / 1e9,
+            "h2d_probe_gbs_per_gpu": float(probe.item()),
+            "h2d_probe": "bare cudaMemcpyAsync loop over the same pinned pool, all ranks concurrently, min over ranks: the platform's "
+                         "host -> device ceiling at this GPU count",
+            "gpu_launches_per_step": pipe.launches,
             "wire_format": {"tracks": "f32 (x, y) as produced", "labels": "u8",
                             "visibility": "bit-packed u32 (S2D_DESC_VIS_BITS)" if bits else "u8 flags"},
             "host_pool": pool_desc, "cpu_binding": binding,
