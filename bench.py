@@ -319,7 +319,10 @@ def main():
     tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "k2_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if tj.get("workload") == args.workload and int(tj.get("videos", -1)) == nvid and tj.get("point_order") == args.point_order:
+        from s2d_b200 import _lib
+        # only a capture of THIS library revision on THIS workload counts; anything else reads as "not measured"
+        if (tj.get("workload") == args.workload and int(tj.get("videos", -1)) == nvid and tj.get("point_order") == args.point_order
+                and int(tj.get("lib_version", -1)) == int(_lib.load().s2d_version())):
             traffic = float(tj["dram_bytes_per_launch"])
     roofline = {"kernel": pv_name, "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

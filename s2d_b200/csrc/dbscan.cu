@@ -6,6 +6,8 @@
 
 #include <limits.h>
 
+#include <algorithm>
+
 namespace s2d {
 
 constexpr int DB_THREADS = 256;
@@ -44,15 +46,47 @@ __device__ __forceinline__ void csa(uint32_t& carry, uint32_t& sum, uint32_t a, 
     sum = u ^ c;
 }
 
-template <int MODE>   // 0: neighbour counts -> core   1: unions   2: border -> min core root
-__global__ void __launch_bounds__(DB_THREADS) db_pass_kernel(const DbProblem* __restrict__ problems) {
-    const DbProblem p = problems[blockIdx.y];
-    const int N = p.N;
-    const int i0 = blockIdx.x * DB_ROWS_I;
-    if (i0 >= N) return;
+// Work list of a batch of problems: wl[0 .. n] = exclusive prefix of the problems' 32-row blocks nb(p) = ceil(N / 32),
+// wl[n + 1 .. 2n + 1] = exclusive prefix of their block PAIRS nb (nb + 1) / 2. Most problems of a batch are empty (a
+// video has 16 cluster slots and uses one or two): the passes below run as persistent CTAs over the non-empty work only
+// instead of launching - and immediately retiring - a CTA per (problem, block) slot (round 1: 23 k CTAs per pass on the
+// C2 batch, 2 944 of them with work).
+__global__ void __launch_bounds__(1024) db_worklist_kernel(const DbProblem* __restrict__ problems, int n, int32_t* __restrict__ wl) {
+    __shared__ int ws0[32], ws1[32];
+    __shared__ int run0, run1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { run0 = 0; run1 = 0; }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int nb = i < n ? (problems[i].N + DB_ROWS_I - 1) / DB_ROWS_I : 0;
+        const int np = nb * (nb + 1) / 2;
+        int x0 = nb, x1 = np;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
+            if (lane >= o) { x0 += y0; x1 += y1; }
+        }
+        if (lane == 31) { ws0[warp] = x0; ws1[warp] = x1; }
+        __syncthreads();
+        int b0 = run0, b1 = run1, t0 = 0, t1 = 0;
+        for (int w = 0; w < 32; ++w) { if (w < warp) { b0 += ws0[w]; b1 += ws1[w]; } t0 += ws0[w]; t1 += ws1[w]; }
+        if (i < n) { wl[i] = b0 + x0 - nb; wl[n + 1 + i] = b1 + x1 - np; }
+        __syncthreads();
+        if (tid == 0) { run0 += t0; run1 += t1; }
+        __syncthreads();
+    }
+    if (tid == 0) { wl[n] = run0; wl[2 * n + 1] = run1; }
+}
 
-    __shared__ uint32_t xi[DB_ROWS_I][DB_NWC];
-    __shared__ uint32_t xjT[DB_NWC][32 * DB_JT + 1];
+// MODE 0: neighbour counts -> core   1: unions   2: border -> min core root. One work item = a 32-row block bi of a
+// problem (MODE 0, 2: against every row j) or a PAIR of blocks bi >= bj (MODE 1: the union-find is lock-free and
+// order-independent, so the pairs need no sequencing, and the critical path of the pass is one tile step instead of N / 32).
+template <int MODE>
+__device__ __forceinline__ void db_item(const DbProblem& p, int bi, int bj, uint32_t (&xi)[DB_ROWS_I][DB_NWC],
+                                        uint32_t (&xjT)[DB_NWC][32 * DB_JT + 1]) {
+    const int N = p.N;
+    const int i0 = bi * DB_ROWS_I;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int irow[4];
@@ -71,10 +105,12 @@ __global__ void __launch_bounds__(DB_THREADS) db_pass_kernel(const DbProblem* __
     }
     if (!__syncthreads_or(mine)) return;   // CTA-uniform: nothing to do for these 32 rows
 
-    const int jend = (MODE == 1) ? min(N, i0 + DB_ROWS_I) : N;   // unions only need j < i
-    const bool single_chunk = p.nw <= DB_NWC;
     constexpr int JROWS = 32 * DB_JT;            // rows j staged per round: DB_JT tiles of 32, one barrier pair for all
-    for (int j0 = 0; j0 < jend; j0 += JROWS) {
+    static_assert(DB_JT == 1, "MODE 1 assigns one 32-row block of j to a work item");
+    const int jbeg = (MODE == 1) ? bj * JROWS : 0;
+    const int jend = (MODE == 1) ? min(min(N, i0 + DB_ROWS_I), jbeg + JROWS) : N;   // unions only need j < i
+    const bool single_chunk = p.nw <= DB_NWC;
+    for (int j0 = jbeg; j0 < jend; j0 += JROWS) {
         int dist[DB_JT][4];
         uint32_t ones[DB_JT][4], twos[DB_JT][4];   // carry-save partial counts (weights 1 and 2)
 #pragma unroll
@@ -85,7 +121,7 @@ __global__ void __launch_bounds__(DB_THREADS) db_pass_kernel(const DbProblem* __
         for (int c0 = 0; c0 < p.nw; c0 += DB_NWC) {
             const int cw = min(DB_NWC, p.nw - c0);
             __syncthreads();
-            if (!(single_chunk && j0 > 0)) {
+            if (!(single_chunk && j0 > jbeg)) {
                 const int cwp = (cw + 3) & ~3;
                 for (int idx = tid; idx < DB_ROWS_I * cwp; idx += DB_THREADS) {
                     const int r = idx / cwp, w = idx - r * cwp, row = i0 + r;
@@ -182,6 +218,33 @@ __global__ void __launch_bounds__(DB_THREADS) db_pass_kernel(const DbProblem* __
     }
 }
 
+template <int MODE>
+__global__ void __launch_bounds__(DB_THREADS) db_pass_kernel(const DbProblem* __restrict__ problems, int n, const int32_t* __restrict__ wl) {
+    __shared__ uint32_t xi[DB_ROWS_I][DB_NWC];
+    __shared__ uint32_t xjT[DB_NWC][32 * DB_JT + 1];
+    const int32_t* pref = wl + (MODE == 1 ? n + 1 : 0);
+    const int total = pref[n];
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        int lo = 0, hi = n;                              // last problem with pref[pr] <= w (CTA-uniform)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(pref + mid) <= w) lo = mid; else hi = mid;
+        }
+        const DbProblem p = problems[lo];
+        int bi = w - __ldg(pref + lo), bj = 0;
+        if (MODE == 1) {
+            const int x = bi;
+            bi = (int)((sqrtf(8.0f * (float)x + 1.0f) - 1.0f) * 0.5f);
+            while ((bi + 1) * (bi + 2) / 2 <= x) ++bi;    // float rounding
+            while (bi * (bi + 1) / 2 > x) --bi;
+            bj = x - bi * (bi + 1) / 2;
+        }
+        S2D_DEV_ASSERT(bi * DB_ROWS_I < p.N && bj <= bi);
+        db_item<MODE>(p, bi, bj, xi, xjT);
+        __syncthreads();                                 // the next item restages xi / xjT
+    }
+}
+
 // cluster numbering by ascending root index + final labels; one CTA per problem
 __global__ void __launch_bounds__(1024) db_label_kernel(const DbProblem* __restrict__ problems) {
     const DbProblem p = problems[blockIdx.x];
@@ -220,15 +283,23 @@ __global__ void __launch_bounds__(1024) db_label_kernel(const DbProblem* __restr
     if (tid == 0 && p.nclusters) *p.nclusters = running;
 }
 
-int launch_dbscan(const DbProblem* problems, int nproblems, int max_N, int max_nw, cudaStream_t st) {
+int launch_dbscan(const DbProblem* problems, int nproblems, int max_N, int max_nw, int32_t* wl, cudaStream_t st) {
     (void)max_nw;
     if (nproblems <= 0 || max_N <= 0) return 0;
-    dim3 grid((max_N + DB_ROWS_I - 1) / DB_ROWS_I, nproblems);
-    db_pass_kernel<0><<<grid, DB_THREADS, 0, st>>>(problems);
+    db_worklist_kernel<<<1, 1024, 0, st>>>(problems, nproblems, wl);
+    S2D_CHECK_LAUNCH("db_worklist_kernel");
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t nb = (max_N + DB_ROWS_I - 1) / DB_ROWS_I;
+    const int64_t cap = (int64_t)nsm * (2048 / DB_THREADS);                      // resident CTAs
+    const unsigned g02 = (unsigned)std::min<int64_t>(cap, nb * nproblems);
+    const unsigned g1 = (unsigned)std::min<int64_t>(cap, nb * (nb + 1) / 2 * nproblems);
+    db_pass_kernel<0><<<g02, DB_THREADS, 0, st>>>(problems, nproblems, wl);
     S2D_CHECK_LAUNCH("db_pass_kernel<0>");
-    db_pass_kernel<1><<<grid, DB_THREADS, 0, st>>>(problems);
+    db_pass_kernel<1><<<g1, DB_THREADS, 0, st>>>(problems, nproblems, wl);
     S2D_CHECK_LAUNCH("db_pass_kernel<1>");
-    db_pass_kernel<2><<<grid, DB_THREADS, 0, st>>>(problems);
+    db_pass_kernel<2><<<g02, DB_THREADS, 0, st>>>(problems, nproblems, wl);
     S2D_CHECK_LAUNCH("db_pass_kernel<2>");
     db_label_kernel<<<nproblems, 1024, 0, st>>>(problems);
     S2D_CHECK_LAUNCH("db_label_kernel");
@@ -288,7 +359,7 @@ static_assert(sizeof(DbProblem) % 8 == 0, "DbProblem must keep 8-byte alignment 
 
 extern "C" int s2d_dbscan_work_ints(int64_t total_rows, int nproblems, int64_t* out) {
     if (!out) return -1;
-    *out = 3 * total_rows + 2 + (int64_t)nproblems * (int64_t)(sizeof(DbProblem) / 4);
+    *out = 3 * total_rows + 2 + (int64_t)nproblems * (int64_t)(sizeof(DbProblem) / 4) + db_worklist_ints(nproblems);
     return 0;
 }
 
@@ -308,7 +379,7 @@ extern "C" int s2d_dbscan_visibility(const s2d_video_desc* descs, int nvideos, i
     db1_setup_kernel<<<(nvideos + 127) / 128, 128, 0, st>>>(descs, nvideos, xbits, eps, min_samples, work,
                                                             labels1, vidinfo, problems);
     S2D_CHECK_LAUNCH("db1_setup_kernel");
-    return launch_dbscan(problems, nvideos, max_Nm, max_TW, st);
+    return launch_dbscan(problems, nvideos, max_Nm, max_TW, reinterpret_cast<int32_t*>(problems + nvideos), st);
 }
 
 extern "C" int s2d_hamming_dbscan(const uint32_t* bits, int N, int stride, int D, double eps,
@@ -323,5 +394,5 @@ extern "C" int s2d_hamming_dbscan(const uint32_t* bits, int N, int stride, int D
     S2D_CHECK_ARG((((uintptr_t)problems) & 7) == 0, "s2d_hamming_dbscan: work must be 8-byte aligned");
     db_single_setup_kernel<<<1, 1, 0, st>>>(bits, N, stride, D, eps, min_samples, work, labels, problems);
     S2D_CHECK_LAUNCH("db_single_setup_kernel");
-    return launch_dbscan(problems, 1, N, (D + 31) / 32, st);
+    return launch_dbscan(problems, 1, N, (D + 31) / 32, reinterpret_cast<int32_t*>(problems + 1), st);
 }

@@ -32,6 +32,8 @@ __device__ __forceinline__ int hamming_kmax(int D, double eps) {
 
 // launches the four phases for `nproblems` problems whose descriptors live in device memory;
 // max_N bounds every problem's N.
-int launch_dbscan(const DbProblem* problems, int nproblems, int max_N, int max_nw, cudaStream_t st);
+// `wl`: int32 scratch of db_worklist_ints(nproblems) elements (the passes' work list, built on the device).
+inline int64_t db_worklist_ints(int nproblems) { return 2 * ((int64_t)nproblems + 1) + 2; }
+int launch_dbscan(const DbProblem* problems, int nproblems, int max_N, int max_nw, int32_t* wl, cudaStream_t st);
 
 }  // namespace s2d

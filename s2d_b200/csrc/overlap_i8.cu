@@ -696,17 +696,23 @@ static void gram_plan(int R, int BN, int64_t npix, int* mt, int* nt, int* kblock
 
 // splits of the pixel range per block so that one wave of <= 148 CTAs finishes together: a diagonal block costs
 // G2_DIAG_COST of an off-diagonal one (it synthesises half the operand rows, but see the constant)
-constexpr double G2_DIAG_COST = 1.0;   // measured: the per-k-block latency chain, not the number of rows, sets the pace
+// measured (tools/r02_k1_diag.sh, C2 video): 1.0 -> 0.310 ms, 0.85 -> 0.303, 0.7 -> 0.279, 0.55 -> 0.288, 0.4 -> 0.356. A diagonal
+// block synthesises half the operand rows; with the cost at 1.0 its CTAs finished early and their SMs idled for a fifth of the kernel
+constexpr double G2_DIAG_COST = 0.7;
 static void gram2_plan(int R, int64_t npix, int* nt, int* kblocks, int* s_off, int* s_diag, int* per_off, int* per_diag, int* Rp) {
     *nt = (R + G2_BN - 1) / G2_BN;
     const int nd = *nt, no = *nt * (*nt - 1) / 2;
     *kblocks = (int)((npix + GM_BLOCK_K - 1) / GM_BLOCK_K);
     int best_o = no ? 1 : 0, best_d = 1;
     double best = 1e300;
+    double diag_cost = G2_DIAG_COST;
+#ifdef S2D_EXPERIMENTS
+    if (getenv("S2D_GRAM_DIAG_COST")) diag_cost = atof(getenv("S2D_GRAM_DIAG_COST"));
+#endif
     for (int sd = 1; sd <= 148; ++sd) {
         const int so = no ? (148 - nd * sd) / no : 0;
         if (no && so < 1) break;
-        const double t = std::max(no ? 1.0 / so : 0.0, G2_DIAG_COST / sd);       // time of the slowest CTA
+        const double t = std::max(no ? 1.0 / so : 0.0, diag_cost / sd);       // time of the slowest CTA
         if (t < best) { best = t; best_o = so; best_d = sd; }
     }
     if (best_d > *kblocks) best_d = *kblocks;

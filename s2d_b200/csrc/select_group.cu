@@ -292,7 +292,8 @@ extern "C" int s2d_select(const s2d_video_desc* descs, int nvideos, int max_Nm, 
 
 extern "C" int s2d_group_work_ints(int64_t total_rows, int nvideos, int64_t* out) {
     if (!out) return -1;
-    *out = 5 * 16 * total_rows + 2 + (int64_t)nvideos * S2D_MAX_CLUSTERS * (int64_t)(sizeof(DbProblem) / 4);
+    *out = 5 * 16 * total_rows + 2 + (int64_t)nvideos * S2D_MAX_CLUSTERS * (int64_t)(sizeof(DbProblem) / 4) +
+           db_worklist_ints(nvideos * S2D_MAX_CLUSTERS);
     return 0;
 }
 
@@ -315,7 +316,8 @@ extern "C" int s2d_group(const s2d_video_desc* descs, int nvideos, int max_Nm, i
     dim3 grid(S2D_MAX_CLUSTERS, nvideos);
     group_prep_kernel<<<grid, GP_THREADS, 0, st>>>(descs, mbits, rowinfo, work, vidinfo, clusterinfo, problems);
     S2D_CHECK_LAUNCH("group_prep_kernel");
-    int rc = launch_dbscan(problems, nvideos * S2D_MAX_CLUSTERS, max_Nm, max_NW, st);
+    int rc = launch_dbscan(problems, nvideos * S2D_MAX_CLUSTERS, max_Nm, max_NW,
+                           reinterpret_cast<int32_t*>(problems + (int64_t)nvideos * S2D_MAX_CLUSTERS), st);
     if (rc) return rc;
     group_finalize_kernel<<<grid, GP_THREADS, 0, st>>>(descs, mbits, rowinfo, one2x, work, glabel, grp_n,
                                                       grp_one2x, clusterinfo, vidinfo);

@@ -49,3 +49,19 @@ def test_reference_arm_ignores_torchrun_thread_cap():
     # both arms print the same `config` (bench.make_config)
     assert set(d["config"]) == {"workload", "videos_per_gpu", "frames_per_video", "resolution", "masks_per_frame",
                                 "tracks_per_query", "queries_per_video", "point_order", "partition", "cache"}
+
+
+def test_reference_arm_of_a_list_workload():
+    """--impl reference --workload c4: the CPU port on one query of a few videos of the list (down-scaled here), same
+    contract line, strong scaling."""
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c4", "--list-videos", "4",
+                        "--list-scale", "0.1", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["impl"] == "reference" and d["scaling"] == "strong" and d["value"] > 0
+    assert d["config"]["workload"].startswith("c4") and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]

@@ -18,7 +18,7 @@ PY
 done
 # launch list of one step (4 videos), then full captures of K2 on the whole C2 batch (DRAM traffic of the benchmarked launch),
 # of the label histogram and of the Gram kernel
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/r02_launches.csv -c 400 python bench.py --videos 4 --steps 2 --warmup 1 --no-e2e --no-cpu --no-k1 > $out/ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/r02_launches.csv -k regex:"label_hist|frame_tables|vis_reduce|binarize|db_|db1_|cluster_count|windows_kernel|pv_|point_votes|select_kernel|group_|video_status" -c 400 python bench.py --videos 4 --steps 2 --warmup 1 --no-e2e --no-cpu --no-k1 > $out/ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:point_votes_tab -s 3 -c 1 -f -o $out/r02_pv_v16_c2full python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-k1 > $out/ncu_pv16.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:label_hist -s 1 -c 1 -f -o $out/r02_label_hist python bench.py --videos 16 --steps 1 --warmup 3 --no-e2e --no-cpu --no-k1 > $out/ncu_lh.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gram_labels2 -c 1 -f -o $out/r02_gram_v6 python tools/k1_one.py > $out/ncu_gram6.log 2>&1
