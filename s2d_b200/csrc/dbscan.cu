@@ -80,8 +80,10 @@ __global__ void __launch_bounds__(1024) db_worklist_kernel(const DbProblem* __re
 }
 
 // MODE 0: neighbour counts -> core   1: unions   2: border -> min core root. One work item = a 32-row block bi of a
-// problem (MODE 0, 2: against every row j) or a PAIR of blocks bi >= bj (MODE 1: the union-find is lock-free and
-// order-independent, so the pairs need no sequencing, and the critical path of the pass is one tile step instead of N / 32).
+// problem against every row j (MODE 1: every row j < i). Measured and rejected: one item per PAIR of blocks in MODE 1
+// (critical path of one tile step instead of N / 32) - a block that walks its j tiles in turn remembers which rows it
+// already united (imember) and issues ~N unions per problem; independent pairs issue one per neighbouring pair of rows
+// (~20 x more atomicCAS / find chains): dbscan1 0.17 -> 0.31 ms, group 0.64 -> 0.95 ms on the C2 batch.
 template <int MODE>
 __device__ __forceinline__ void db_item(const DbProblem& p, int bi, int bj, uint32_t (&xi)[DB_ROWS_I][DB_NWC],
                                         uint32_t (&xjT)[DB_NWC][32 * DB_JT + 1]) {
@@ -106,9 +108,9 @@ __device__ __forceinline__ void db_item(const DbProblem& p, int bi, int bj, uint
     if (!__syncthreads_or(mine)) return;   // CTA-uniform: nothing to do for these 32 rows
 
     constexpr int JROWS = 32 * DB_JT;            // rows j staged per round: DB_JT tiles of 32, one barrier pair for all
-    static_assert(DB_JT == 1, "MODE 1 assigns one 32-row block of j to a work item");
-    const int jbeg = (MODE == 1) ? bj * JROWS : 0;
-    const int jend = (MODE == 1) ? min(min(N, i0 + DB_ROWS_I), jbeg + JROWS) : N;   // unions only need j < i
+    const int jbeg = 0;
+    (void)bj;
+    const int jend = (MODE == 1) ? min(N, i0 + DB_ROWS_I) : N;   // unions only need j < i
     const bool single_chunk = p.nw <= DB_NWC;
     for (int j0 = jbeg; j0 < jend; j0 += JROWS) {
         int dist[DB_JT][4];
@@ -222,7 +224,7 @@ template <int MODE>
 __global__ void __launch_bounds__(DB_THREADS) db_pass_kernel(const DbProblem* __restrict__ problems, int n, const int32_t* __restrict__ wl) {
     __shared__ uint32_t xi[DB_ROWS_I][DB_NWC];
     __shared__ uint32_t xjT[DB_NWC][32 * DB_JT + 1];
-    const int32_t* pref = wl + (MODE == 1 ? n + 1 : 0);
+    const int32_t* pref = wl;
     const int total = pref[n];
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
         int lo = 0, hi = n;                              // last problem with pref[pr] <= w (CTA-uniform)
@@ -231,15 +233,8 @@ __global__ void __launch_bounds__(DB_THREADS) db_pass_kernel(const DbProblem* __
             if (__ldg(pref + mid) <= w) lo = mid; else hi = mid;
         }
         const DbProblem p = problems[lo];
-        int bi = w - __ldg(pref + lo), bj = 0;
-        if (MODE == 1) {
-            const int x = bi;
-            bi = (int)((sqrtf(8.0f * (float)x + 1.0f) - 1.0f) * 0.5f);
-            while ((bi + 1) * (bi + 2) / 2 <= x) ++bi;    // float rounding
-            while (bi * (bi + 1) / 2 > x) --bi;
-            bj = x - bi * (bi + 1) / 2;
-        }
-        S2D_DEV_ASSERT(bi * DB_ROWS_I < p.N && bj <= bi);
+        const int bi = w - __ldg(pref + lo), bj = 0;
+        S2D_DEV_ASSERT(bi * DB_ROWS_I < p.N);
         db_item<MODE>(p, bi, bj, xi, xjT);
         __syncthreads();                                 // the next item restages xi / xjT
     }
@@ -294,10 +289,9 @@ int launch_dbscan(const DbProblem* problems, int nproblems, int max_N, int max_n
     const int64_t nb = (max_N + DB_ROWS_I - 1) / DB_ROWS_I;
     const int64_t cap = (int64_t)nsm * (2048 / DB_THREADS);                      // resident CTAs
     const unsigned g02 = (unsigned)std::min<int64_t>(cap, nb * nproblems);
-    const unsigned g1 = (unsigned)std::min<int64_t>(cap, nb * (nb + 1) / 2 * nproblems);
     db_pass_kernel<0><<<g02, DB_THREADS, 0, st>>>(problems, nproblems, wl);
     S2D_CHECK_LAUNCH("db_pass_kernel<0>");
-    db_pass_kernel<1><<<g1, DB_THREADS, 0, st>>>(problems, nproblems, wl);
+    db_pass_kernel<1><<<g02, DB_THREADS, 0, st>>>(problems, nproblems, wl);
     S2D_CHECK_LAUNCH("db_pass_kernel<1>");
     db_pass_kernel<2><<<g02, DB_THREADS, 0, st>>>(problems, nproblems, wl);
     S2D_CHECK_LAUNCH("db_pass_kernel<2>");

@@ -607,14 +607,17 @@ constexpr uint32_t PV_PK_INVALID = 0xFFFFFFFFu;
 //                        phase A has read this tile's, i.e. during the table fetch and phase B)
 //   [.., +BUF + 64)      the buffer: the tile's tracks (not SPLIT), then its label table (+ 64 B slack for row copies)
 constexpr int PV_FIXED_BYTES = 1664;
-__host__ __device__ constexpr int pv_buf_bytes(int threads, int ppt, int ctas, bool split) {
+// `nch`: a tile's tracks arrive in nch chunks through a ring of TWO chunk slots at the start of the buffer (nch = 2: the
+// whole tile is resident, as for 4096-point tiles; nch = 4: 128 KB tiles stream through 64 KB, so two CTAs fit an SM)
+__host__ __device__ constexpr int pv_buf_bytes(int threads, int ppt, int ctas, bool split, int nch = 2) {
     // 228 KB per SM, 1 KB reserved by the system per CTA
     const int avail = 233472 / ctas - 1024 - PV_FIXED_BYTES - 64 - (split ? threads * ppt * 8 : 0);
     const int cap = (avail / 128) * 128;
-    return (!split && cap < threads * ppt * 8) ? threads * ppt * 8 : cap;
+    const int ring = threads * ppt * 8 * 2 / nch;
+    return (!split && cap < ring) ? ring : cap;
 }
-__host__ __device__ constexpr int pv_smem_bytes(int threads, int ppt, int ctas, bool split) {
-    return PV_FIXED_BYTES + (split ? threads * ppt * 8 : 0) + pv_buf_bytes(threads, ppt, ctas, split) + 64;
+__host__ __device__ constexpr int pv_smem_bytes(int threads, int ppt, int ctas, bool split, int nch = 2) {
+    return PV_FIXED_BYTES + (split ? threads * ppt * 8 : 0) + pv_buf_bytes(threads, ppt, ctas, split, nch) + 64;
 }
 
 // (iy << 16 | ix) of a point that lands inside the frame, PV_PK_INVALID otherwise (W, H <= 65535)
@@ -732,12 +735,15 @@ struct PvCtl {
 };
 static_assert(sizeof(PvCtl) <= 512, "PvCtl must fit its slot of the shared-memory layout");
 
-template <int THREADS, int PPT, int CTAS, bool SPLIT>
+template <int THREADS, int PPT, int CTAS, bool SPLIT, int NCH>
 __global__ void __launch_bounds__(THREADS, CTAS)
 point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __restrict__ rowplan,
                        int total_rows, int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
                        int32_t* __restrict__ uniq, const uint8_t* __restrict__ tmaps) {
-    constexpr int BUF_BYTES = pv_buf_bytes(THREADS, PPT, CTAS, SPLIT);
+    constexpr int BUF_BYTES = pv_buf_bytes(THREADS, PPT, CTAS, SPLIT, NCH);
+    constexpr int SLOT_BYTES = THREADS * PPT * 8 / NCH;          // one chunk of a tile's tracks
+    constexpr int KCH = PPT / 2 / NCH;                           // 16-byte point pairs of a thread per chunk
+    static_assert(NCH >= 2 && NCH % 2 == 0 && PPT % (2 * NCH) == 0 && (!SPLIT || NCH == 2), "chunking of the tracks");
     constexpr int TRK_BYTES = SPLIT ? THREADS * PPT * 8 : 0;
     constexpr int NWARPS = THREADS / 32;
     static_assert(NWARPS <= 16, "PvCtl::wred");
@@ -789,14 +795,18 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
         if (lane == 0) { plan_s = pl; nsrc_s = src; more_s = ok ? 1 : 0; }
     };
     // tracks of the planned tile -> buffer, as two bulk copies on two mbarriers (the halves of the k loop of phase A)
+    // chunk c of a tile (P points at src) -> ring slot c & 1, completion on that slot's mbarrier (full / full2)
+    auto issue_chunk = [&](const float* src, int P, int c) {
+        const uint32_t bytes = (uint32_t)P * 8u, off = (uint32_t)c * SLOT_BYTES;
+        const uint32_t nb = bytes > off ? min(bytes - off, (uint32_t)SLOT_BYTES) : 0u;
+        uint64_t* bar = (c & 1) ? &full2 : &full;
+        mbar_expect_tx(bar, nb);
+        if (nb) bulk_g2s_hint(trk + (c & 1) * SLOT_BYTES, reinterpret_cast<const uint8_t*>(src) + off, nb, bar, l2_policy_evict_first());
+    };
+    // the first two chunks of the planned tile (NCH = 2: the whole tile, in two halves: phase A starts on the first)
     auto issue_tracks = [&](int P) {
-        const uint32_t bytes = (uint32_t)P * 8u;
-        const uint32_t b1 = min(bytes, (uint32_t)(THREADS * PPT * 4));
-        const uint64_t pol = l2_policy_evict_first();
-        mbar_expect_tx(&full, b1);
-        bulk_g2s_hint(trk, nsrc_s, b1, &full, pol);
-        mbar_expect_tx(&full2, bytes - b1);
-        if (bytes > b1) bulk_g2s_hint(trk + b1, reinterpret_cast<const uint8_t*>(nsrc_s) + b1, bytes - b1, &full2, pol);
+        issue_chunk(nsrc_s, P, 0);
+        issue_chunk(nsrc_s, P, 1);
     };
     if (warp == 0) {
         plan(&tinfo[0]);
@@ -815,39 +825,41 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     for (int j = 0;; ++j) {
         const PvTile* ti = &tinfo[scur];
         if (!ti->valid) break;                        // written before the barrier that precedes this read
-        if (warp == 0) mbar_wait(&full, j & 1);       // one warp polls the mbarrier, the rest park at the hardware barrier
-        __syncthreads();
         const uint32_t W = ti->W, H = ti->H;
         if (W > 65535u || H > 65535u) __trap();      // packed 16-bit coordinates (documented limit)
         const int n = ti->n;
 
-        // ---- phase A: buffer -> registers, round / bounds / pack, bounding box ----------------
+        // ---- phase A: ring slots -> registers, round / bounds / pack, bounding box ----------------
         uint32_t pk[PPT];
         uint32_t mn = 0xFFFFFFFFu, mx = 0;
-        const float4* sp = reinterpret_cast<const float4*>(trk);
-        auto point_pair = [&](int k) -> float4 { return sp[k * THREADS + tid]; };
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            if (half == 1) {                          // second half of the tracks
-                if (warp == 0) mbar_wait(&full2, j & 1);
-                __syncthreads();
-            }
+        for (int c = 0; c < NCH; ++c) {
+            // slot c & 1 completes NCH / 2 times per tile; one warp polls the mbarrier, the rest park at the hardware barrier
+            if (warp == 0) mbar_wait((c & 1) ? &full2 : &full, (uint32_t)(j * (NCH / 2) + (c >> 1)) & 1u);
+            __syncthreads();
+            const float4* sp = reinterpret_cast<const float4*>(trk + (c & 1) * SLOT_BYTES);
             if (n >= THREADS * PPT) {
 #pragma unroll
-                for (int k = half * (PPT / 4); k < (half + 1) * (PPT / 4); ++k) {
-                    const float4 v = point_pair(k);
+                for (int kk = 0; kk < KCH; ++kk) {
+                    const int k = c * KCH + kk;
+                    const float4 v = sp[kk * THREADS + tid];
                     pk[2 * k] = pv_pack(v.x, v.y, W, H);
                     pk[2 * k + 1] = pv_pack(v.z, v.w, W, H);
                 }
             } else {
 #pragma unroll
-                for (int k = half * (PPT / 4); k < (half + 1) * (PPT / 4); ++k) {
-                    const float4 v = point_pair(k);
+                for (int kk = 0; kk < KCH; ++kk) {
+                    const int k = c * KCH + kk;
+                    const float4 v = sp[kk * THREADS + tid];
                     const int p0 = 2 * (k * THREADS + tid);
                     const uint32_t a = pv_pack(v.x, v.y, W, H), b = pv_pack(v.z, v.w, W, H);
                     pk[2 * k] = (p0 < n) ? a : PV_PK_INVALID;
                     pk[2 * k + 1] = (p0 + 1 < n) ? b : PV_PK_INVALID;
                 }
+            }
+            if (c + 2 < NCH) {                        // the slot is free once everybody has read it: chunk c + 2 streams in
+                __syncthreads();
+                if (tid == 0) issue_chunk(ti->src, ti->pad, c + 2);
             }
         }
 #pragma unroll
@@ -1034,11 +1046,11 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     }
 }
 
-template <int THREADS, int PPT, int CTAS, bool SPLIT = false>
+template <int THREADS, int PPT, int CTAS, bool SPLIT = false, int NCH = 2>
 static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, const int4* rowplan,
                          int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq, const uint8_t* tmaps) {
-    const int smem = pv_smem_bytes(THREADS, PPT, CTAS, SPLIT);
-    auto kfn = point_votes_tab_kernel<THREADS, PPT, CTAS, SPLIT>;
+    const int smem = pv_smem_bytes(THREADS, PPT, CTAS, SPLIT, NCH);
+    auto kfn = point_votes_tab_kernel<THREADS, PPT, CTAS, SPLIT, NCH>;
     static bool configured[S2D_MAX_DEVICES] = {};
     {
         cudaError_t e = opt_in_smem(kfn, smem, configured);
@@ -1205,7 +1217,12 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
 #endif
             if (max_P <= 128 * 32) return launch_pv_tab<128, 32, 6>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
             if (max_P <= 256 * 32) return launch_pv_tab<256, 32, 3>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-            return launch_pv_tab<512, 32, 1>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);     // 128 KB tiles: one CTA per SM
+#ifdef S2D_EXPERIMENTS
+            if (getenv("S2D_PV_BIG") && atoi(getenv("S2D_PV_BIG")) == 1)
+                return launch_pv_tab<512, 32, 1>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);     // round 1: 128 KB tiles resident, one CTA per SM
+#endif
+            // 128 KB tiles stream through a ring of two 32 KB slots: two CTAs of 256 threads per SM
+            return launch_pv_tab<256, 64, 2, false, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
         }
 #ifdef S2D_EXPERIMENTS
         if (max_P <= 256 * 4) return launch_pv_tma<256, 4>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);   // 4 CTAs/SM

@@ -74,7 +74,8 @@ def pv_variant(request):
     _lib.call("s2d_point_votes_variant", 0)
 
 
-@pytest.mark.parametrize("P,H,W", [(1000, 480, 854), (4096, 720, 1280), (777, 33, 1900), (8192, 1080, 1920), (20000, 64, 64)])
+@pytest.mark.parametrize("P,H,W", [(1000, 480, 854), (4096, 720, 1280), (777, 33, 1900), (8192, 1080, 1920), (20000, 64, 64),
+                                   (16384, 480, 854), (12002, 300, 500), (2048, 96, 1280)])
 def test_point_votes_shapes_and_bands(P, H, W, pv_variant):
     """odd P (no 128-bit path), P above the register tile, bounding boxes that need several
     bitmap bands (points spread over the whole 1080p frame), heavy duplication (P >> H*W)."""
