@@ -234,6 +234,16 @@ int s2d_group(const s2d_video_desc* descs, int nvideos, int max_Nm, int max_NW, 
               int32_t* glabel, int32_t* grp_n, int32_t* grp_one2x, int32_t* vidinfo,
               int32_t* clusterinfo, void* stream);
 
+/* The same with the pairwise distances of large problems taken from a Gram matrix computed on the tensor cores: for a
+ * video v with gram_off[v] >= 0, gram + gram_off[v] is G = X X^T (int32 [Nm][Nm]) of the video's match rows as 0/1 vectors
+ * (s2d_unpack_bits + s2d_overlap_i8 on mbits), and DBSCAN #2 uses dist(a, b) = G[a][a] + G[b][b] - 2 G[a][b] instead of
+ * XOR + popc over the bit rows - O(Nm^2) reads instead of O(Nm^3 / 32) bit operations (a 300-frame video has Nm = 9 000
+ * rows). gram_off: DEVICE int64 [nvideos], -1 = no Gram for that video; gram / gram_off NULL = s2d_group. Same results. */
+int s2d_group_gram(const s2d_video_desc* descs, int nvideos, int max_Nm, int max_NW, int64_t total_rows,
+                   const uint32_t* mbits, const int32_t* rowinfo, const int32_t* one2x, int32_t* work,
+                   int32_t* glabel, int32_t* grp_n, int32_t* grp_one2x, int32_t* vidinfo,
+                   int32_t* clusterinfo, const int32_t* gram, const int64_t* gram_off, void* stream);
+
 /* Generic Hamming DBSCAN on one bit matrix (device), N rows of `stride` words, D columns
  * (padding bits must be zero). work: s2d_dbscan_work_ints(N, 1) int32, 8-byte aligned. */
 int s2d_hamming_dbscan(const uint32_t* bits, int N, int stride, int D, double eps,
@@ -245,6 +255,8 @@ int s2d_hamming_dbscan(const uint32_t* bits, int N, int stride, int D, double ep
  * _bits: operands bit-packed ([N][ceil(npix/32)] u32), AND + popc on CUDA cores.
  * _i8  : operands u8 0/1 ([N][npix]), tcgen05.mma kind::i8, int32 accumulators in TMEM. */
 int s2d_pack_bits(const uint8_t* planes, int N, int64_t npix, uint32_t* bits, void* stream);
+/* inverse: bit rows [N][stride_words] -> u8 0/1 planes [N][ncols] (ncols % 16 == 0; columns beyond the words are 0) */
+int s2d_unpack_bits(const uint32_t* bits, int N, int stride_words, int64_t ncols, uint8_t* planes, void* stream);
 int s2d_overlap_bits(const uint32_t* Abits, int Na, const uint32_t* Bbits, int Nb, int64_t nwords,
                      int32_t* I, int32_t* areaA, int32_t* areaB, void* stream);
 

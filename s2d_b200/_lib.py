@@ -61,6 +61,8 @@ SIGNATURES = {
     "s2d_select": [_P, _I, _I, _L, _P, _P, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P],
     "s2d_group_work_ints": [_L, _I, C.POINTER(C.c_int64)],
     "s2d_group": [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "s2d_group_gram": [_P, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "s2d_unpack_bits": [_P, _I, _I, _L, _P, _P],
     "s2d_hamming_dbscan": [_P, _I, _I, _I, _D, _I, _P, _P, _P],
     "s2d_pack_bits": [_P, _I, _L, _P, _P],
     "s2d_overlap_bits": [_P, _I, _P, _I, _L, _P, _P, _P, _P],

@@ -112,6 +112,17 @@ __device__ __forceinline__ void db_item(const DbProblem& p, int bi, int bj, uint
     (void)bj;
     const int jend = (MODE == 1) ? min(N, i0 + DB_ROWS_I) : N;   // unions only need j < i
     const bool single_chunk = p.nw <= DB_NWC;
+    // Gram mode (large problems): the caller computed G = X X^T of the 0/1 rows on the tensor cores; the Hamming distance
+    // of two rows is |a| + |b| - 2 a.b with |a| = G[a][a]; rows that are not valid are all-zero rows
+    int ipop[4] = {0, 0, 0, 0};
+    bool ival[4] = {false, false, false, false};
+    if (p.gram) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            ival[r] = irow[r] < N && (!p.valid || p.valid[irow[r]]);
+            ipop[r] = ival[r] ? p.gram[(int64_t)irow[r] * p.gstride + irow[r]] : 0;
+        }
+    }
     for (int j0 = jbeg; j0 < jend; j0 += JROWS) {
         int dist[DB_JT][4];
         uint32_t ones[DB_JT][4], twos[DB_JT][4];   // carry-save partial counts (weights 1 and 2)
@@ -120,6 +131,16 @@ __device__ __forceinline__ void db_item(const DbProblem& p, int bi, int bj, uint
 #pragma unroll
             for (int r = 0; r < 4; ++r) { dist[jt][r] = 0; ones[jt][r] = 0; twos[jt][r] = 0; }
         const int jrows = min(JROWS, ((jend - j0 + 31) >> 5) << 5);
+        if (p.gram) {
+            const int j = j0 + lane;
+            const bool vj = j < N && (!p.valid || p.valid[j]);
+            const int jpop = vj ? p.gram[(int64_t)j * p.gstride + j] : 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int g = (ival[r] && vj) ? p.gram[(int64_t)irow[r] * p.gstride + j] : 0;
+                dist[0][r] = ipop[r] + jpop - 2 * g;
+            }
+        } else {
         for (int c0 = 0; c0 < p.nw; c0 += DB_NWC) {
             const int cw = min(DB_NWC, p.nw - c0);
             __syncthreads();
@@ -170,6 +191,7 @@ __device__ __forceinline__ void db_item(const DbProblem& p, int bi, int bj, uint
         for (int jt = 0; jt < DB_JT; ++jt)
 #pragma unroll
             for (int r = 0; r < 4; ++r) dist[jt][r] = 4 * dist[jt][r] + 2 * __popc(twos[jt][r]) + __popc(ones[jt][r]);
+        }
 #pragma unroll
         for (int jt = 0; jt < DB_JT; ++jt) {
             if (jt * 32 >= jrows) break;
@@ -315,6 +337,7 @@ __global__ void db1_setup_kernel(const s2d_video_desc* __restrict__ descs, int n
     p.parent = p.core + d.Nm;
     p.aux = p.parent + d.Nm;
     p.labels = labels1 + d.row0;
+    p.gram = nullptr; p.gstride = 0; p.pad = 0;
     p.nclusters = vidinfo + (int64_t)v * S2D_VIDINFO_WORDS + 0;
     p.stride = d.TW;
     p.w0 = 0;
@@ -335,6 +358,7 @@ __global__ void db_single_setup_kernel(const uint32_t* bits, int N, int stride, 
     p.parent = work + N;
     p.aux = work + 2 * N;
     p.labels = labels;
+    p.gram = nullptr; p.gstride = 0; p.pad = 0;
     p.nclusters = nullptr;
     p.stride = stride;
     p.w0 = 0;

@@ -14,6 +14,8 @@ struct DbProblem {
     int32_t* aux;           // work [N]
     int32_t* labels;        // out  [N]
     int32_t* nclusters;     // out  (optional)
+    const int32_t* gram;    // optional: G = X X^T of the rows (row 0 of the problem at gram[0], pitch gstride); distances
+    int32_t gstride, pad;   //           then come from G instead of XOR + popc over the bit rows
     int32_t stride;         // words per row
     int32_t w0, nw;         // word window compared
     int32_t N;

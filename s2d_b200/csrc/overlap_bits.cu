@@ -32,6 +32,23 @@ __global__ void pack_bits_kernel(const uint8_t* __restrict__ planes, int64_t nwo
     bits[w] = m;
 }
 
+// ---- unpack: bit rows -> u8 0/1 planes (the tensor-core operand of a Gram over bit rows); one thread per 16 output bytes
+__global__ void unpack_bits_kernel(const uint32_t* __restrict__ bits, int N, int stride, int64_t ncols, uint8_t* __restrict__ planes) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per_row = ncols / 16;
+    if (i >= (int64_t)N * per_row) return;
+    const int64_t row = i / per_row, c16 = i - row * per_row;
+    const int64_t w = c16 >> 1;
+    uint32_t m = w < stride ? bits[row * stride + w] : 0u;
+    m = (c16 & 1) ? (m >> 16) : m;
+    uint4 o;
+    o.x = ((m & 0xFu) * 0x00204081u) & 0x01010101u;
+    o.y = (((m >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+    o.z = (((m >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+    o.w = (((m >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+    reinterpret_cast<uint4*>(planes + row * ncols)[c16] = o;
+}
+
 // ---- rasterise: one CTA per frame, scatter 1s (duplicates collapse) ------------------------
 __global__ void rasterise_kernel(const float* __restrict__ tracks, int P, int H, int W,
                                  uint8_t* __restrict__ planes) {
@@ -105,6 +122,16 @@ extern "C" int s2d_pack_bits(const uint8_t* planes, int N, int64_t npix, uint32_
     const int64_t wpr = (npix + 31) / 32, total = wpr * N;
     pack_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(planes, total, npix, wpr, bits);
     S2D_CHECK_LAUNCH("pack_bits_kernel");
+    return 0;
+}
+
+extern "C" int s2d_unpack_bits(const uint32_t* bits, int N, int stride_words, int64_t ncols, uint8_t* planes, void* stream) {
+    S2D_ENTER(stream);
+    S2D_CHECK_ARG(bits && planes && N > 0 && stride_words > 0 && ncols > 0 && ncols % 16 == 0 && (((uintptr_t)planes) & 15) == 0,
+                  "s2d_unpack_bits: bad arguments (ncols must be a multiple of 16, planes 16-byte aligned)");
+    const int64_t n = (int64_t)N * (ncols / 16);
+    unpack_bits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bits, N, stride_words, ncols, planes);
+    S2D_CHECK_LAUNCH("unpack_bits_kernel");
     return 0;
 }
 

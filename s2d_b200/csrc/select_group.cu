@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(GP_THREADS)
 group_prep_kernel(const s2d_video_desc* __restrict__ descs, const uint32_t* __restrict__ mbits,
                   const int32_t* __restrict__ rowinfo, int32_t* __restrict__ work,
                   int32_t* __restrict__ vidinfo, int32_t* __restrict__ clusterinfo,
-                  DbProblem* __restrict__ problems) {
+                  DbProblem* __restrict__ problems, const int32_t* __restrict__ gram, const int64_t* __restrict__ gram_off) {
     const int v = blockIdx.y, c = blockIdx.x;
     const s2d_video_desc d = descs[v];
     const int32_t* vi = vidinfo + (int64_t)v * S2D_VIDINFO_WORDS;
@@ -176,6 +176,7 @@ group_prep_kernel(const s2d_video_desc* __restrict__ descs, const uint32_t* __re
         DbProblem p;
         p.bits = nullptr; p.valid = nullptr; p.core = base; p.parent = base + d.Nm; p.aux = base + 2 * (int64_t)d.Nm;
         p.labels = base + 3 * (int64_t)d.Nm; p.nclusters = nullptr;
+        p.gram = nullptr; p.gstride = 0; p.pad = 0;
         p.stride = d.NW; p.w0 = 0; p.nw = 0; p.N = 0; p.kmax = 0; p.min_samples = 1;
         ci[5] = -1; ci[6] = -1; ci[7] = -1; ci[8] = -1; ci[9] = 0; ci[10] = 0;
         if (active && rmax >= 0) {
@@ -187,6 +188,10 @@ group_prep_kernel(const s2d_video_desc* __restrict__ descs, const uint32_t* __re
             p.bits = mbits + d.mbits_off + (int64_t)rmin * d.NW;
             p.valid = valid + rmin;
             p.core += rmin; p.parent += rmin; p.aux += rmin; p.labels += rmin;   // keep absolute row indexing
+            if (gram && gram_off && gram_off[v] >= 0) {      // the video's Gram matrix [Nm][Nm] of its match rows
+                p.gram = gram + gram_off[v] + (int64_t)rmin * d.Nm + rmin;
+                p.gstride = d.Nm;
+            }
             p.w0 = cmin >> 5;
             p.nw = (cmax >> 5) - p.w0 + 1;
             p.N = rmax - rmin + 1;
@@ -301,6 +306,15 @@ extern "C" int s2d_group(const s2d_video_desc* descs, int nvideos, int max_Nm, i
                          const uint32_t* mbits, const int32_t* rowinfo, const int32_t* one2x,
                          int32_t* work, int32_t* glabel, int32_t* grp_n, int32_t* grp_one2x,
                          int32_t* vidinfo, int32_t* clusterinfo, void* stream) {
+    return s2d_group_gram(descs, nvideos, max_Nm, max_NW, total_rows, mbits, rowinfo, one2x, work, glabel, grp_n, grp_one2x,
+                          vidinfo, clusterinfo, nullptr, nullptr, stream);
+}
+
+extern "C" int s2d_group_gram(const s2d_video_desc* descs, int nvideos, int max_Nm, int max_NW, int64_t total_rows,
+                              const uint32_t* mbits, const int32_t* rowinfo, const int32_t* one2x,
+                              int32_t* work, int32_t* glabel, int32_t* grp_n, int32_t* grp_one2x,
+                              int32_t* vidinfo, int32_t* clusterinfo, const int32_t* gram, const int64_t* gram_off,
+                              void* stream) {
     S2D_ENTER(stream);
     S2D_CHECK_ARG(descs && mbits && rowinfo && one2x && work && glabel && grp_n && grp_one2x && vidinfo && clusterinfo,
                   "s2d_group: null pointer");
@@ -314,7 +328,7 @@ extern "C" int s2d_group(const s2d_video_desc* descs, int nvideos, int max_Nm, i
     cudaMemsetAsync(grp_n, 0, (size_t)total_rows * 16 * sizeof(int32_t), st);
     cudaMemsetAsync(grp_one2x, 0, (size_t)total_rows * 16 * sizeof(int32_t), st);
     dim3 grid(S2D_MAX_CLUSTERS, nvideos);
-    group_prep_kernel<<<grid, GP_THREADS, 0, st>>>(descs, mbits, rowinfo, work, vidinfo, clusterinfo, problems);
+    group_prep_kernel<<<grid, GP_THREADS, 0, st>>>(descs, mbits, rowinfo, work, vidinfo, clusterinfo, problems, gram, gram_off);
     S2D_CHECK_LAUNCH("group_prep_kernel");
     int rc = launch_dbscan(problems, nvideos * S2D_MAX_CLUSTERS, max_Nm, max_NW,
                            reinterpret_cast<int32_t*>(problems + (int64_t)nvideos * S2D_MAX_CLUSTERS), st);

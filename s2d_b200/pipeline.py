@@ -61,7 +61,7 @@ class Batch:
     only enqueues kernels, so a Batch can be re-run (benchmarks) without touching the allocator."""
 
     def __init__(self, videos: List[VideoInput], device=None, stages: str = "LVBD", persistent_votes: bool = True,
-                 label_tmaps: bool = True):
+                 label_tmaps: bool = True, gram_min_rows: int = 2048):
         """`persistent_votes=False` runs K2 as one CTA per tile (the library's fallback for odd P / unaligned
         tracks), `label_tmaps=False` makes the persistent kernel fetch its label tables row by row instead of as TMA
         boxes; both exist for tests and profiling comparisons, the defaults are the product path."""
@@ -186,6 +186,21 @@ class Batch:
             self.glabel = z(row0)
             self.grp_n = z(16 * row0)
             self.grp_one2x = z(16 * row0)
+            # DBSCAN #2 of videos with many rows: the pairwise distances come from one int8 Gram contraction of the
+            # video's match rows on the tensor cores (O(Nm^2) reads in the DBSCAN passes instead of O(Nm^3 / 32) bit ops)
+            self.gram = self.gram_off = self.gram_planes = None
+            big = [i for i in range(nv) if descs[i].Nm >= gram_min_rows]
+            if big:
+                offs, tot, pmax = [-1] * nv, 0, 0
+                for i in big:
+                    offs[i] = tot
+                    tot += descs[i].Nm * descs[i].Nm
+                    tot += (-tot) % 4                         # 16-byte aligned matrices
+                    pmax = max(pmax, descs[i].Nm * descs[i].NW * 32)
+                self.gram = z(tot)
+                self.gram_off = torch.tensor(offs, dtype=torch.int64, device=dev)
+                self.gram_planes = torch.empty(pmax, dtype=torch.uint8, device=dev)
+                self._gram_videos = [(i, offs[i]) for i in big]
         self.kernel_launches_per_run = 0
         # persistent TMA-fed votes kernel (the library falls back by itself when P is odd)
         self.use_tma = bool(persistent_votes)
@@ -241,9 +256,16 @@ class Batch:
             call("select", 1, "s2d_select", d, nv, self.max_Nm, self.total_mw, p(self.hits), p(self.uniq),
                  p(self.gid_of), p(self.rowinfo), params.matching_threshold, params.one2x_iou,
                  params.one2x_frames, p(self.mbits), p(self.one2x), p(self.nmatch), p(self.vidinfo), st)
-            call("group", 7, "s2d_group", d, nv, self.max_Nm, self.max_NW, self.total_rows, p(self.mbits),
+            if self.gram is not None:
+                for i, off in self._gram_videos:           # match rows -> u8 planes -> G = X X^T (tcgen05 kind::i8)
+                    hd = self.host_descs[i]
+                    mb = self.mbits.data_ptr() + 4 * hd.mbits_off
+                    call("group", 1, "s2d_unpack_bits", mb, hd.Nm, hd.NW, hd.NW * 32, p(self.gram_planes), st)
+                    call("group", 2, "s2d_overlap_i8", p(self.gram_planes), hd.Nm, p(self.gram_planes), hd.Nm, hd.NW * 32,
+                         self.gram.data_ptr() + 4 * off, st)
+            call("group", 7, "s2d_group_gram", d, nv, self.max_Nm, self.max_NW, self.total_rows, p(self.mbits),
                  p(self.rowinfo), p(self.one2x), p(self.grpwork), p(self.glabel), p(self.grp_n),
-                 p(self.grp_one2x), p(self.vidinfo), p(self.clusterinfo), st)
+                 p(self.grp_one2x), p(self.vidinfo), p(self.clusterinfo), p(self.gram), p(self.gram_off), st)
         self.kernel_launches_per_run = launches
         return launches
 

@@ -30,6 +30,37 @@ def test_pipeline_matches_reference_golden(golden_case):
     check_against_golden(res, g)
 
 
+def test_gram_dbscan_path_matches_reference_golden(golden_case):
+    """DBSCAN #2 with the pairwise distances taken from the int8 Gram contraction of the match rows (the path videos with
+    >= 2048 rows take: s2d_unpack_bits + s2d_overlap_i8 + s2d_group_gram), forced on for every golden video: same groups,
+    coverages and one2x sums as the reference."""
+    from s2d_b200.pipeline import Batch, Params
+    name, g, labels, tracks, vis = golden_case
+    b = Batch([_video(labels, tracks, vis)], gram_min_rows=1)
+    assert b.gram is not None
+    b.run(Params(g["visibility_threshold"], g["matching_threshold"]))
+    torch.cuda.synchronize()
+    check_against_golden(b.decode()[0], g)
+
+
+def test_unpack_bits_is_the_inverse_of_pack_bits():
+    from s2d_b200 import _lib
+    rng = np.random.default_rng(9)
+    d = _dev()
+    for N, D in ((5, 33), (40, 128), (7, 300), (64, 1000)):
+        stride = (D + 31) // 32
+        ncols = stride * 32
+        X = (rng.random((N, D)) < 0.3)
+        Xp = np.zeros((N, ncols), np.uint8)
+        Xp[:, :D] = X
+        words = np.packbits(Xp, axis=1, bitorder="little").view(np.uint32).reshape(N, stride)
+        bits = torch.from_numpy(words.view(np.int32).copy()).to(d)
+        planes = torch.full((N, ncols), 7, dtype=torch.uint8, device=d)
+        _lib.call("s2d_unpack_bits", bits.data_ptr(), N, stride, ncols, planes.data_ptr(), torch.cuda.current_stream(d).cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(planes.cpu().numpy(), Xp)
+
+
 def test_batched_heterogeneous_videos_match_goldens():
     """all golden cases in ONE batch (different T/H/W/P/Nm per video)."""
     from tests.conftest import GOLDEN_CASES, load_golden
