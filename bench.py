@@ -595,6 +595,7 @@ def list_workload(args):
                 "results": {"digest": digest, "reference_digest": ref_digest, "results_equal": equal,
                             "videos_ok": sum(1 for r in results if r["status"] == 1), "keymasks": sum(r["keymasks"] for r in results),
                             "candidates": sum(r["candidates"] for r in results)},
+                "stage_ms_rank0": {k: round(v, 3) for k, v in local_stats["stage_ms"].items()},
                 "e2e": None, "cpu_binding": binding}
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, all_cores)

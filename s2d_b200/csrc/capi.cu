@@ -14,7 +14,7 @@ void set_error(const char* fmt, ...) {
 }  // namespace s2d
 
 extern "C" const char* s2d_last_error(void) { return s2d::g_err; }
-extern "C" int s2d_version(void) { return 202; }     // round 2, kernel revision 2 (recorded beside committed ncu-derived figures)
+extern "C" int s2d_version(void) { return 203; }     // round 2, kernel revision 3 (recorded beside committed ncu-derived figures)
 extern "C" int s2d_desc_size(void) { return (int)sizeof(s2d_video_desc); }
 
 extern "C" int s2d_device_sm_count(int device) {

@@ -4,7 +4,7 @@ out=gpurun_out; mkdir -p $out
 python -m pytest tests -m gpu -x -q > $out/r02_gputest_product.log 2>&1; echo "exit $?" >> $out/r02_gputest_product.log; tail -3 $out/r02_gputest_product.log
 S2D_B200_LIB=$PWD/s2d_b200/libs2d_b200_check.so python -m pytest tests -m gpu -q > $out/r02_gputest_boundscheck.log 2>&1; echo "exit $?" >> $out/r02_gputest_boundscheck.log; tail -3 $out/r02_gputest_boundscheck.log
 python __graft_entry__.py smoke 2>&1 | tail -1
-python bench.py > $out/r02_bench_c2_final.json 2> $out/r02_bench_c2_final.err; tail -c 400 $out/r02_bench_c2_final.err
+python bench.py --steps 20 > $out/r02_bench_c2_final.json 2> $out/r02_bench_c2_final.err; tail -c 400 $out/r02_bench_c2_final.err
 python bench.py --workload target --no-cpu > $out/r02_bench_target_480p.json 2>> $out/r02_bench_c2_final.err
 python bench.py --workload c1 --steps 50 > $out/r02_bench_c1.json 2>> $out/r02_bench_c2_final.err
 python bench.py --workload c1 --steps 50 --graph --no-cpu > $out/r02_bench_c1_cuda_graph.json 2>> $out/r02_bench_c2_final.err
