@@ -669,7 +669,11 @@ __device__ __forceinline__ bool pv_plan_next(PvPlan& pl, PvTile* rec, int lane, 
     if (pl.pi == pl.pi_end) {
         // consecutive tiles per claim: up to PV_CHUNK (same query, neighbouring frames: label maps stay hot
         // in L2), fewer when the launch is small so that every CTA gets work
+#ifdef S2D_EXPERIMENTS
+        const int chunk = max(1, min(ctrl[2] > 0 ? ctrl[2] : PV_CHUNK, total / (int)(gridDim.x * 2u)));      // ctrl[2]: S2D_PV_CHUNK
+#else
         const int chunk = max(1, min(PV_CHUNK, total / (int)(gridDim.x * 2u)));
+#endif
         int c = 0;
         if (lane == 0) c = atomicAdd(&ctrl[0], chunk);
         c = __shfl_sync(0xffffffffu, c, 0);
@@ -1193,6 +1197,13 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
         S2D_CHECK_LAUNCH("pv_plan_rows_kernel");
         pv_scan_kernel<<<1, 1024, 0, st>>>(rowplan, total_rows, ctrl);
         S2D_CHECK_LAUNCH("pv_scan_kernel");
+#ifdef S2D_EXPERIMENTS
+        {
+            static int32_t chunk_h = 0;
+            chunk_h = getenv("S2D_PV_CHUNK") ? atoi(getenv("S2D_PV_CHUNK")) : 0;
+            cudaMemcpyAsync(ctrl + 2, &chunk_h, sizeof(int32_t), cudaMemcpyHostToDevice, st);
+        }
+#endif
         const int tr = (int)total_rows;
         if (variant == 0) {      // label-table kernels
 #ifdef S2D_EXPERIMENTS   // 8 KB tiles: CTAs per SM / split tracks region (A/B runs)
