@@ -87,55 +87,8 @@ windows_kernel(const s2d_video_desc* __restrict__ descs, const uint32_t* __restr
             cr[3] = v1;
         }
     }
-    __syncthreads();
-
-    // phase B: one thread per row: winners of every run and the candidate run
-    __shared__ int s_ncand_total;
-    if (tid == 0) s_ncand_total = 0;
-    __syncthreads();
-    for (int q = tid; q < d.Nm; q += WIN_THREADS) {
-        const int c = labels1[d.row0 + q];
-        int cand = -1, v0 = -1, v1 = -1;
-        uint32_t* wb = winbits + d.xbits_off + (int64_t)q * TW;
-        for (int w = 0; w < TW; ++w) wb[w] = 0;
-        if (c >= 0) {
-            const uint32_t* xr = xbits + d.xbits_off + (int64_t)q * TW;
-            const uint32_t* mj = majbits + d.xbits_off + (int64_t)c * TW;
-            const int f = qframe[d.row0 + q];
-            v0 = clrow[(d.row0 + c) * 4 + 2];
-            v1 = clrow[(d.row0 + c) * 4 + 3];
-            int run = -1, cntv = 0, start = 0;
-            bool inrun = false;
-            for (int t = 0; t <= T; ++t) {
-                const bool m = t < T && ((mj[t >> 5] >> (t & 31)) & 1u);
-                if (m) {
-                    if (!inrun) { inrun = true; start = t; cntv = 0; ++run; }
-                    cntv += (xr[t >> 5] >> (t & 31)) & 1u;
-                } else if (inrun) {
-                    inrun = false;
-                    const int end = t - 1, len = end - start + 1;
-                    // frac = counts / length in float32, frac > 0.3 (float32), windows.py:100-103
-                    if (__fdiv_rn((float)cntv, (float)len) > winner_fraction) {
-                        S2D_DEV_ASSERT((run >> 5) < TW);
-                        wb[run >> 5] |= 1u << (run & 31);
-                        if (f >= start && f <= end) cand = run;
-                    }
-                }
-            }
-            if (cand >= 0) atomicAdd(&s_ncand_total, 1);
-        }
-        reinterpret_cast<int4*>(rowinfo)[d.row0 + q] = make_int4(c, cand, v0, v1);
-    }
-    __syncthreads();
-
-    // phase C: per-cluster candidate counts (first S2D_MAX_CLUSTERS clusters) + stage-B status
-    __shared__ int s_ncand[S2D_MAX_CLUSTERS];
-    if (tid < S2D_MAX_CLUSTERS) s_ncand[tid] = 0;
-    __syncthreads();
-    for (int q = tid; q < d.Nm; q += WIN_THREADS) {
-        const int4 ri = reinterpret_cast<const int4*>(rowinfo)[d.row0 + q];
-        if (ri.x >= 0 && ri.x < S2D_MAX_CLUSTERS && ri.y >= 0) atomicAdd(&s_ncand[ri.x], 1);
-    }
+    // clusterinfo of the video: sizes / windows now, candidate counts by windows_rows_kernel (atomics), status by
+    // windows_status_kernel
     __syncthreads();
     if (tid < S2D_MAX_CLUSTERS) {
         int32_t* ci = clusterinfo + ((int64_t)v * S2D_MAX_CLUSTERS + tid) * S2D_CLINFO_WORDS;
@@ -143,23 +96,77 @@ windows_kernel(const s2d_video_desc* __restrict__ descs, const uint32_t* __restr
         if (tid < k) {
             const int32_t* cr = clrow + (d.row0 + tid) * 4;
             ci[0] = cr[0];
-            ci[1] = s_ncand[tid];
             ci[2] = cr[2];
             ci[3] = cr[3];
             ci[4] = cr[1];
         }
     }
-    if (tid == 0) {
-        // load_cluster_masks sorts `cluster_*` folders lexicographically and drops empty ones:
-        // the video survives stage D only with 1..10 clusters that all own a candidate
-        // (cotracker_matching.py:89-90, 937-938, 1014-1017, 1042-1051; Appendix A.7 quirks 2, 3)
-        int ok = (k >= 1 && k <= 10);
-        for (int c = 0; c < k && c < S2D_MAX_CLUSTERS; ++c) ok &= s_ncand[c] > 0;
-        vi[1] = ok ? 1 : -1;
-        vi[2] = -1;
-        vi[3] = -1;
-        vi[4] = s_ncand_total;
+    if (tid == 0) vi[4] = 0;
+}
+
+// phase B: one thread per row (grid over the rows of every video: a 300-frame video has 9 000 of them): winners of every
+// run and the candidate run; candidate counts per cluster and per video by atomics
+__global__ void __launch_bounds__(WIN_THREADS)
+windows_rows_kernel(const s2d_video_desc* __restrict__ descs, const uint32_t* __restrict__ xbits,
+                    const int32_t* __restrict__ labels1, const int32_t* __restrict__ qframe, float winner_fraction,
+                    const uint32_t* __restrict__ majbits, uint32_t* __restrict__ winbits, int32_t* __restrict__ rowinfo,
+                    const int32_t* __restrict__ clrow, int32_t* __restrict__ vidinfo, int32_t* __restrict__ clusterinfo) {
+    const int v = blockIdx.y;
+    const s2d_video_desc d = descs[v];
+    const int q = blockIdx.x * WIN_THREADS + threadIdx.x;
+    if (q >= d.Nm) return;
+    const int T = d.T, TW = d.TW;
+    const int c = labels1[d.row0 + q];
+    int cand = -1, v0 = -1, v1 = -1;
+    uint32_t* wb = winbits + d.xbits_off + (int64_t)q * TW;
+    for (int w = 0; w < TW; ++w) wb[w] = 0;
+    if (c >= 0) {
+        const uint32_t* xr = xbits + d.xbits_off + (int64_t)q * TW;
+        const uint32_t* mj = majbits + d.xbits_off + (int64_t)c * TW;
+        const int f = qframe[d.row0 + q];
+        v0 = clrow[(d.row0 + c) * 4 + 2];
+        v1 = clrow[(d.row0 + c) * 4 + 3];
+        int run = -1, cntv = 0, start = 0;
+        bool inrun = false;
+        for (int t = 0; t <= T; ++t) {
+            const bool m = t < T && ((mj[t >> 5] >> (t & 31)) & 1u);
+            if (m) {
+                if (!inrun) { inrun = true; start = t; cntv = 0; ++run; }
+                cntv += (xr[t >> 5] >> (t & 31)) & 1u;
+            } else if (inrun) {
+                inrun = false;
+                const int end = t - 1, len = end - start + 1;
+                // frac = counts / length in float32, frac > 0.3 (float32), windows.py:100-103
+                if (__fdiv_rn((float)cntv, (float)len) > winner_fraction) {
+                    S2D_DEV_ASSERT((run >> 5) < TW);
+                    wb[run >> 5] |= 1u << (run & 31);
+                    if (f >= start && f <= end) cand = run;
+                }
+            }
+        }
+        if (cand >= 0) {
+            atomicAdd(&vidinfo[(int64_t)v * S2D_VIDINFO_WORDS + 4], 1);
+            if (c < S2D_MAX_CLUSTERS) atomicAdd(&clusterinfo[((int64_t)v * S2D_MAX_CLUSTERS + c) * S2D_CLINFO_WORDS + 1], 1);
+        }
     }
+    reinterpret_cast<int4*>(rowinfo)[d.row0 + q] = make_int4(c, cand, v0, v1);
+}
+
+// phase C: stage-B status of every video
+__global__ void windows_status_kernel(int nvideos, int32_t* __restrict__ vidinfo, const int32_t* __restrict__ clusterinfo) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvideos) return;
+    int32_t* vi = vidinfo + (int64_t)v * S2D_VIDINFO_WORDS;
+    const int k = vi[0];
+    // load_cluster_masks sorts `cluster_*` folders lexicographically and drops empty ones:
+    // the video survives stage D only with 1..10 clusters that all own a candidate
+    // (cotracker_matching.py:89-90, 937-938, 1014-1017, 1042-1051; Appendix A.7 quirks 2, 3)
+    int ok = (k >= 1 && k <= 10);
+    for (int c = 0; c < k && c < S2D_MAX_CLUSTERS; ++c)
+        ok &= clusterinfo[((int64_t)v * S2D_MAX_CLUSTERS + c) * S2D_CLINFO_WORDS + 1] > 0;
+    vi[1] = ok ? 1 : -1;
+    vi[2] = -1;
+    vi[3] = -1;
 }
 
 }  // namespace s2d
@@ -187,5 +194,12 @@ extern "C" int s2d_windows(const s2d_video_desc* descs, int nvideos, int64_t max
                                                    majbits, rsbits, rebits, winbits, rowinfo, clrow, vidinfo,
                                                    clusterinfo);
     S2D_CHECK_LAUNCH("windows_kernel");
+    const int64_t max_rows = max_rows_x_TW;      // an upper bound of every video's row count (rows x words per row, words >= 1)
+    dim3 rgrid((unsigned)((max_rows + WIN_THREADS - 1) / WIN_THREADS), nvideos);
+    windows_rows_kernel<<<rgrid, WIN_THREADS, 0, st>>>(descs, xbits, labels1, qframe, winner_fraction, majbits, winbits, rowinfo,
+                                                     clrow, vidinfo, clusterinfo);
+    S2D_CHECK_LAUNCH("windows_rows_kernel");
+    windows_status_kernel<<<(nvideos + 127) / 128, 128, 0, st>>>(nvideos, vidinfo, clusterinfo);
+    S2D_CHECK_LAUNCH("windows_status_kernel");
     return 0;
 }

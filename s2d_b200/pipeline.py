@@ -241,10 +241,10 @@ class Batch:
         if "B" in stages:
             call("binarize", 1, "s2d_binarize", d, nv, self.max_rows_x_TW, p(self.V),
                  float(np.float32(params.visibility_threshold)), p(self.xbits), st)
-            call("dbscan1", 5, "s2d_dbscan_visibility", d, nv, self.max_Nm, self.max_TW, self.total_rows,
+            call("dbscan1", 6, "s2d_dbscan_visibility", d, nv, self.max_Nm, self.max_TW, self.total_rows,
                  p(self.xbits), params.dbscan1_eps, params.dbscan1_min_samples, p(self.dbwork), p(self.labels1),
                  p(self.vidinfo), st)
-            call("windows", 2, "s2d_windows", d, nv, self.max_rows_x_TW, self.max_TW, self.total_rows,
+            call("windows", 4, "s2d_windows", d, nv, self.max_rows_x_TW, self.max_TW, self.total_rows,
                  self.total_vt, p(self.xbits), p(self.labels1), p(self.qframe),
                  float(np.float32(params.winner_fraction)), p(self.ccount), p(self.clrow), p(self.majbits),
                  p(self.rsbits), p(self.rebits), p(self.winbits), p(self.rowinfo), p(self.vidinfo),
@@ -263,7 +263,7 @@ class Batch:
                     call("group", 1, "s2d_unpack_bits", mb, hd.Nm, hd.NW, hd.NW * 32, p(self.gram_planes), st)
                     call("group", 2, "s2d_overlap_i8", p(self.gram_planes), hd.Nm, p(self.gram_planes), hd.Nm, hd.NW * 32,
                          self.gram.data_ptr() + 4 * off, st)
-            call("group", 7, "s2d_group_gram", d, nv, self.max_Nm, self.max_NW, self.total_rows, p(self.mbits),
+            call("group", 8, "s2d_group_gram", d, nv, self.max_Nm, self.max_NW, self.total_rows, p(self.mbits),
                  p(self.rowinfo), p(self.one2x), p(self.grpwork), p(self.glabel), p(self.grp_n),
                  p(self.grp_one2x), p(self.vidinfo), p(self.clusterinfo), p(self.gram), p(self.gram_off), st)
         self.kernel_launches_per_run = launches
