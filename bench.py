@@ -220,6 +220,8 @@ def main():
                     help="host staging pool of the e2e leg: huge-page mapping + cudaHostRegister, or torch pin_memory")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-k1", action="store_true")
+    ap.add_argument("--no-block-maps", action="store_true",
+                    help="A/B runs: votes kernel without the block-summary maps of its sparse-tile mode (P <= 1024)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -256,7 +258,7 @@ def main():
 
     nvid, T, H, W, M, P, desc = WORKLOADS[args.workload]
     vids = build_videos(args.workload, dev, 2024 + 1000 * rank, args.point_order)
-    batch = Batch(vids)
+    batch = Batch(vids, block_maps=not args.no_block_maps)
     params = Params()
 
     def barrier():
@@ -496,7 +498,8 @@ def list_workload(args):
         host_pg = dist.new_group(backend="gloo")
         warm = [None] * world if rank == 0 else None
         dist.gather_object(("warm", rank), warm, dst=0, group=host_pg)
-    runner = wl.DeviceRunner(dev, Params(), budget_bytes=args.hbm_budget_gb * 1e9, point_order=args.point_order)
+    runner = wl.DeviceRunner(dev, Params(), budget_bytes=args.hbm_budget_gb * 1e9, point_order=args.point_order,
+                             block_maps=not args.no_block_maps)
     peak, peak_src = _peaks()
 
     def barrier():

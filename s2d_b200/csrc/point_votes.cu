@@ -271,6 +271,8 @@ struct PvTile {             // written by the producer thread, read by everybody
     const uint8_t* tm;      // label-table kernel: the video's TMA descriptors (s2d_point_votes_tmaps) or null
     uint32_t ybase, pad2;   // t * H: first row of the frame in the descriptors' [T*H][W] view
     const float* src;       // label-table kernel: tracks[q, t] of the tile
+    const uint8_t* bm;      // block-summary map of the target frame (sparse-tile mode) or null
+    uint32_t bpitch, pad3;  // its row pitch
 };
 
 struct PvOut { int32_t* hout; int32_t* uout; int32_t L, pad; };
@@ -665,7 +667,7 @@ __device__ __forceinline__ bool pv_plan_next(PvPlan& pl, PvTile* rec, int lane, 
                                              const int4* __restrict__ rowplan, int total_rows, int total,
                                              int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
                                              int32_t* __restrict__ uniq, const uint8_t* __restrict__ tmaps,
-                                             const float** src) {
+                                             const float** src, const uint8_t* __restrict__ bmap, const int64_t* __restrict__ bmap_off) {
     if (pl.pi == pl.pi_end) {
         // consecutive tiles per claim: up to PV_CHUNK (same query, neighbouring frames: label maps stay hot
         // in L2), fewer when the launch is small so that every CTA gets work
@@ -722,6 +724,14 @@ __device__ __forceinline__ bool pv_plan_next(PvPlan& pl, PvTile* rec, int lane, 
         const int32_t* tsp = dp->tstart;
         const int64_t ts = t - (tsp ? tsp[q] : 0);           // frame index inside the stored track window
         ti.src = dp->tracks + ((int64_t)q * dp->Ttr + ts) * P * 2;
+        ti.bm = nullptr; ti.bpitch = 0; ti.pad3 = 0;
+        if (bmap && bmap_off) {
+            const int64_t bo = bmap_off[pl.prp.w];
+            if (bo >= 0) {
+                ti.bpitch = (uint32_t)bm_pitch(dp->W);
+                ti.bm = bmap + bo + (int64_t)t * bm_rows(dp->H) * ti.bpitch;
+            }
+        }
         *rec = ti;
         *src = ti.src;
     }
@@ -743,7 +753,8 @@ template <int THREADS, int PPT, int CTAS, bool SPLIT, int NCH>
 __global__ void __launch_bounds__(THREADS, CTAS)
 point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __restrict__ rowplan,
                        int total_rows, int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
-                       int32_t* __restrict__ uniq, const uint8_t* __restrict__ tmaps) {
+                       int32_t* __restrict__ uniq, const uint8_t* __restrict__ tmaps,
+                       const uint8_t* __restrict__ bmap, const int64_t* __restrict__ bmap_off) {
     constexpr int BUF_BYTES = pv_buf_bytes(THREADS, PPT, CTAS, SPLIT, NCH);
     constexpr int SLOT_BYTES = THREADS * PPT * 8 / NCH;          // one chunk of a tile's tracks
     constexpr int KCH = PPT / 2 / NCH;                           // 16-byte point pairs of a thread per chunk
@@ -794,7 +805,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     auto plan = [&](PvTile* rec) {
         PvPlan pl = plan_s;
         const float* src = nullptr;
-        const bool ok = pv_plan_next(pl, rec, lane, descs, rowplan, total_rows, total, ctrl, hits, uniq, tmaps, &src);
+        const bool ok = pv_plan_next(pl, rec, lane, descs, rowplan, total_rows, total, ctrl, hits, uniq, tmaps, &src, bmap, bmap_off);
         __syncwarp();
         if (lane == 0) { plan_s = pl; nsrc_s = src; more_s = ok ? 1 : 0; }
     };
@@ -905,7 +916,92 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                 R = (uint32_t)BUF_BYTES / pitch;
             }
             const uint8_t* lbl = ti->lbl;
-            if (L <= 255 && R * PV_MAX_BANDS >= bh) {
+            // ---- sparse-tile mode (tiles of <= 1024 points, block-summary maps given): the table of such a tile is the
+            // whole bounding box of the object (27 KB at 480p, up to 138 KB at 1080p for 8 KB of tracks), i.e. L2 -> shared
+            // traffic of 3-17 x the algorithmic bytes. Here the tile fetches the block-summary map of its bounding box
+            // (1 / 16 of the bytes), de-duplicates in a bitmap of the box and reads exact labels from the label map only
+            // for first points that fall into mixed 4 x 4 blocks (object borders).
+            bool bm_done = false;
+            if (THREADS * PPT <= 1024 && ti->bm != nullptr && L <= 255) {
+                const uint32_t bx0 = x0 >> 2, by0 = y0 >> 2;
+                const uint32_t bwb = ((x0 + bw - 1u) >> 2) - bx0 + 1u, bhb = ((y0 + bh - 1u) >> 2) - by0 + 1u;
+                const uint32_t a4 = bx0 & 3u;
+                const uint32_t wpr = (a4 + bwb + 3u) >> 2;                    // 32-bit words per staged block row
+                const uint32_t pitchb = 4u * wpr;
+                const uint32_t nblk = bhb * wpr;                              // words of the staged block map
+                const uint32_t nbw = (bh * bw + 31u) >> 5;                    // words of the box's bitmap (bit = dy * bw + dx)
+                const uint32_t blk_bytes = (4u * nblk + 15u) & ~15u;
+                if (blk_bytes + 4u * nbw <= (uint32_t)BUF_BYTES) {
+                    bm_done = true;
+                    // every word of the block map is its own 4-byte cp.async: all of a thread's copies are in flight at once
+                    // (a load -> store loop would pay one L2 round trip per iteration)
+                    {
+                        const uint8_t* brow0 = ti->bm + (int64_t)by0 * ti->bpitch + (bx0 - a4);
+                        const uint32_t dq = (uint32_t)THREADS / wpr, dr = (uint32_t)THREADS - dq * wpr;
+                        uint32_t r = (uint32_t)tid / wpr, w = (uint32_t)tid - r * wpr;
+                        for (uint32_t i = tid; i < nblk; i += THREADS) {
+                            S2D_DEV_ASSERT(r * wpr + w == i && bx0 - a4 + 4u * w + 4u <= ti->bpitch && by0 + r < (uint32_t)bm_rows((int)H));
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                                         :: "r"(tab_s + 4u * i), "l"(brow0 + (int64_t)r * ti->bpitch + 4u * w) : "memory");
+                            r += dq; w += dr;
+                            if (w >= wpr) { w -= wpr; ++r; }
+                        }
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    }
+                    uint32_t* bits = reinterpret_cast<uint32_t*>(buf + blk_bytes);
+                    for (uint32_t i = tid; i < nbw; i += THREADS) bits[i] = 0u;
+                    if (warp == 0) {                  // the plan's dependent loads fly with the block-map copies
+                        plan(&tinfo[snxt]);
+                        planned = true;
+                        if (SPLIT) {
+                            __syncwarp();
+                            if (lane == 0 && more_s) issue_tracks(tinfo[snxt].pad);
+                        }
+                    }
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncthreads();
+                    // Three passes over the thread's points so that nothing serialises on a memory round trip: (1) claim the
+                    // pixels (shared atomics; points outside the frame claim a dummy word that is all ones), (2) block labels
+                    // of the first points, (3) exact labels of first points in mixed blocks - independent global loads, all
+                    // issued before the first is used - and the votes.
+                    const uint32_t pk0 = (y0 << 16) + x0, lim = bh << 16;
+                    const uint32_t bits_s = tab_s + blk_bytes;
+                    const uint32_t blk_s = tab_s + a4 - (by0 * pitchb + bx0);     // + (iy >> 2) * pitchb + (ix >> 2): the point's block
+                    uint32_t first = 0;                                       // bit k: point k is the first on its pixel
+                    uint32_t lab[PPT];
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) {
+                        const uint32_t e = pk[k] - pk0;
+                        const bool in = e < lim;                              // a valid point (all of them lie inside the box)
+                        const uint32_t bit = (e >> 16) * bw + (e & 0xFFFFu);
+                        S2D_DEV_ASSERT(!in || ((e & 0xFFFFu) < bw && (bit >> 5) < nbw));
+                        const uint32_t m = 1u << (bit & 31u);
+                        const uint32_t addr = in ? bits_s + 4u * (bit >> 5) : dummy_s;
+                        uint32_t old;
+                        asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(m) : "memory");
+                        first |= ((old & m) ? 0u : 1u) << k;
+                    }
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) {
+                        const uint32_t ix = pk[k] & 0xFFFFu, iy = pk[k] >> 16;
+                        lab[k] = 0xFFu;
+                        if ((first >> k) & 1u) {
+                            S2D_DEV_ASSERT(((iy >> 2) - by0) * pitchb + (ix >> 2) - bx0 + a4 < 4u * nblk);
+                            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(lab[k]) : "r"(blk_s + (iy >> 2) * pitchb + (ix >> 2)));
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) {
+                        const uint32_t ix = pk[k] & 0xFFFFu, iy = pk[k] >> 16;
+                        if (((first >> k) & 1u) && lab[k] == 0xFFu) lab[k] = __ldg(lbl + (size_t)iy * W + ix);
+                    }
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k)
+                        if ((first >> k) & 1u) asm volatile("red.shared.add.u32 [%0], 1;" :: "r"((lab[k] << 2) | hist_s) : "memory");
+                }
+            }
+            if (bm_done) {
+            } else if (L <= 255 && R * PV_MAX_BANDS >= bh) {
                 // ---- table mode ---------------------------------------------------------------
                 for (uint32_t b0 = 0; b0 < bh; b0 += R) {
                     const uint32_t rows = min(R, bh - b0);
@@ -1052,7 +1148,8 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
 
 template <int THREADS, int PPT, int CTAS, bool SPLIT = false, int NCH = 2>
 static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, const int4* rowplan,
-                         int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq, const uint8_t* tmaps) {
+                         int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq, const uint8_t* tmaps,
+                         const uint8_t* bmap = nullptr, const int64_t* bmap_off = nullptr) {
     const int smem = pv_smem_bytes(THREADS, PPT, CTAS, SPLIT, NCH);
     auto kfn = point_votes_tab_kernel<THREADS, PPT, CTAS, SPLIT, NCH>;
     static bool configured[S2D_MAX_DEVICES] = {};
@@ -1063,7 +1160,7 @@ static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, 
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, THREADS, smem);
     if (per_sm < 1) per_sm = 1;
-    kfn<<<nsm * per_sm, THREADS, smem, st>>>(descs, rowplan, total_rows, ctrl, hits, uniq, tmaps);
+    kfn<<<nsm * per_sm, THREADS, smem, st>>>(descs, rowplan, total_rows, ctrl, hits, uniq, tmaps, bmap, bmap_off);
     S2D_CHECK_LAUNCH("point_votes_tab_kernel");
     return 0;
 }
@@ -1175,6 +1272,15 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
                                int vec4_ok, int64_t total_rows, const int32_t* rowinfo,
                                const int32_t* vidinfo, int32_t* work, const void* label_tmaps,
                                int32_t* hits, int32_t* uniq, void* stream) {
+    return s2d_point_votes_bm(descs, nvideos, max_T, max_Nm, max_P, vec4_ok, total_rows, rowinfo, vidinfo, work, label_tmaps,
+                              nullptr, nullptr, hits, uniq, stream);
+}
+
+extern "C" int s2d_point_votes_bm(const s2d_video_desc* descs, int nvideos, int max_T, int max_Nm, int max_P,
+                                  int vec4_ok, int64_t total_rows, const int32_t* rowinfo,
+                                  const int32_t* vidinfo, int32_t* work, const void* label_tmaps,
+                                  const uint8_t* bmap, const int64_t* bmap_off,
+                                  int32_t* hits, int32_t* uniq, void* stream) {
     S2D_ENTER(stream);
     S2D_CHECK_ARG((((uintptr_t)label_tmaps) & 63) == 0, "s2d_point_votes: label_tmaps must be 64-byte aligned");
     const uint8_t* tm = static_cast<const uint8_t*>(label_tmaps);
@@ -1210,13 +1316,17 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
             if (max_P <= 128 * 8 && getenv("S2D_PV_SMALL")) {
                 const int v = atoi(getenv("S2D_PV_SMALL"));
                 if (v == 60) return launch_pv_tab<128, 8, 6, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-                if (v == 6) return launch_pv_tab<128, 8, 6, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-                if (v == 7) return launch_pv_tab<128, 8, 7, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-                if (v == 8) return launch_pv_tab<128, 8, 8, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-                if (v == 9) return launch_pv_tab<128, 8, 9, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                if (v == 6) return launch_pv_tab<128, 8, 6, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
+                if (v == 7) return launch_pv_tab<128, 8, 7, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
+                if (v == 8) return launch_pv_tab<128, 8, 8, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
+                if (v == 9) return launch_pv_tab<128, 8, 9, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
+                if (v == 1608) return launch_pv_tab<64, 16, 8, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
+                if (v == 1610) return launch_pv_tab<64, 16, 10, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
+                if (v == 1612) return launch_pv_tab<64, 16, 12, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
+                if (v == 408) return launch_pv_tab<256, 4, 4, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
             }
 #endif
-            if (max_P <= 128 * 8) return launch_pv_tab<128, 8, 7, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+            if (max_P <= 128 * 8) return launch_pv_tab<128, 8, 6, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
             if (max_P <= 128 * 16) return launch_pv_tab<128, 16, 6>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
 #ifdef S2D_EXPERIMENTS   // CTAs per SM of the 4096-point configuration (A/B runs; 6 x 128 threads is the measured best)
             if (max_P <= 256 * 16) {
