@@ -220,8 +220,6 @@ def main():
                     help="host staging pool of the e2e leg: huge-page mapping + cudaHostRegister, or torch pin_memory")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-k1", action="store_true")
-    ap.add_argument("--no-block-maps", action="store_true",
-                    help="A/B runs: votes kernel without the block-summary maps of its sparse-tile mode (P <= 1024)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -258,7 +256,7 @@ def main():
 
     nvid, T, H, W, M, P, desc = WORKLOADS[args.workload]
     vids = build_videos(args.workload, dev, 2024 + 1000 * rank, args.point_order)
-    batch = Batch(vids, block_maps=not args.no_block_maps)
+    batch = Batch(vids)
     params = Params()
 
     def barrier():
@@ -312,8 +310,10 @@ def main():
     k2_ms = stage_ms["point_votes"]
     achieved = alg_bytes / (k2_ms / 1000.0) / 1e9
     vr_bytes = sum(d.Nm * d.T * d.P + 8 * d.Nm * d.T for d in batch.host_descs)
-    pv_name = ("point_votes_tab_kernel (persistent; tile's tracks by cp.async.bulk, bbox of the label map by TMA "
-               "boxes into the same smem buffer, one shared atomic per point)" if batch.use_tma and batch.vec4 and P <= 8192
+    pv_name = ("point_votes_warp_kernel (persistent, one warp per tile: tracks by cp.async.bulk, bitmap of the bounding box in "
+               "shared memory, labels of first points straight from the label map)" if batch.use_tma and batch.vec4 and P <= 1024
+               else "point_votes_tab_kernel (persistent; tile's tracks by cp.async.bulk, bbox of the label map by TMA "
+               "boxes into the same smem buffer, one shared atomic per point)" if batch.use_tma and batch.vec4 and P <= 16384
                else "point_votes_kernel (one CTA per tile)")
     # DRAM traffic of the same launch from the committed `ncu --set full` capture (profiles/), if it
     # was taken on this workload: dram__bytes_read.sum + dram__bytes_write.sum
@@ -498,8 +498,7 @@ def list_workload(args):
         host_pg = dist.new_group(backend="gloo")
         warm = [None] * world if rank == 0 else None
         dist.gather_object(("warm", rank), warm, dst=0, group=host_pg)
-    runner = wl.DeviceRunner(dev, Params(), budget_bytes=args.hbm_budget_gb * 1e9, point_order=args.point_order,
-                             block_maps=not args.no_block_maps)
+    runner = wl.DeviceRunner(dev, Params(), budget_bytes=args.hbm_budget_gb * 1e9, point_order=args.point_order)
     peak, peak_src = _peaks()
 
     def barrier():

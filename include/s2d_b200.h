@@ -167,29 +167,14 @@ int s2d_windows(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_TW,
  * a multiple of 16 get no descriptors and keep the row-by-row fetch. */
 #define S2D_PV_TMAPS 32                            /* box widths 16, 32, ... 512 pixels, 16 rows each */
 #define S2D_PV_TMAP_BYTES (S2D_PV_TMAPS * 128 + 128)
-int s2d_point_votes_variant(int variant);   /* process-wide; 0 label table, 2 one CTA per tile (1, the superseded
-                                             * bitmap kernel, only exists in the experiments build: make exp) */
+int s2d_point_votes_variant(int variant);   /* process-wide; 0 product dispatch (one warp per tile for P <= 1024, label
+                                             * table above), 2 one CTA per tile, 3 label table for every P (1, the
+                                             * superseded bitmap kernel, only exists in the experiments build: make exp) */
 int s2d_point_votes_work_ints(int64_t total_rows, int64_t* out);
 int s2d_point_votes_tmaps(const s2d_video_desc* host_descs, int nvideos, void* host_out);
 int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max_T, int max_Nm, int max_P,
                     int vec4_ok, int64_t total_rows, const int32_t* rowinfo, const int32_t* vidinfo,
                     int32_t* work, const void* label_tmaps, int32_t* hits, int32_t* uniq, void* stream);
-
-/* Sparse tiles (P <= 1024 tracked points per query): a tile's label table is the whole bounding box of the object - 3 to
- * 17 times the bytes of the tile's tracks. With block-summary maps the votes kernel fetches 1/16 of that: bmap holds, per
- * video v at byte offset bmap_off[v] (DEVICE int64 [nvideos], multiples of 16, -1 = none), u8 [T][ceil(H/4)][Wbp] with
- * Wbp = ceil(W/4) rounded up to a multiple of 4: the label of a 4 x 4 pixel block when it is uniform, 0xFF when it is mixed
- * (exact labels are then read from the label map, only for first points in such blocks). s2d_label_blockmap builds the maps
- * (max_blocks >= ceil(H/4) * Wbp of every video; s2d_label_blockmap_bytes gives a video's size), s2d_point_votes_bm is
- * s2d_point_votes with the maps (NULL / NULL = s2d_point_votes). Results are identical; label id 255 in use, tiles of more
- * than 1024 points and boxes whose map + bitmap exceed the shared buffer keep the table path. */
-int s2d_label_blockmap_bytes(int T, int H, int W, int64_t* out);
-int s2d_label_blockmap(const s2d_video_desc* descs, int nvideos, int max_T, int64_t max_blocks, uint8_t* bmap,
-                       const int64_t* bmap_off, void* stream);
-int s2d_point_votes_bm(const s2d_video_desc* descs, int nvideos, int max_T, int max_Nm, int max_P,
-                       int vec4_ok, int64_t total_rows, const int32_t* rowinfo, const int32_t* vidinfo,
-                       int32_t* work, const void* label_tmaps, const uint8_t* bmap, const int64_t* bmap_off,
-                       int32_t* hits, int32_t* uniq, void* stream);
 
 /* K3d. Appearance events of visibility curves V f32 [N][T] (device): moving average of odd length
  * smoothing_window (reflect padding), `>= thresh`, morphological opening with window

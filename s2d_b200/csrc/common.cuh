@@ -83,10 +83,6 @@ __device__ __forceinline__ int4 ld_stream(const int4* p) {
     return r;
 }
 
-// geometry of the block-summary label maps (label_blockmap_kernel / the votes kernel's sparse-tile mode)
-__host__ __device__ inline int64_t bm_pitch(int W) { return (((int64_t)W + 3) / 4 + 3) & ~(int64_t)3; }
-__host__ __device__ inline int64_t bm_rows(int H) { return ((int64_t)H + 3) / 4; }
-
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
 __device__ __forceinline__ int cdiv(int a, int b) { return (a + b - 1) / b; }

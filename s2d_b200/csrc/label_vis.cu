@@ -183,40 +183,6 @@ frame_tables_kernel(const s2d_video_desc* __restrict__ descs, const int32_t* __r
 }
 
 // ------------------------------------------------------------------------------------------
-// K0c: block-summary maps for the votes kernel's sparse tiles. bmap[t][by][bx] = the label of the 4 x 4 pixel block
-// (by, bx) when all its in-frame pixels carry one label (< 255), 0xFF when they do not. Row pitch Wbp = ceil(W / 4)
-// rounded up to a multiple of 4 (padding bytes 0xFF), so that rows can be copied as aligned 32-bit words.
-// A 1024-point tile of an object looks up 1/16 of the bytes of its bounding box and fetches exact labels only for
-// points in mixed blocks (object borders).
-// ------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(256)
-label_blockmap_kernel(const s2d_video_desc* __restrict__ descs, uint8_t* __restrict__ bmap, const int64_t* __restrict__ bmap_off) {
-    const s2d_video_desc d = descs[blockIdx.z];
-    const int t = blockIdx.y;
-    if (t >= d.T || bmap_off[blockIdx.z] < 0) return;
-    const int64_t Wbp = bm_pitch(d.W), Hb = bm_rows(d.H);
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= Hb * Wbp) return;
-    const int by = (int)(i / Wbp), bx = (int)(i - (int64_t)by * Wbp);
-    const uint8_t* lab = d.labels + (int64_t)t * d.H * d.W;
-    uint32_t out = 0xFFu;
-    if (4 * bx < d.W) {
-        const int x0 = 4 * bx, y0 = 4 * by, nx = min(4, d.W - x0), ny = min(4, d.H - y0);
-        const uint32_t first = lab[(int64_t)y0 * d.W + x0];
-        bool uni = true;
-        const bool fast = nx == 4 && ((d.W & 3) == 0) && ((((uintptr_t)lab) & 3) == 0);
-        for (int r = 0; r < ny; ++r) {
-            const uint8_t* row = lab + (int64_t)(y0 + r) * d.W + x0;
-            if (fast) uni &= *reinterpret_cast<const uint32_t*>(row) == first * 0x01010101u;
-            else for (int c = 0; c < nx; ++c) uni &= row[c] == first;
-        }
-        if (uni && first != 0xFFu) out = first;
-    }
-    bmap[bmap_off[blockIdx.z] + ((int64_t)t * Hb + by) * Wbp + bx] = (uint8_t)out;
-}
-
-// ------------------------------------------------------------------------------------------
 // K3a: visibility reduce. One warp per (row, frame): popcount of nonzero flag bytes.
 // ------------------------------------------------------------------------------------------
 constexpr int VR_WARPS = 8;
@@ -312,23 +278,6 @@ extern "C" int s2d_label_stats(const s2d_video_desc* descs, int nvideos, int max
     S2D_CHECK_LAUNCH("label_hist_kernel");
     frame_tables_kernel<<<nvideos, S2D_MAX_LABELS, 0, st>>>(descs, area, gid_of, frameinfo, qframe, qlabel, vidinfo);
     S2D_CHECK_LAUNCH("frame_tables_kernel");
-    return 0;
-}
-
-extern "C" int s2d_label_blockmap_bytes(int T, int H, int W, int64_t* out) {
-    if (!out || T <= 0 || H <= 0 || W <= 0) return -1;
-    *out = ((int64_t)T * bm_rows(H) * bm_pitch(W) + 15) & ~(int64_t)15;
-    return 0;
-}
-
-extern "C" int s2d_label_blockmap(const s2d_video_desc* descs, int nvideos, int max_T, int64_t max_blocks, uint8_t* bmap,
-                                  const int64_t* bmap_off, void* stream) {
-    S2D_ENTER(stream);
-    S2D_CHECK_ARG(descs && bmap && bmap_off && nvideos > 0 && nvideos <= 65535 && max_T > 0 && max_T <= 65535 && max_blocks > 0,
-                  "s2d_label_blockmap: bad arguments");
-    dim3 grid((unsigned)((max_blocks + 255) / 256), max_T, nvideos);
-    label_blockmap_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs, bmap, bmap_off);
-    S2D_CHECK_LAUNCH("label_blockmap_kernel");
     return 0;
 }
 

@@ -271,8 +271,6 @@ struct PvTile {             // written by the producer thread, read by everybody
     const uint8_t* tm;      // label-table kernel: the video's TMA descriptors (s2d_point_votes_tmaps) or null
     uint32_t ybase, pad2;   // t * H: first row of the frame in the descriptors' [T*H][W] view
     const float* src;       // label-table kernel: tracks[q, t] of the tile
-    const uint8_t* bm;      // block-summary map of the target frame (sparse-tile mode) or null
-    uint32_t bpitch, pad3;  // its row pitch
 };
 
 struct PvOut { int32_t* hout; int32_t* uout; int32_t L, pad; };
@@ -667,7 +665,7 @@ __device__ __forceinline__ bool pv_plan_next(PvPlan& pl, PvTile* rec, int lane, 
                                              const int4* __restrict__ rowplan, int total_rows, int total,
                                              int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
                                              int32_t* __restrict__ uniq, const uint8_t* __restrict__ tmaps,
-                                             const float** src, const uint8_t* __restrict__ bmap, const int64_t* __restrict__ bmap_off) {
+                                             const float** src) {
     if (pl.pi == pl.pi_end) {
         // consecutive tiles per claim: up to PV_CHUNK (same query, neighbouring frames: label maps stay hot
         // in L2), fewer when the launch is small so that every CTA gets work
@@ -724,14 +722,6 @@ __device__ __forceinline__ bool pv_plan_next(PvPlan& pl, PvTile* rec, int lane, 
         const int32_t* tsp = dp->tstart;
         const int64_t ts = t - (tsp ? tsp[q] : 0);           // frame index inside the stored track window
         ti.src = dp->tracks + ((int64_t)q * dp->Ttr + ts) * P * 2;
-        ti.bm = nullptr; ti.bpitch = 0; ti.pad3 = 0;
-        if (bmap && bmap_off) {
-            const int64_t bo = bmap_off[pl.prp.w];
-            if (bo >= 0) {
-                ti.bpitch = (uint32_t)bm_pitch(dp->W);
-                ti.bm = bmap + bo + (int64_t)t * bm_rows(dp->H) * ti.bpitch;
-            }
-        }
         *rec = ti;
         *src = ti.src;
     }
@@ -753,8 +743,7 @@ template <int THREADS, int PPT, int CTAS, bool SPLIT, int NCH>
 __global__ void __launch_bounds__(THREADS, CTAS)
 point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __restrict__ rowplan,
                        int total_rows, int32_t* __restrict__ ctrl, int32_t* __restrict__ hits,
-                       int32_t* __restrict__ uniq, const uint8_t* __restrict__ tmaps,
-                       const uint8_t* __restrict__ bmap, const int64_t* __restrict__ bmap_off) {
+                       int32_t* __restrict__ uniq, const uint8_t* __restrict__ tmaps) {
     constexpr int BUF_BYTES = pv_buf_bytes(THREADS, PPT, CTAS, SPLIT, NCH);
     constexpr int SLOT_BYTES = THREADS * PPT * 8 / NCH;          // one chunk of a tile's tracks
     constexpr int KCH = PPT / 2 / NCH;                           // 16-byte point pairs of a thread per chunk
@@ -805,7 +794,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
     auto plan = [&](PvTile* rec) {
         PvPlan pl = plan_s;
         const float* src = nullptr;
-        const bool ok = pv_plan_next(pl, rec, lane, descs, rowplan, total_rows, total, ctrl, hits, uniq, tmaps, &src, bmap, bmap_off);
+        const bool ok = pv_plan_next(pl, rec, lane, descs, rowplan, total_rows, total, ctrl, hits, uniq, tmaps, &src);
         __syncwarp();
         if (lane == 0) { plan_s = pl; nsrc_s = src; more_s = ok ? 1 : 0; }
     };
@@ -916,92 +905,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
                 R = (uint32_t)BUF_BYTES / pitch;
             }
             const uint8_t* lbl = ti->lbl;
-            // ---- sparse-tile mode (tiles of <= 1024 points, block-summary maps given): the table of such a tile is the
-            // whole bounding box of the object (27 KB at 480p, up to 138 KB at 1080p for 8 KB of tracks), i.e. L2 -> shared
-            // traffic of 3-17 x the algorithmic bytes. Here the tile fetches the block-summary map of its bounding box
-            // (1 / 16 of the bytes), de-duplicates in a bitmap of the box and reads exact labels from the label map only
-            // for first points that fall into mixed 4 x 4 blocks (object borders).
-            bool bm_done = false;
-            if (THREADS * PPT <= 1024 && ti->bm != nullptr && L <= 255) {
-                const uint32_t bx0 = x0 >> 2, by0 = y0 >> 2;
-                const uint32_t bwb = ((x0 + bw - 1u) >> 2) - bx0 + 1u, bhb = ((y0 + bh - 1u) >> 2) - by0 + 1u;
-                const uint32_t a4 = bx0 & 3u;
-                const uint32_t wpr = (a4 + bwb + 3u) >> 2;                    // 32-bit words per staged block row
-                const uint32_t pitchb = 4u * wpr;
-                const uint32_t nblk = bhb * wpr;                              // words of the staged block map
-                const uint32_t nbw = (bh * bw + 31u) >> 5;                    // words of the box's bitmap (bit = dy * bw + dx)
-                const uint32_t blk_bytes = (4u * nblk + 15u) & ~15u;
-                if (blk_bytes + 4u * nbw <= (uint32_t)BUF_BYTES) {
-                    bm_done = true;
-                    // every word of the block map is its own 4-byte cp.async: all of a thread's copies are in flight at once
-                    // (a load -> store loop would pay one L2 round trip per iteration)
-                    {
-                        const uint8_t* brow0 = ti->bm + (int64_t)by0 * ti->bpitch + (bx0 - a4);
-                        const uint32_t dq = (uint32_t)THREADS / wpr, dr = (uint32_t)THREADS - dq * wpr;
-                        uint32_t r = (uint32_t)tid / wpr, w = (uint32_t)tid - r * wpr;
-                        for (uint32_t i = tid; i < nblk; i += THREADS) {
-                            S2D_DEV_ASSERT(r * wpr + w == i && bx0 - a4 + 4u * w + 4u <= ti->bpitch && by0 + r < (uint32_t)bm_rows((int)H));
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
-                                         :: "r"(tab_s + 4u * i), "l"(brow0 + (int64_t)r * ti->bpitch + 4u * w) : "memory");
-                            r += dq; w += dr;
-                            if (w >= wpr) { w -= wpr; ++r; }
-                        }
-                        asm volatile("cp.async.commit_group;" ::: "memory");
-                    }
-                    uint32_t* bits = reinterpret_cast<uint32_t*>(buf + blk_bytes);
-                    for (uint32_t i = tid; i < nbw; i += THREADS) bits[i] = 0u;
-                    if (warp == 0) {                  // the plan's dependent loads fly with the block-map copies
-                        plan(&tinfo[snxt]);
-                        planned = true;
-                        if (SPLIT) {
-                            __syncwarp();
-                            if (lane == 0 && more_s) issue_tracks(tinfo[snxt].pad);
-                        }
-                    }
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    __syncthreads();
-                    // Three passes over the thread's points so that nothing serialises on a memory round trip: (1) claim the
-                    // pixels (shared atomics; points outside the frame claim a dummy word that is all ones), (2) block labels
-                    // of the first points, (3) exact labels of first points in mixed blocks - independent global loads, all
-                    // issued before the first is used - and the votes.
-                    const uint32_t pk0 = (y0 << 16) + x0, lim = bh << 16;
-                    const uint32_t bits_s = tab_s + blk_bytes;
-                    const uint32_t blk_s = tab_s + a4 - (by0 * pitchb + bx0);     // + (iy >> 2) * pitchb + (ix >> 2): the point's block
-                    uint32_t first = 0;                                       // bit k: point k is the first on its pixel
-                    uint32_t lab[PPT];
-#pragma unroll
-                    for (int k = 0; k < PPT; ++k) {
-                        const uint32_t e = pk[k] - pk0;
-                        const bool in = e < lim;                              // a valid point (all of them lie inside the box)
-                        const uint32_t bit = (e >> 16) * bw + (e & 0xFFFFu);
-                        S2D_DEV_ASSERT(!in || ((e & 0xFFFFu) < bw && (bit >> 5) < nbw));
-                        const uint32_t m = 1u << (bit & 31u);
-                        const uint32_t addr = in ? bits_s + 4u * (bit >> 5) : dummy_s;
-                        uint32_t old;
-                        asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(m) : "memory");
-                        first |= ((old & m) ? 0u : 1u) << k;
-                    }
-#pragma unroll
-                    for (int k = 0; k < PPT; ++k) {
-                        const uint32_t ix = pk[k] & 0xFFFFu, iy = pk[k] >> 16;
-                        lab[k] = 0xFFu;
-                        if ((first >> k) & 1u) {
-                            S2D_DEV_ASSERT(((iy >> 2) - by0) * pitchb + (ix >> 2) - bx0 + a4 < 4u * nblk);
-                            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(lab[k]) : "r"(blk_s + (iy >> 2) * pitchb + (ix >> 2)));
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < PPT; ++k) {
-                        const uint32_t ix = pk[k] & 0xFFFFu, iy = pk[k] >> 16;
-                        if (((first >> k) & 1u) && lab[k] == 0xFFu) lab[k] = __ldg(lbl + (size_t)iy * W + ix);
-                    }
-#pragma unroll
-                    for (int k = 0; k < PPT; ++k)
-                        if ((first >> k) & 1u) asm volatile("red.shared.add.u32 [%0], 1;" :: "r"((lab[k] << 2) | hist_s) : "memory");
-                }
-            }
-            if (bm_done) {
-            } else if (L <= 255 && R * PV_MAX_BANDS >= bh) {
+            if (L <= 255 && R * PV_MAX_BANDS >= bh) {
                 // ---- table mode ---------------------------------------------------------------
                 for (uint32_t b0 = 0; b0 < bh; b0 += R) {
                     const uint32_t rows = min(R, bh - b0);
@@ -1148,8 +1052,7 @@ point_votes_tab_kernel(const s2d_video_desc* __restrict__ descs, const int4* __r
 
 template <int THREADS, int PPT, int CTAS, bool SPLIT = false, int NCH = 2>
 static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, const int4* rowplan,
-                         int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq, const uint8_t* tmaps,
-                         const uint8_t* bmap = nullptr, const int64_t* bmap_off = nullptr) {
+                         int total_rows, int32_t* ctrl, int32_t* hits, int32_t* uniq, const uint8_t* tmaps) {
     const int smem = pv_smem_bytes(THREADS, PPT, CTAS, SPLIT, NCH);
     auto kfn = point_votes_tab_kernel<THREADS, PPT, CTAS, SPLIT, NCH>;
     static bool configured[S2D_MAX_DEVICES] = {};
@@ -1160,8 +1063,202 @@ static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, 
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, THREADS, smem);
     if (per_sm < 1) per_sm = 1;
-    kfn<<<nsm * per_sm, THREADS, smem, st>>>(descs, rowplan, total_rows, ctrl, hits, uniq, tmaps, bmap, bmap_off);
+    kfn<<<nsm * per_sm, THREADS, smem, st>>>(descs, rowplan, total_rows, ctrl, hits, uniq, tmaps);
     S2D_CHECK_LAUNCH("point_votes_tab_kernel");
+    return 0;
+}
+
+// ==========================================================================================
+// K2 for sparse tiles (P <= 1024 tracked points per query): ONE WARP PER TILE.
+//
+// The label-table kernel above spends about 2 200 warp-instructions of fixed work on every tile (plan by one warp while
+// three wait, five block-wide barriers, a 256-bin output pass by four warps, the table fetch): for a 4096-point tile that
+// is 40 % on top of the per-point work, for a 1024-point tile it is twice the per-point work, and the kernel ends up
+// bound by instruction issue at a third of the HBM roofline (ncu: 3 504 instructions per 8 KB tile). Here a tile belongs
+// to one warp of a one-warp CTA - no block barriers, no idle warps, ~15 tiles in flight per SM:
+//   * the tile's 8 P bytes of tracks land in the warp's 8 KB of shared memory by one cp.async.bulk (mbarrier), the next
+//     tile's copy is issued as soon as the points sit in registers (32 per lane, packed (iy << 16) | ix);
+//   * the bounding box comes from packed 16-bit min / max and four warp reductions;
+//   * de-duplication is a bitmap of the bounding box in shared memory (4 KB = 32 768 pixels per band, bit index =
+//     dy * bw + dx - band base; larger boxes take several bands), claimed with one shared atomic per point;
+//   * the first point on a pixel reads the pixel's label straight from the label map (L2): eight independent loads in
+//     flight per lane, and points arrive close to raster order, so a warp-wide load touches a handful of sectors;
+//   * votes are shared-memory reductions into the warp's own 256-bin histogram, which one pass writes to hits / uniq.
+// Any label id (0..255) and any box size are handled by this one path; results are identical to the other kernels'.
+// ==========================================================================================
+constexpr int PVW_BITS = 32768;                                     // bitmap bits per band
+constexpr int PVW_TRK_BYTES = 8192;                                 // 1024 points
+constexpr int PVW_CTL_OFF = 1152, PVW_TRK_OFF = 1536, PVW_BITS_OFF = PVW_TRK_OFF + PVW_TRK_BYTES;
+constexpr int PVW_SMEM_BYTES = PVW_BITS_OFF + PVW_BITS / 8;         // hist 1 KB | dummy 128 B | control | tracks | bitmap
+constexpr int PVW_G = 8;                                            // points per lane whose atomics / loads are issued together
+
+struct PvwCtl { uint64_t full; PvTile tinfo[2]; };
+static_assert(sizeof(PvwCtl) <= PVW_TRK_OFF - PVW_CTL_OFF, "PvwCtl must fit its slot");
+
+__global__ void __launch_bounds__(32, 15)
+point_votes_warp_kernel(const s2d_video_desc* __restrict__ descs, const int4* __restrict__ rowplan, int total_rows,
+                        int32_t* __restrict__ ctrl, int32_t* __restrict__ hits, int32_t* __restrict__ uniq) {
+    extern __shared__ __align__(1024) uint8_t dsm[];
+    int* const hist = reinterpret_cast<int*>(dsm);
+    uint32_t* const dummy = reinterpret_cast<uint32_t*>(dsm + 1024);
+    PvwCtl& ctl = *reinterpret_cast<PvwCtl*>(dsm + PVW_CTL_OFF);
+    uint8_t* const trk = dsm + PVW_TRK_OFF;
+    uint32_t* const bits = reinterpret_cast<uint32_t*>(dsm + PVW_BITS_OFF);
+    const int lane = threadIdx.x;
+    const int total = ctrl[1];
+
+#pragma unroll
+    for (int i = lane; i < S2D_MAX_LABELS; i += 32) hist[i] = 0;
+    dummy[lane] = 0xFFFFFFFFu;
+    if (lane == 0) {
+        mbar_init(&ctl.full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    auto issue_tracks = [&](const PvTile* rec) {        // lane 0: the tile's tracks -> shared memory, completion on `full`
+        const uint32_t bytes = (uint32_t)rec->pad * 8u;
+        mbar_expect_tx(&ctl.full, bytes);
+        bulk_g2s_hint(trk, rec->src, bytes, &ctl.full, l2_policy_evict_first());
+    };
+    PvPlan pl;
+    pl.pi = pl.pi_end = pl.prow = 0;
+    pl.prp = make_int4(0, 0, 0, 0);
+    const float* unused_src = nullptr;
+    bool more = pv_plan_next(pl, &ctl.tinfo[0], lane, descs, rowplan, total_rows, total, ctrl, hits, uniq, nullptr, &unused_src);
+    __syncwarp();
+    if (lane == 0 && more) issue_tracks(&ctl.tinfo[0]);
+
+    const uint32_t hist_s = __shfl_sync(0xffffffffu, smem_u32(dsm), 0);
+    if (hist_s & 1023u) __trap();                       // a bin's address is formed as (4 * label) | hist_s
+    const uint32_t bits_s = hist_s + (uint32_t)PVW_BITS_OFF;
+    const uint32_t dummy_s = hist_s + 1024u + 4u * (uint32_t)lane;
+    int scur = 0;
+    for (int j = 0;; ++j) {
+        const PvTile* ti = &ctl.tinfo[scur];
+        if (!ti->valid) break;
+        const uint32_t W = ti->W, H = ti->H;
+        if (W > 65535u || H > 65535u) __trap();        // packed 16-bit coordinates (documented limit)
+        const int n = ti->n, L = ti->L;
+        const uint8_t* const lbl = ti->lbl;
+        int32_t* const hout = ti->hout;
+        int32_t* const uout = ti->uout;
+        S2D_DEV_ASSERT(ti->pad >= 1 && ti->pad <= 1024 && n <= ti->pad);
+
+        // the next tile's record is prepared while this tile's tracks are in flight (the plan is a chain of global loads)
+        more = pv_plan_next(pl, &ctl.tinfo[scur ^ 1], lane, descs, rowplan, total_rows, total, ctrl, hits, uniq, nullptr, &unused_src);
+
+        // ---- phase A: shared memory -> registers, round / bounds / pack ------------------------------
+        mbar_wait(&ctl.full, (uint32_t)j & 1u);
+        // lane l holds points 64 k + 2 l, + 1 (k = 0..15): rows k < kfull are complete, row kfull may be ragged (n points)
+        const int kfull = n >> 6, kmax = (n + 63) >> 6;
+        uint32_t pk[32];
+        const float4* sp = reinterpret_cast<const float4*>(trk);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            uint32_t a = PV_PK_INVALID, b = PV_PK_INVALID;
+            if (k < kfull) {
+                const float4 v = sp[k * 32 + lane];
+                a = pv_pack(v.x, v.y, W, H);
+                b = pv_pack(v.z, v.w, W, H);
+            } else if (k < kmax) {
+                const float4 v = sp[k * 32 + lane];
+                const int p0 = 2 * (k * 32 + lane);
+                if (p0 < n) a = pv_pack(v.x, v.y, W, H);
+                if (p0 + 1 < n) b = pv_pack(v.z, v.w, W, H);
+            }
+            pk[2 * k] = a;
+            pk[2 * k + 1] = b;
+        }
+        __syncwarp();                                   // every lane has read the tracks: the region is free again
+        if (lane == 0 && more) issue_tracks(&ctl.tinfo[scur ^ 1]);
+
+        // ---- bounding box ------------------------------------------------------------------------------
+        uint32_t mn = 0xFFFFFFFFu, mx = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            // per-halfword min / max; an invalid point is (0xFFFF, 0xFFFF) for the min and, after the
+            // +0x00010001, (1, 0) for the max: harmless, any valid point has iy + 1 >= 1
+            mn = __vimin3_u16x2(mn, pk[2 * k], pk[2 * k + 1]);
+            mx = __vimax3_u16x2(mx, pk[2 * k] + 0x00010001u, pk[2 * k + 1] + 0x00010001u);
+        }
+        const uint32_t x0 = __reduce_min_sync(0xffffffffu, mn & 0xFFFFu), y0 = __reduce_min_sync(0xffffffffu, mn >> 16);
+        const uint32_t x1 = __reduce_max_sync(0xffffffffu, mx & 0xFFFFu), y1 = __reduce_max_sync(0xffffffffu, mx >> 16);
+        if (((y0 << 16) | x0) != 0xFFFFFFFFu) {         // at least one point inside the frame
+            const uint32_t bw = x1 - x0, bh = y1 - y0;  // the max holds coordinate + 1
+            S2D_DEV_ASSERT(bw >= 1 && bh >= 1 && x0 + bw <= W && y0 + bh <= H);
+            const uint32_t pk0 = (y0 << 16) + x0, lim = bh << 16;
+            const uint32_t npx = bw * bh;               // <= W * H < 2^32
+            const uint32_t org = y0 * W + x0;           // pixel index of the box's corner
+            for (uint32_t base = 0; base < npx; base += (uint32_t)PVW_BITS) {
+                // an opaque copy of pk0 per band: without it the compiler hoists the 32 points' band-invariant terms (bit
+                // index, label address: ~100 registers) out of this loop, which has one iteration for most tiles
+                uint32_t pk0b;
+                asm volatile("mov.u32 %0, %1;" : "=r"(pk0b) : "r"(pk0));
+                const uint32_t nq = (min((uint32_t)PVW_BITS, npx - base) + 127u) >> 7;      // 128-bit words to clear
+                for (uint32_t i = lane; i < nq; i += 32) reinterpret_cast<uint4*>(bits)[i] = make_uint4(0, 0, 0, 0);
+                __syncwarp();
+#pragma unroll
+                for (int g = 0; g < 32; g += PVW_G) {
+                    if (g / 2 >= kmax) break;           // no points beyond (uniform)
+                    // (1) claim the pixels: points outside the frame / the band hit a per-lane dummy word that is all ones
+                    uint32_t first = 0;
+#pragma unroll
+                    for (int k = 0; k < PVW_G; ++k) {
+                        const uint32_t e = pk[g + k] - pk0b;                   // (dy << 16) + dx of a valid point
+                        const uint32_t lin = (e >> 16) * bw + (e & 0xFFFFu) - base;
+                        const bool ok = (e < lim) && (lin < (uint32_t)PVW_BITS);
+                        S2D_DEV_ASSERT(!(e < lim) || (e & 0xFFFFu) < bw);
+                        const uint32_t m = 1u << (lin & 31u);
+                        const uint32_t addr = ok ? bits_s + ((lin >> 5) << 2) : dummy_s;
+                        uint32_t old;
+                        asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(m) : "memory");
+                        first |= ((old & m) ? 0u : 1u) << k;
+                    }
+                    // (2) labels of the first points: independent loads, all issued before the first is used
+                    uint32_t lab[PVW_G];
+#pragma unroll
+                    for (int k = 0; k < PVW_G; ++k) {
+                        lab[k] = 0;
+                        if ((first >> k) & 1u) {
+                            const uint32_t e = pk[g + k] - pk0b;
+                            S2D_DEV_ASSERT((e >> 16) < bh && (e & 0xFFFFu) < bw);
+                            lab[k] = __ldg(lbl + (size_t)(org + (e >> 16) * W + (e & 0xFFFFu)));
+                        }
+                    }
+                    // (3) votes
+#pragma unroll
+                    for (int k = 0; k < PVW_G; ++k)
+                        if ((first >> k) & 1u) asm volatile("red.shared.add.u32 [%0], 1;" :: "r"((lab[k] << 2) | hist_s) : "memory");
+                }
+                if (base + (uint32_t)PVW_BITS < npx) __syncwarp();             // the next band clears the bitmap
+            }
+        }
+        __syncwarp();                                   // histogram complete
+
+        // ---- output: hits[q, t, :] and uniq[q, t] = number of distinct pixels --------------------------------
+        int sum = 0;
+#pragma unroll
+        for (int b = lane; b < S2D_MAX_LABELS; b += 32) {
+            const int h = hist[b];
+            if (b < L) hout[b] = h;
+            hist[b] = 0;
+            sum += h;
+        }
+        sum = __reduce_add_sync(0xffffffffu, sum);
+        if (lane == 0) *uout = sum;
+        __syncwarp();                                   // histogram resets before the next tile's votes
+        scur ^= 1;
+    }
+}
+
+static int launch_pv_warp(cudaStream_t st, int nsm, const s2d_video_desc* descs, const int4* rowplan, int total_rows,
+                          int32_t* ctrl, int32_t* hits, int32_t* uniq) {
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, point_votes_warp_kernel, 32, PVW_SMEM_BYTES);
+    if (per_sm < 1) per_sm = 1;
+    point_votes_warp_kernel<<<nsm * per_sm, 32, PVW_SMEM_BYTES, st>>>(descs, rowplan, total_rows, ctrl, hits, uniq);
+    S2D_CHECK_LAUNCH("point_votes_warp_kernel");
     return 0;
 }
 
@@ -1205,9 +1302,9 @@ static int g_pv_variant = 0;
 
 extern "C" int s2d_point_votes_variant(int variant) {
 #ifdef S2D_EXPERIMENTS
-    S2D_CHECK_ARG(variant >= 0 && variant <= 2, "s2d_point_votes_variant: %d not in {0 label table, 1 bitmap, 2 one CTA per tile}", variant);
+    S2D_CHECK_ARG(variant >= 0 && variant <= 3, "s2d_point_votes_variant: %d not in {0 product dispatch, 1 bitmap, 2 one CTA per tile, 3 label table for every P}", variant);
 #else
-    S2D_CHECK_ARG(variant == 0 || variant == 2, "s2d_point_votes_variant: %d not in {0 label table, 2 one CTA per tile} "
+    S2D_CHECK_ARG(variant == 0 || variant == 2 || variant == 3, "s2d_point_votes_variant: %d not in {0 product dispatch, 2 one CTA per tile, 3 label table for every P} "
                   "(1, the superseded bitmap kernel, exists only in the experiments build: make -C s2d_b200/csrc exp)", variant);
 #endif
     g_pv_variant = variant;
@@ -1272,15 +1369,6 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
                                int vec4_ok, int64_t total_rows, const int32_t* rowinfo,
                                const int32_t* vidinfo, int32_t* work, const void* label_tmaps,
                                int32_t* hits, int32_t* uniq, void* stream) {
-    return s2d_point_votes_bm(descs, nvideos, max_T, max_Nm, max_P, vec4_ok, total_rows, rowinfo, vidinfo, work, label_tmaps,
-                              nullptr, nullptr, hits, uniq, stream);
-}
-
-extern "C" int s2d_point_votes_bm(const s2d_video_desc* descs, int nvideos, int max_T, int max_Nm, int max_P,
-                                  int vec4_ok, int64_t total_rows, const int32_t* rowinfo,
-                                  const int32_t* vidinfo, int32_t* work, const void* label_tmaps,
-                                  const uint8_t* bmap, const int64_t* bmap_off,
-                                  int32_t* hits, int32_t* uniq, void* stream) {
     S2D_ENTER(stream);
     S2D_CHECK_ARG((((uintptr_t)label_tmaps) & 63) == 0, "s2d_point_votes: label_tmaps must be 64-byte aligned");
     const uint8_t* tm = static_cast<const uint8_t*>(label_tmaps);
@@ -1290,7 +1378,8 @@ extern "C" int s2d_point_votes_bm(const s2d_video_desc* descs, int nvideos, int 
     S2D_CHECK_ARG(max_P >= 1 && max_P <= 32768, "s2d_point_votes: P=%d not in [1, 32768]", max_P);
     cudaStream_t st = (cudaStream_t)stream;
     const bool v4 = vec4_ok != 0;
-    const int variant = g_pv_variant;
+    const bool warp_tiles = g_pv_variant != 3;      // variant 3: the label-table kernel also for tiles of <= 1024 points
+    const int variant = g_pv_variant == 3 ? 0 : g_pv_variant;
     if (variant != 2 && v4 && work && max_P <= (variant == 0 ? 16384 : 8192) && total_rows > 0 && total_rows <= 2147483647LL) {
         // persistent TMA path
         S2D_CHECK_ARG((((uintptr_t)work) & 15) == 0, "s2d_point_votes: work must be 16-byte aligned");
@@ -1316,17 +1405,14 @@ extern "C" int s2d_point_votes_bm(const s2d_video_desc* descs, int nvideos, int 
             if (max_P <= 128 * 8 && getenv("S2D_PV_SMALL")) {
                 const int v = atoi(getenv("S2D_PV_SMALL"));
                 if (v == 60) return launch_pv_tab<128, 8, 6, false>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
-                if (v == 6) return launch_pv_tab<128, 8, 6, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
-                if (v == 7) return launch_pv_tab<128, 8, 7, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
-                if (v == 8) return launch_pv_tab<128, 8, 8, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
-                if (v == 9) return launch_pv_tab<128, 8, 9, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
-                if (v == 1608) return launch_pv_tab<64, 16, 8, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
-                if (v == 1610) return launch_pv_tab<64, 16, 10, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
-                if (v == 1612) return launch_pv_tab<64, 16, 12, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
-                if (v == 408) return launch_pv_tab<256, 4, 4, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
+                if (v == 6) return launch_pv_tab<128, 8, 6, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                if (v == 7) return launch_pv_tab<128, 8, 7, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                if (v == 8) return launch_pv_tab<128, 8, 8, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
+                if (v == 9) return launch_pv_tab<128, 8, 9, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
             }
 #endif
-            if (max_P <= 128 * 8) return launch_pv_tab<128, 8, 6, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm, bmap, bmap_off);
+            if (max_P <= 128 * 8 && warp_tiles) return launch_pv_warp(st, nsm, descs, rowplan, tr, ctrl, hits, uniq);
+            if (max_P <= 128 * 8) return launch_pv_tab<128, 8, 7, true>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
             if (max_P <= 128 * 16) return launch_pv_tab<128, 16, 6>(st, nsm, descs, rowplan, tr, ctrl, hits, uniq, tm);
 #ifdef S2D_EXPERIMENTS   // CTAs per SM of the 4096-point configuration (A/B runs; 6 x 128 threads is the measured best)
             if (max_P <= 256 * 16) {

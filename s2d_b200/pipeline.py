@@ -61,7 +61,7 @@ class Batch:
     only enqueues kernels, so a Batch can be re-run (benchmarks) without touching the allocator."""
 
     def __init__(self, videos: List[VideoInput], device=None, stages: str = "LVBD", persistent_votes: bool = True,
-                 label_tmaps: bool = True, gram_min_rows: int = 2048, block_maps: bool = True):
+                 label_tmaps: bool = True, gram_min_rows: int = 2048):
         """`persistent_votes=False` runs K2 as one CTA per tile (the library's fallback for odd P / unaligned
         tracks), `label_tmaps=False` makes the persistent kernel fetch its label tables row by row instead of as TMA
         boxes; both exist for tests and profiling comparisons, the defaults are the product path."""
@@ -167,8 +167,6 @@ class Batch:
             self.majbits, self.rsbits, self.rebits, self.winbits = z(xw), z(xw), z(xw), z(xw)
         self.pvwork = self.pvtmaps = self.hits = self.uniq = self.mbits = self.one2x = self.nmatch = None
         self.grpwork = self.glabel = self.grp_n = self.grp_one2x = None
-        self.bmap = self.bmap_off = None
-        self.max_bm_blocks = 0
         if "D" in st:
             _lib.call("s2d_point_votes_work_ints", row0, C.byref(n))
             self.pvwork = z(n.value + 4)
@@ -178,17 +176,6 @@ class Batch:
                 _lib.call("s2d_point_votes_tmaps", descs, nv, hbuf.ctypes.data)
                 self.pvtmaps = torch.from_numpy(hbuf).to(dev)
                 assert self.pvtmaps.data_ptr() % 64 == 0
-            # block-summary label maps for the sparse tiles of batches with <= 1024 points per query (include/s2d_b200.h)
-            if (block_maps and persistent_votes and self.vec4 and self.max_P <= 1024
-                    and all(v.labels is not None for v in videos)):
-                offs, tot = [], 0
-                for i in range(nv):
-                    _lib.call("s2d_label_blockmap_bytes", descs[i].T, descs[i].H, descs[i].W, C.byref(n))
-                    offs.append(tot)
-                    tot += n.value
-                    self.max_bm_blocks = max(self.max_bm_blocks, n.value // descs[i].T + 16)
-                self.bmap = torch.empty(tot, dtype=torch.uint8, device=dev)
-                self.bmap_off = torch.tensor(offs, dtype=torch.int64, device=dev)
             self.hits = z(hits)
             self.uniq = z(vt)
             self.mbits = z(mw)
@@ -263,12 +250,9 @@ class Batch:
                  p(self.rsbits), p(self.rebits), p(self.winbits), p(self.rowinfo), p(self.vidinfo),
                  p(self.clusterinfo), st)
         if "D" in stages:
-            if self.bmap is not None:
-                call("point_votes", 1, "s2d_label_blockmap", d, nv, self.max_T, self.max_bm_blocks, p(self.bmap), p(self.bmap_off), st)
-            call("point_votes", 3 if self.use_tma else 1, "s2d_point_votes_bm", d, nv, self.max_T, self.max_Nm, self.max_P,
+            call("point_votes", 3 if self.use_tma else 1, "s2d_point_votes", d, nv, self.max_T, self.max_Nm, self.max_P,
                  self.vec4, self.total_rows, p(self.rowinfo), p(self.vidinfo),
-                 p(self.pvwork) if self.use_tma else None, p(self.pvtmaps), p(self.bmap), p(self.bmap_off),
-                 p(self.hits), p(self.uniq), st)
+                 p(self.pvwork) if self.use_tma else None, p(self.pvtmaps), p(self.hits), p(self.uniq), st)
             call("select", 1, "s2d_select", d, nv, self.max_Nm, self.total_mw, p(self.hits), p(self.uniq),
                  p(self.gid_of), p(self.rowinfo), params.matching_threshold, params.one2x_iou,
                  params.one2x_frames, p(self.mbits), p(self.one2x), p(self.nmatch), p(self.vidinfo), st)
@@ -305,13 +289,10 @@ class Batch:
     def votes_all(self, stream=None):
         """K2 over every (query, frame) of every video, ignoring candidates/status (tests, bench)."""
         st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
-        pb = lambda t: t.data_ptr() if t is not None else None
-        if self.bmap is not None:
-            _lib.call("s2d_label_blockmap", self.descs.data_ptr(), self.nv, self.max_T, self.max_bm_blocks, pb(self.bmap),
-                      pb(self.bmap_off), st)
-        _lib.call("s2d_point_votes_bm", self.descs.data_ptr(), self.nv, self.max_T, self.max_Nm, self.max_P, self.vec4,
+        _lib.call("s2d_point_votes", self.descs.data_ptr(), self.nv, self.max_T, self.max_Nm, self.max_P, self.vec4,
                   self.total_rows, None, None, self.pvwork.data_ptr() if self.use_tma else None,
-                  pb(self.pvtmaps), pb(self.bmap), pb(self.bmap_off), self.hits.data_ptr(), self.uniq.data_ptr(), st)
+                  self.pvtmaps.data_ptr() if self.pvtmaps is not None else None,
+                  self.hits.data_ptr(), self.uniq.data_ptr(), st)
 
     # ------------------------------------------------------------------ results
     def fetch_summary(self):

@@ -113,10 +113,8 @@ def list_digest(results: Sequence[dict]) -> str:
 class DeviceRunner:
     """Runs a list of VideoSpec through the device pipeline in chunks that fit `budget_bytes` of HBM."""
 
-    def __init__(self, device, params: Params = Params(), budget_bytes: float = 110e9, point_order: str = "raster",
-                 block_maps: bool = True):
+    def __init__(self, device, params: Params = Params(), budget_bytes: float = 110e9, point_order: str = "raster"):
         self.device = torch.device(device)
-        self.block_maps = block_maps          # False: A/B runs of the votes kernel's sparse-tile mode (bench.py --no-block-maps)
         self.params = params
         self.budget = float(budget_bytes)
         self.point_order = point_order
@@ -153,7 +151,7 @@ class DeviceRunner:
                     scenes.append(sc)
                     vids.append(VideoInput(sc["labels"], sc["tracks"], sc["vis"], tstart=sc.get("tstart"), vis_bits=s.vis_bits,
                                            max_label=s.M, name=s.name))
-                batch = Batch(vids, device=dev, block_maps=self.block_maps)
+                batch = Batch(vids, device=dev)
                 windowed = any(specs[i].window > 0 for i in idx)
                 host = {k: torch.empty(getattr(batch, k).shape, dtype=getattr(batch, k).dtype, pin_memory=True)
                         for k in ("vidinfo", "clusterinfo", "rowinfo", "glabel", "one2x")}

@@ -92,7 +92,7 @@ def test_point_votes_all_pairs_vs_oracle(golden_case):
         assert np.array_equal(h, hits[q]), (name, q)
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["table", "bitmap", "cta_per_tile"])
+@pytest.fixture(params=[0, 1, 2, 3], ids=["product", "bitmap", "cta_per_tile", "table_any_P"])
 def pv_variant(request):
     """run a test once per point-votes kernel variant (include/s2d_b200.h: s2d_point_votes_variant)"""
     from s2d_b200 import _lib
@@ -177,91 +177,43 @@ def test_point_votes_scene_geometry(H, W, P, M, lab255, off, pv_variant):
         assert np.array_equal(h, hits[q]), q
 
 
-@pytest.mark.parametrize("T,H,W,off", [(3, 480, 854, 0), (2, 33, 1900, 5), (2, 97, 131, 3), (2, 720, 1280, 16), (1, 5, 5, 0),
-                                       (2, 64, 66, 1)])
-def test_label_blockmap_kernel_vs_host_model(T, H, W, off):
-    """s2d_label_blockmap (block-summary maps of the votes kernel's sparse-tile mode) against the numpy model of
-    tests/test_k2_blockmap_model.py: widths / heights that are not multiples of 4, label maps on odd byte offsets,
-    label 255 in use (such blocks read as mixed), two videos of different shapes in one call."""
-    import ctypes as C
-    from s2d_b200 import _lib
-    from s2d_b200.pipeline import Batch, VideoInput
-    from tests.test_k2_blockmap_model import blockmap_model, bm_pitch, bm_rows
-    rng = np.random.default_rng(H + W)
-    d = _dev()
-
-    def make(T, H, W, off, seed):
-        r = np.random.default_rng(seed)
-        lab = np.zeros((T, H, W), np.uint8)
-        for t in range(T):
-            for k in range(1, 9):
-                y, x = r.integers(0, H), r.integers(0, W)
-                lab[t, y:y + r.integers(1, H // 2 + 2), x:x + r.integers(1, W // 2 + 2)] = k if k < 8 else 255
-            lab[t][r.random((H, W)) < 0.01] = 9
-        raw = torch.zeros(lab.size + 64, dtype=torch.uint8, device=d)
-        raw[off:off + lab.size] = torch.from_numpy(lab.reshape(-1)).to(d)
-        P = 64
-        tracks = torch.zeros((2, T, P, 2), dtype=torch.float32, device=d)
-        vis = torch.zeros((2, T, P), dtype=torch.uint8, device=d)
-        return lab, VideoInput(labels=raw[off:off + lab.size].view(lab.shape), tracks=tracks, vis=vis, max_label=255)
-
-    l0, v0 = make(T, H, W, off, 1)
-    l1, v1 = make(2, 40, 52, 0, 2)
-    b = Batch([v0, v1])
-    assert b.bmap is not None
-    b.bmap.fill_(0x5A)
-    _lib.call("s2d_label_blockmap", b.descs.data_ptr(), b.nv, b.max_T, b.max_bm_blocks, b.bmap.data_ptr(), b.bmap_off.data_ptr(),
-              torch.cuda.current_stream(d).cuda_stream)
-    torch.cuda.synchronize()
-    got = b.bmap.cpu().numpy()
-    offs = b.bmap_off.cpu().numpy()
-    n = C.c_int64()
-    for i, lab in enumerate((l0, l1)):
-        Tt, Hh, Ww = lab.shape
-        _lib.call("s2d_label_blockmap_bytes", Tt, Hh, Ww, C.byref(n))
-        assert n.value >= Tt * bm_rows(Hh) * bm_pitch(Ww) and n.value % 16 == 0 and offs[i] % 16 == 0
-        mine = got[offs[i]:offs[i] + Tt * bm_rows(Hh) * bm_pitch(Ww)].reshape(Tt, bm_rows(Hh), bm_pitch(Ww))
-        for t in range(Tt):
-            assert np.array_equal(mine[t], blockmap_model(lab[t])), (i, t)
-
-
-@pytest.mark.parametrize("H,W,P,M,spread,off", [(480, 854, 1000, 10, False, 5), (480, 864, 1024, 12, False, 0),
-                                                (1080, 1920, 1024, 30, False, 0), (1080, 1920, 512, 6, True, 0),
-                                                (97, 131, 256, 5, False, 3), (240, 426, 1024, 8, True, 0)])
-def test_point_votes_block_maps_equal_table_path(H, W, P, M, spread, off):
-    """Sparse tiles (P <= 1024): the block-summary-map mode of the votes kernel against the label-table mode of the same
-    kernel and against the oracle - object-shaped clouds (the mode's main path), clouds spread over the whole frame (1080p:
-    the box does not fit the buffer, the tile keeps the table / bitmap path), unaligned label maps."""
-    from s2d_b200.pipeline import Batch, VideoInput
-    from s2d_b200.synth import make_scene
-    sc = make_scene(77 + H + P, 4, H, W, M, P, specials=True, dup_rate=0.05)
-    tracks = sc.tracks.copy()
+@pytest.mark.parametrize("H,W,P,nlab,spread", [(1080, 1920, 1024, 256, True), (1080, 1920, 256, 40, True), (480, 854, 1000, 256, False),
+                                                (720, 1280, 1024, 21, False), (64, 64, 1024, 7, True), (33, 1900, 2, 5, True)])
+def test_point_votes_sparse_tiles_warp_kernel(H, W, P, nlab, spread, pv_variant):
+    """Tiles of <= 1024 points (one warp per tile in the product dispatch): boxes of many bitmap bands (points spread over
+    a 1080p frame), every label id in use (255 included), heavy duplication (P >> pixels of the box), P = 2, ragged point
+    counts; the same inputs through the other variants."""
+    from s2d_b200.pipeline import Batch
+    rng = np.random.default_rng(H + P + nlab)
+    T, Nm = 3, 6
+    labels = rng.integers(0, nlab, size=(T, H, W)).astype(np.uint8)
+    labels[:, : H // 2, : W // 2] = nlab - 1
+    tracks = np.empty((Nm, T, P, 2), np.float32)
     if spread:
-        rng = np.random.default_rng(3)
-        tracks[::2, :, :, 0] = rng.uniform(-5, W + 5, size=tracks[::2, :, :, 0].shape)
-        tracks[::2, :, :, 1] = rng.uniform(-5, H + 5, size=tracks[::2, :, :, 1].shape)
-    d = _dev()
-    labels = sc.labels
-    raw = torch.zeros(labels.size + 64, dtype=torch.uint8, device=d)
-    raw[off:off + labels.size] = torch.from_numpy(labels.reshape(-1)).to(d)
-    lab_dev = raw[off:off + labels.size].view(labels.shape)
-    maxlab = int(labels.max())
-    out = []
-    for on in (True, False):
-        vid = VideoInput(labels=lab_dev, tracks=torch.from_numpy(tracks).to(d), vis=torch.from_numpy(sc.vis).to(d), max_label=maxlab)
-        b = Batch([vid], block_maps=on)
-        assert (b.bmap is not None) == on
-        b.hits.fill_(-3); b.uniq.fill_(-3)
-        b.votes_all()
-        torch.cuda.synchronize()
-        out.append((b.hits.cpu().numpy().copy(), b.uniq.cpu().numpy().copy()))
-    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
-    Nm, T = tracks.shape[:2]
-    L = maxlab + 1
-    hits, uniq = out[0][0].reshape(Nm, T, L), out[0][1].reshape(Nm, T)
-    for q in range(0, Nm, max(1, Nm // 24)):
-        h, u = ko.point_votes(tracks[q], labels, 0, T - 1, nbins=L)
-        assert np.array_equal(u, uniq[q]) and np.array_equal(h, hits[q]), q
+        tracks[..., 0] = rng.uniform(-20, W + 20, size=(Nm, T, P))
+        tracks[..., 1] = rng.uniform(-20, H + 20, size=(Nm, T, P))
+    else:                                           # object-sized clouds around a centre per (query, frame)
+        cx = rng.uniform(0.2 * W, 0.8 * W, size=(Nm, T, 1)); cy = rng.uniform(0.2 * H, 0.8 * H, size=(Nm, T, 1))
+        tracks[..., 0] = cx + rng.normal(0, 0.06 * W, size=(Nm, T, P))
+        tracks[..., 1] = cy + rng.normal(0, 0.07 * H, size=(Nm, T, P))
+        tracks[..., 0].sort(axis=-1)
+    tracks[1, 1, ::5, 0] = np.nan
+    tracks[2, :, :, :] = np.round(tracks[2]) + 0.5
+    tracks[3, 0] = tracks[3, 0, 0]                  # all points on one pixel
+    tracks[4, 2, :, 1] = -7                         # nothing inside the frame
+    vis = rng.integers(0, 2, size=(Nm, T, P)).astype(np.uint8)
+    v = _video(labels, tracks, vis, max_label=nlab - 1)
+    npts = np.asarray([P, P, P, P, P, max(P - 3, 0)], np.int32)
+    v.npts = torch.from_numpy(npts).to(_dev())
+    b = Batch([v])
+    b.hits.fill_(-5); b.uniq.fill_(-5)
+    b.votes_all()
+    torch.cuda.synchronize()
+    hits = b.hits.cpu().numpy().reshape(Nm, T, nlab)
+    uniq = b.uniq.cpu().numpy().reshape(Nm, T)
+    for q in range(Nm):
+        h, u = ko.point_votes(tracks[q][:, : int(npts[q])], labels, 0, T - 1, nbins=nlab)
+        assert np.array_equal(u, uniq[q]) and np.array_equal(h, hits[q]), (q, u, uniq[q])
 
 
 def test_ragged_npts(pv_variant):

@@ -130,6 +130,31 @@ def test_coco_rle_restatement_known_answers_and_roundtrip():
     assert codec.from_string(codec.to_string(big)) == big
 
 
+def test_coco_rle_counts_vs_third_party_encoder():
+    """The run counts of oracle/coco_rle.py (the comparator of the GPU encoder, row f2) against an implementation that is
+    not ours: transformers' SAM post-processing `_mask_to_rle` ("in the format expected by pycoco tools": column-major
+    runs, leading zero run, `size` = [h, w]) - the uncompressed form pycocotools' frPyObjects accepts. pycocotools itself
+    is not installable here, so this pins the counts to a second, independent restatement of the COCO convention; the
+    string codec stays pinned by the hand-derived answers above."""
+    torch = pytest.importorskip("torch")
+    sam = pytest.importorskip("transformers.models.sam.image_processing_sam")
+    from oracle import coco_rle as cr
+    rng = np.random.default_rng(11)
+    masks = [np.zeros((7, 5), np.uint8), np.ones((7, 5), np.uint8)]
+    for h, w, p in [(1, 1, 0.5), (5, 7, 0.4), (33, 64, 0.1), (120, 97, 0.7), (64, 64, 0.02)]:
+        masks.append((rng.random((h, w)) < p).astype(np.uint8))
+    blob = np.zeros((90, 130), np.uint8)
+    yy, xx = np.mgrid[:90, :130]
+    blob[((yy - 40) / 25.0) ** 2 + ((xx - 70) / 40.0) ** 2 <= 1.0] = 1      # an object-shaped mask
+    blob[0, 0] = 1                                                           # starts set: leading zero-length run
+    masks.append(blob)
+    for m in masks:
+        theirs = sam._mask_to_rle(torch.from_numpy(m.astype(bool))[None])[0]
+        assert theirs["size"] == list(m.shape)
+        assert [int(c) for c in theirs["counts"]] == cr.counts(m), m.shape
+        assert cr.area(m) == int(m.sum()) == sum(int(c) for c in theirs["counts"][1::2])
+
+
 def test_colour_to_label_rule_vs_reference_golden():
     """f1: the product's host rule for colour-coded mask frames (rank of the RGB tuple among the frame's non-black
     colours, lexicographic) against outputs of the unmodified reference's convert_lblimg_to_maskid
