@@ -311,7 +311,7 @@ def main():
     achieved = alg_bytes / (k2_ms / 1000.0) / 1e9
     vr_bytes = sum(d.Nm * d.T * d.P + 8 * d.Nm * d.T for d in batch.host_descs)
     pv_name = ("point_votes_warp_kernel (persistent, one warp per tile: tracks by cp.async.bulk, bitmap of the bounding box in "
-               "shared memory, labels of first points straight from the label map)" if batch.use_tma and batch.vec4 and P <= 1024
+               "shared memory, labels of first points straight from the label map)" if batch.use_tma and batch.vec4 and P <= 1024 and H * W <= 524288
                else "point_votes_tab_kernel (persistent; tile's tracks by cp.async.bulk, bbox of the label map by TMA "
                "boxes into the same smem buffer, one shared atomic per point)" if batch.use_tma and batch.vec4 and P <= 16384
                else "point_votes_kernel (one CTA per tile)")

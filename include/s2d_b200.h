@@ -167,14 +167,23 @@ int s2d_windows(const s2d_video_desc* descs, int nvideos, int64_t max_rows_x_TW,
  * a multiple of 16 get no descriptors and keep the row-by-row fetch. */
 #define S2D_PV_TMAPS 32                            /* box widths 16, 32, ... 512 pixels, 16 rows each */
 #define S2D_PV_TMAP_BYTES (S2D_PV_TMAPS * 128 + 128)
-int s2d_point_votes_variant(int variant);   /* process-wide; 0 product dispatch (one warp per tile for P <= 1024, label
-                                             * table above), 2 one CTA per tile, 3 label table for every P (1, the
-                                             * superseded bitmap kernel, only exists in the experiments build: make exp) */
+int s2d_point_votes_variant(int variant);   /* process-wide, for tests and A/B runs; 0 product dispatch, 2 one CTA per tile,
+                                             * 3 label table for every P, 4 one warp per tile for every frame size (P <= 1024)
+                                             * (1, the superseded bitmap kernel, only exists in the experiments build: make exp) */
 int s2d_point_votes_work_ints(int64_t total_rows, int64_t* out);
 int s2d_point_votes_tmaps(const s2d_video_desc* host_descs, int nvideos, void* host_out);
 int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max_T, int max_Nm, int max_P,
                     int vec4_ok, int64_t total_rows, const int32_t* rowinfo, const int32_t* vidinfo,
                     int32_t* work, const void* label_tmaps, int32_t* hits, int32_t* uniq, void* stream);
+
+/* s2d_point_votes with the size of the largest frame of the batch (H * W pixels; 0 = unknown = s2d_point_votes): batches of
+ * <= 1024 tracked points per query on frames of up to 512 Ki pixels (480 x 854) run the one-warp-per-tile kernel instead of
+ * the label-table kernel (measured: 40 % instead of 31 % of the HBM copy peak on 480p videos; larger frames keep the table
+ * kernel, whose cost does not grow with the bounding box). Results are identical either way. */
+int s2d_point_votes_sized(const s2d_video_desc* descs, int nvideos, int max_T, int max_Nm, int max_P,
+                          int vec4_ok, int64_t total_rows, const int32_t* rowinfo, const int32_t* vidinfo,
+                          int32_t* work, const void* label_tmaps, int64_t max_frame_pixels, int32_t* hits, int32_t* uniq,
+                          void* stream);
 
 /* K3d. Appearance events of visibility curves V f32 [N][T] (device): moving average of odd length
  * smoothing_window (reflect padding), `>= thresh`, morphological opening with window

@@ -53,6 +53,7 @@ SIGNATURES = {
     "s2d_point_votes_work_ints": [_L, C.POINTER(C.c_int64)],
     "s2d_point_votes_tmaps": [_P, _I, _P],
     "s2d_point_votes": [_P, _I, _I, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P],
+    "s2d_point_votes_sized": [_P, _I, _I, _I, _I, _I, _L, _P, _P, _P, _P, _L, _P, _P, _P],
     "s2d_appearance_events": [_P, _I, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P],
     "s2d_boolean_visibility": [_P, _L, _F, _P, _P],
     "s2d_rle_work_ints": [_I, _I, _I, _I, C.POINTER(C.c_int64)],

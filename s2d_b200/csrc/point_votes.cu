@@ -1075,168 +1075,173 @@ static int launch_pv_tab(cudaStream_t st, int nsm, const s2d_video_desc* descs, 
 // three wait, five block-wide barriers, a 256-bin output pass by four warps, the table fetch): for a 4096-point tile that
 // is 40 % on top of the per-point work, for a 1024-point tile it is twice the per-point work, and the kernel ends up
 // bound by instruction issue at a third of the HBM roofline (ncu: 3 504 instructions per 8 KB tile). Here a tile belongs
-// to one warp of a one-warp CTA - no block barriers, no idle warps, 21 tiles in flight per SM:
-//   * the lanes read the tile's tracks straight from global memory (streaming 128-bit loads, eight in flight per lane),
-//     round / bound / pack them to (iy << 16) | ix and park the packed points in 4 KB of shared memory;
-//   * the bounding box comes from packed 16-bit min / max and warp reductions;
+// to one warp of a one-warp CTA - no block barriers, no idle warps, ~15 tiles in flight per SM:
+//   * the tile's 8 P bytes of tracks land in the warp's 8 KB of shared memory by one cp.async.bulk (mbarrier), the next
+//     tile's copy is issued as soon as the points sit in registers (32 per lane, packed (iy << 16) | ix);
+//   * the bounding box comes from packed 16-bit min / max and four warp reductions;
 //   * de-duplication is a bitmap of the bounding box in shared memory (4 KB = 32 768 pixels per band, bit index =
-//     dy * bw + dx - band base; larger boxes take several bands, and a group of 256 consecutive points whose index
-//     range misses the band is skipped as a whole), claimed with one shared atomic per point;
-//   * the first point on a pixel reads the pixel's label straight from the label map (L2): sixteen independent loads in
+//     dy * bw + dx - band base; larger boxes take several bands), claimed with one shared atomic per point;
+//   * the first point on a pixel reads the pixel's label straight from the label map (L2): eight independent loads in
 //     flight per lane, and points arrive close to raster order, so a warp-wide load touches a handful of sectors;
 //   * votes are shared-memory reductions into the warp's own 256-bin histogram, which one pass writes to hits / uniq.
-// The loops over point groups are real loops (the body is ~1 k instructions: a first version with all 32 points of a lane
-// unrolled in registers was 56 KB of code and stalled on instruction fetch more than on anything else).
 // Any label id (0..255) and any box size are handled by this one path; results are identical to the other kernels'.
+// Measured (profiles/r02_k2_small_ab_warp_v1.json): 480p videos 31 -> 40 % of the HBM copy peak against the label-table
+// kernel, but 32 -> 25 % on the 720p / 1080p mixture, whose boxes take 2-5 bitmap bands with all 32 points of a lane
+// re-tested per band - the product dispatch therefore uses it for frames of up to PVW_MAX_FRAME_PIXELS only. The kernel is
+// 56 KB of code (all points of a lane unrolled in registers) and its first stall reason is instruction fetch; a version
+// with real loops and synchronous track loads (profiles/r02_k2_small_ab_warp_v2_sync_loads_rejected.json) removed that
+// stall and lost more on the exposed loads.
 // ==========================================================================================
 constexpr int PVW_BITS = 32768;                                     // bitmap bits per band
-constexpr int PVW_CTL_OFF = 1024, PVW_PK_OFF = 1280, PVW_BITS_OFF = PVW_PK_OFF + 4096;
-constexpr int PVW_SMEM_BYTES = PVW_BITS_OFF + PVW_BITS / 8;         // hist 1 KB | control | packed points 4 KB | bitmap 4 KB
+constexpr int64_t PVW_MAX_FRAME_PIXELS = 16 * PVW_BITS;             // product dispatch: frames up to 512 Ki pixels (480 x 854: yes, 720p: no)
+constexpr int PVW_TRK_BYTES = 8192;                                 // 1024 points
+constexpr int PVW_CTL_OFF = 1152, PVW_TRK_OFF = 1536, PVW_BITS_OFF = PVW_TRK_OFF + PVW_TRK_BYTES;
+constexpr int PVW_SMEM_BYTES = PVW_BITS_OFF + PVW_BITS / 8;         // hist 1 KB | dummy 128 B | control | tracks | bitmap
+constexpr int PVW_G = 8;                                            // points per lane whose atomics / loads are issued together
 
-struct PvwCtl { PvTile tinfo[2]; uint32_t gmin[4], gmax1[4]; };
-static_assert(sizeof(PvwCtl) <= PVW_PK_OFF - PVW_CTL_OFF, "PvwCtl must fit its slot");
+struct PvwCtl { uint64_t full; PvTile tinfo[2]; };
+static_assert(sizeof(PvwCtl) <= PVW_TRK_OFF - PVW_CTL_OFF, "PvwCtl must fit its slot");
 
-__global__ void __launch_bounds__(32, 20)
+__global__ void __launch_bounds__(32, 15)
 point_votes_warp_kernel(const s2d_video_desc* __restrict__ descs, const int4* __restrict__ rowplan, int total_rows,
                         int32_t* __restrict__ ctrl, int32_t* __restrict__ hits, int32_t* __restrict__ uniq) {
     extern __shared__ __align__(1024) uint8_t dsm[];
     int* const hist = reinterpret_cast<int*>(dsm);
+    uint32_t* const dummy = reinterpret_cast<uint32_t*>(dsm + 1024);
     PvwCtl& ctl = *reinterpret_cast<PvwCtl*>(dsm + PVW_CTL_OFF);
-    uint2* const pks = reinterpret_cast<uint2*>(dsm + PVW_PK_OFF);           // [row k][lane]: points 64 k + 2 lane, + 1
+    uint8_t* const trk = dsm + PVW_TRK_OFF;
     uint32_t* const bits = reinterpret_cast<uint32_t*>(dsm + PVW_BITS_OFF);
     const int lane = threadIdx.x;
     const int total = ctrl[1];
 
 #pragma unroll
     for (int i = lane; i < S2D_MAX_LABELS; i += 32) hist[i] = 0;
+    dummy[lane] = 0xFFFFFFFFu;
+    if (lane == 0) {
+        mbar_init(&ctl.full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    auto issue_tracks = [&](const PvTile* rec) {        // lane 0: the tile's tracks -> shared memory, completion on `full`
+        const uint32_t bytes = (uint32_t)rec->pad * 8u;
+        mbar_expect_tx(&ctl.full, bytes);
+        bulk_g2s_hint(trk, rec->src, bytes, &ctl.full, l2_policy_evict_first());
+    };
     PvPlan pl;
     pl.pi = pl.pi_end = pl.prow = 0;
     pl.prp = make_int4(0, 0, 0, 0);
     const float* unused_src = nullptr;
     bool more = pv_plan_next(pl, &ctl.tinfo[0], lane, descs, rowplan, total_rows, total, ctrl, hits, uniq, nullptr, &unused_src);
     __syncwarp();
+    if (lane == 0 && more) issue_tracks(&ctl.tinfo[0]);
 
     const uint32_t hist_s = __shfl_sync(0xffffffffu, smem_u32(dsm), 0);
     if (hist_s & 1023u) __trap();                       // a bin's address is formed as (4 * label) | hist_s
     const uint32_t bits_s = hist_s + (uint32_t)PVW_BITS_OFF;
+    const uint32_t dummy_s = hist_s + 1024u + 4u * (uint32_t)lane;
     int scur = 0;
-    while (more) {
+    for (int j = 0;; ++j) {
         const PvTile* ti = &ctl.tinfo[scur];
+        if (!ti->valid) break;
         const uint32_t W = ti->W, H = ti->H;
         if (W > 65535u || H > 65535u) __trap();        // packed 16-bit coordinates (documented limit)
         const int n = ti->n, L = ti->L;
         const uint8_t* const lbl = ti->lbl;
         int32_t* const hout = ti->hout;
         int32_t* const uout = ti->uout;
-        const int4* const gp = reinterpret_cast<const int4*>(ti->src) + lane;
-        S2D_DEV_ASSERT(ti->valid && ti->pad >= 1 && ti->pad <= 1024 && n <= ti->pad);
-        const int kmax = (n + 63) >> 6;                 // rows of 64 points that hold points
+        S2D_DEV_ASSERT(ti->pad >= 1 && ti->pad <= 1024 && n <= ti->pad);
 
-        // ---- phase A: global -> registers (eight 128-bit loads in flight per lane), round / bounds / pack -> shared ----
-        uint32_t mn16 = 0xFFFFFFFFu, mx16 = 0;          // per-halfword min / max + 1 (bounding box in x)
-        uint32_t gmn = 0xFFFFFFFFu, gmx1 = 0;           // numeric min / max + 1 of the packed points of a group of 4 rows
-#pragma unroll 1
-        for (int kb = 0; kb < 16; kb += 8) {
-            if (kb > 0 && kb >= kmax) break;            // the first half always runs: it also plans the next tile
-            int4 v[8];
+        // the next tile's record is prepared while this tile's tracks are in flight (the plan is a chain of global loads)
+        more = pv_plan_next(pl, &ctl.tinfo[scur ^ 1], lane, descs, rowplan, total_rows, total, ctrl, hits, uniq, nullptr, &unused_src);
+
+        // ---- phase A: shared memory -> registers, round / bounds / pack ------------------------------
+        mbar_wait(&ctl.full, (uint32_t)j & 1u);
+        // lane l holds points 64 k + 2 l, + 1 (k = 0..15): rows k < kfull are complete, row kfull may be ragged (n points)
+        const int kfull = n >> 6, kmax = (n + 63) >> 6;
+        uint32_t pk[32];
+        const float4* sp = reinterpret_cast<const float4*>(trk);
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-                v[kk] = make_int4(0, 0, 0, 0);
-                if (2 * ((kb + kk) * 32 + lane) < n) v[kk] = ld_stream(gp + (kb + kk) * 32);     // n <= P, P even: the pair is inside the tile
+        for (int k = 0; k < 16; ++k) {
+            uint32_t a = PV_PK_INVALID, b = PV_PK_INVALID;
+            if (k < kfull) {
+                const float4 v = sp[k * 32 + lane];
+                a = pv_pack(v.x, v.y, W, H);
+                b = pv_pack(v.z, v.w, W, H);
+            } else if (k < kmax) {
+                const float4 v = sp[k * 32 + lane];
+                const int p0 = 2 * (k * 32 + lane);
+                if (p0 < n) a = pv_pack(v.x, v.y, W, H);
+                if (p0 + 1 < n) b = pv_pack(v.z, v.w, W, H);
             }
-            if (kb == 0) {
-                // the next tile's record is prepared while this tile's tracks are in flight (the plan is a chain of loads)
-                more = pv_plan_next(pl, &ctl.tinfo[scur ^ 1], lane, descs, rowplan, total_rows, total, ctrl, hits, uniq, nullptr, &unused_src);
-            }
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-                const int p0 = 2 * ((kb + kk) * 32 + lane);
-                uint32_t a = PV_PK_INVALID, b = PV_PK_INVALID;
-                if (p0 < n) a = pv_pack(__int_as_float(v[kk].x), __int_as_float(v[kk].y), W, H);
-                if (p0 + 1 < n) b = pv_pack(__int_as_float(v[kk].z), __int_as_float(v[kk].w), W, H);
-                pks[(kb + kk) * 32 + lane] = make_uint2(a, b);
-                // an invalid point is (0xFFFF, 0xFFFF) for the min and, after the +0x00010001, (1, 0) for the max: harmless,
-                // any valid point has iy + 1 >= 1
-                mn16 = __vimin3_u16x2(mn16, a, b);
-                mx16 = __vimax3_u16x2(mx16, a + 0x00010001u, b + 0x00010001u);
-                gmn = min(gmn, min(a, b));
-                gmx1 = max(gmx1, max(a + 1u, b + 1u));          // invalid + 1 wraps to 0
-                if ((kk & 3) == 3) {                    // end of a group of 4 rows (256 consecutive points)
-                    const uint32_t rmn = __reduce_min_sync(0xffffffffu, gmn), rmx = __reduce_max_sync(0xffffffffu, gmx1);
-                    if (lane == 0) { ctl.gmin[(kb + kk) >> 2] = rmn; ctl.gmax1[(kb + kk) >> 2] = rmx; }
-                    gmn = 0xFFFFFFFFu; gmx1 = 0;
-                }
-            }
+            pk[2 * k] = a;
+            pk[2 * k + 1] = b;
         }
-        __syncwarp();                                   // packed points and group ranges visible to the warp
+        __syncwarp();                                   // every lane has read the tracks: the region is free again
+        if (lane == 0 && more) issue_tracks(&ctl.tinfo[scur ^ 1]);
 
         // ---- bounding box ------------------------------------------------------------------------------
-        const uint32_t x0 = __reduce_min_sync(0xffffffffu, mn16 & 0xFFFFu), y0 = __reduce_min_sync(0xffffffffu, mn16 >> 16);
-        const uint32_t x1 = __reduce_max_sync(0xffffffffu, mx16 & 0xFFFFu), y1 = __reduce_max_sync(0xffffffffu, mx16 >> 16);
-        if (kmax > 0 && ((y0 << 16) | x0) != 0xFFFFFFFFu) {      // at least one point inside the frame
+        uint32_t mn = 0xFFFFFFFFu, mx = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            // per-halfword min / max; an invalid point is (0xFFFF, 0xFFFF) for the min and, after the
+            // +0x00010001, (1, 0) for the max: harmless, any valid point has iy + 1 >= 1
+            mn = __vimin3_u16x2(mn, pk[2 * k], pk[2 * k + 1]);
+            mx = __vimax3_u16x2(mx, pk[2 * k] + 0x00010001u, pk[2 * k + 1] + 0x00010001u);
+        }
+        const uint32_t x0 = __reduce_min_sync(0xffffffffu, mn & 0xFFFFu), y0 = __reduce_min_sync(0xffffffffu, mn >> 16);
+        const uint32_t x1 = __reduce_max_sync(0xffffffffu, mx & 0xFFFFu), y1 = __reduce_max_sync(0xffffffffu, mx >> 16);
+        if (((y0 << 16) | x0) != 0xFFFFFFFFu) {         // at least one point inside the frame
             const uint32_t bw = x1 - x0, bh = y1 - y0;  // the max holds coordinate + 1
             S2D_DEV_ASSERT(bw >= 1 && bh >= 1 && x0 + bw <= W && y0 + bh <= H);
             const uint32_t pk0 = (y0 << 16) + x0, lim = bh << 16;
             const uint32_t npx = bw * bh;               // <= W * H < 2^32
             const uint32_t org = y0 * W + x0;           // pixel index of the box's corner
-            const int ngroups = (kmax + 3) >> 2;
             for (uint32_t base = 0; base < npx; base += (uint32_t)PVW_BITS) {
+                // an opaque copy of pk0 per band: without it the compiler hoists the 32 points' band-invariant terms (bit
+                // index, label address: ~100 registers) out of this loop, which has one iteration for most tiles
+                uint32_t pk0b;
+                asm volatile("mov.u32 %0, %1;" : "=r"(pk0b) : "r"(pk0));
                 const uint32_t nq = (min((uint32_t)PVW_BITS, npx - base) + 127u) >> 7;      // 128-bit words to clear
                 for (uint32_t i = lane; i < nq; i += 32) reinterpret_cast<uint4*>(bits)[i] = make_uint4(0, 0, 0, 0);
                 __syncwarp();
-                // (1) claim the pixels: bit g * 8 + k of `first` = point k of group g is the first on its pixel
-                uint32_t first = 0;
-#pragma unroll 1
-                for (int g = 0; g < ngroups; ++g) {
-                    // points arrive close to raster order: a group whose range of bit indices misses the band is skipped
-                    const uint32_t lo = ctl.gmin[g] - pk0, hi1 = ctl.gmax1[g];
-                    if (hi1 == 0u) continue;            // no point of the group inside the frame
-                    const uint32_t hi = hi1 - 1u - pk0;
-                    const uint32_t lo_lin = (lo >> 16) * bw + (lo & 0xFFFFu), hi_lin = (hi >> 16) * bw + (hi & 0xFFFFu);    // monotone in the packed value
-                    S2D_DEV_ASSERT(lo_lin <= hi_lin && hi_lin < npx);
-                    if (hi_lin < base || (lo_lin >= base && lo_lin - base >= (uint32_t)PVW_BITS)) continue;
-                    uint32_t fg = 0;
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const uint2 pp = pks[(4 * g + r) * 32 + lane];
+                for (int g = 0; g < 32; g += PVW_G) {
+                    if (g / 2 >= kmax) break;           // no points beyond (uniform)
+                    // (1) claim the pixels: points outside the frame / the band hit a per-lane dummy word that is all ones
+                    uint32_t first = 0;
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const uint32_t e = (c ? pp.y : pp.x) - pk0;            // (dy << 16) + dx of a valid point
-                            const uint32_t lin = (e >> 16) * bw + (e & 0xFFFFu) - base;
-                            S2D_DEV_ASSERT(!(e < lim) || (e & 0xFFFFu) < bw);
-                            if ((e < lim) && (lin < (uint32_t)PVW_BITS)) {
-                                const uint32_t m = 1u << (lin & 31u);
-                                uint32_t old;
-                                asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(bits_s + ((lin >> 5) << 2)), "r"(m) : "memory");
-                                if (!(old & m)) fg |= 1u << (2 * r + c);
-                            }
+                    for (int k = 0; k < PVW_G; ++k) {
+                        const uint32_t e = pk[g + k] - pk0b;                   // (dy << 16) + dx of a valid point
+                        const uint32_t lin = (e >> 16) * bw + (e & 0xFFFFu) - base;
+                        const bool ok = (e < lim) && (lin < (uint32_t)PVW_BITS);
+                        S2D_DEV_ASSERT(!(e < lim) || (e & 0xFFFFu) < bw);
+                        const uint32_t m = 1u << (lin & 31u);
+                        const uint32_t addr = ok ? bits_s + ((lin >> 5) << 2) : dummy_s;
+                        uint32_t old;
+                        asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(m) : "memory");
+                        first |= ((old & m) ? 0u : 1u) << k;
+                    }
+                    // (2) labels of the first points: independent loads, all issued before the first is used
+                    uint32_t lab[PVW_G];
+#pragma unroll
+                    for (int k = 0; k < PVW_G; ++k) {
+                        lab[k] = 0;
+                        if ((first >> k) & 1u) {
+                            const uint32_t e = pk[g + k] - pk0b;
+                            S2D_DEV_ASSERT((e >> 16) < bh && (e & 0xFFFFu) < bw);
+                            lab[k] = __ldg(lbl + (size_t)(org + (e >> 16) * W + (e & 0xFFFFu)));
                         }
                     }
-                    first |= fg << (8 * g);
-                }
-                // (2) labels of the first points, sixteen independent loads per lane, and the votes
-#pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t f16 = (first >> (16 * h)) & 0xFFFFu;
-                    if (!__any_sync(0xffffffffu, f16 != 0u)) continue;
-                    uint32_t lab[16];
+                    // (3) votes
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        lab[2 * r] = lab[2 * r + 1] = 0;
-                        if ((f16 >> (2 * r)) & 3u) {
-                            const uint2 pp = pks[(8 * h + r) * 32 + lane];
-                            const uint32_t e0 = pp.x - pk0, e1 = pp.y - pk0;
-                            if ((f16 >> (2 * r)) & 1u) lab[2 * r] = __ldg(lbl + (size_t)(org + (e0 >> 16) * W + (e0 & 0xFFFFu)));
-                            if ((f16 >> (2 * r + 1)) & 1u) lab[2 * r + 1] = __ldg(lbl + (size_t)(org + (e1 >> 16) * W + (e1 & 0xFFFFu)));
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 16; ++k)
-                        if ((f16 >> k) & 1u) asm volatile("red.shared.add.u32 [%0], 1;" :: "r"((lab[k] << 2) | hist_s) : "memory");
+                    for (int k = 0; k < PVW_G; ++k)
+                        if ((first >> k) & 1u) asm volatile("red.shared.add.u32 [%0], 1;" :: "r"((lab[k] << 2) | hist_s) : "memory");
                 }
-                __syncwarp();                           // votes / claims done before the bitmap is cleared or the histogram read
+                if (base + (uint32_t)PVW_BITS < npx) __syncwarp();             // the next band clears the bitmap
             }
         }
+        __syncwarp();                                   // histogram complete
 
         // ---- output: hits[q, t, :] and uniq[q, t] = number of distinct pixels --------------------------------
         int sum = 0;
@@ -1249,7 +1254,7 @@ point_votes_warp_kernel(const s2d_video_desc* __restrict__ descs, const int4* __
         }
         sum = __reduce_add_sync(0xffffffffu, sum);
         if (lane == 0) *uout = sum;
-        __syncwarp();                                   // histogram resets and the next record before the next tile
+        __syncwarp();                                   // histogram resets before the next tile's votes
         scur ^= 1;
     }
 }
@@ -1304,9 +1309,9 @@ static int g_pv_variant = 0;
 
 extern "C" int s2d_point_votes_variant(int variant) {
 #ifdef S2D_EXPERIMENTS
-    S2D_CHECK_ARG(variant >= 0 && variant <= 3, "s2d_point_votes_variant: %d not in {0 product dispatch, 1 bitmap, 2 one CTA per tile, 3 label table for every P}", variant);
+    S2D_CHECK_ARG(variant >= 0 && variant <= 4, "s2d_point_votes_variant: %d not in {0 product dispatch, 1 bitmap, 2 one CTA per tile, 3 label table for every P, 4 one warp per tile for every frame size}", variant);
 #else
-    S2D_CHECK_ARG(variant == 0 || variant == 2 || variant == 3, "s2d_point_votes_variant: %d not in {0 product dispatch, 2 one CTA per tile, 3 label table for every P} "
+    S2D_CHECK_ARG(variant == 0 || variant == 2 || variant == 3 || variant == 4, "s2d_point_votes_variant: %d not in {0 product dispatch, 2 one CTA per tile, 3 label table for every P, 4 one warp per tile for every frame size} "
                   "(1, the superseded bitmap kernel, exists only in the experiments build: make -C s2d_b200/csrc exp)", variant);
 #endif
     g_pv_variant = variant;
@@ -1371,6 +1376,14 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
                                int vec4_ok, int64_t total_rows, const int32_t* rowinfo,
                                const int32_t* vidinfo, int32_t* work, const void* label_tmaps,
                                int32_t* hits, int32_t* uniq, void* stream) {
+    return s2d_point_votes_sized(descs, nvideos, max_T, max_Nm, max_P, vec4_ok, total_rows, rowinfo, vidinfo, work, label_tmaps,
+                                 0, hits, uniq, stream);
+}
+
+extern "C" int s2d_point_votes_sized(const s2d_video_desc* descs, int nvideos, int max_T, int max_Nm, int max_P,
+                                     int vec4_ok, int64_t total_rows, const int32_t* rowinfo,
+                                     const int32_t* vidinfo, int32_t* work, const void* label_tmaps,
+                                     int64_t max_frame_pixels, int32_t* hits, int32_t* uniq, void* stream) {
     S2D_ENTER(stream);
     S2D_CHECK_ARG((((uintptr_t)label_tmaps) & 63) == 0, "s2d_point_votes: label_tmaps must be 64-byte aligned");
     const uint8_t* tm = static_cast<const uint8_t*>(label_tmaps);
@@ -1380,8 +1393,10 @@ extern "C" int s2d_point_votes(const s2d_video_desc* descs, int nvideos, int max
     S2D_CHECK_ARG(max_P >= 1 && max_P <= 32768, "s2d_point_votes: P=%d not in [1, 32768]", max_P);
     cudaStream_t st = (cudaStream_t)stream;
     const bool v4 = vec4_ok != 0;
-    const bool warp_tiles = g_pv_variant != 3;      // variant 3: the label-table kernel also for tiles of <= 1024 points
-    const int variant = g_pv_variant == 3 ? 0 : g_pv_variant;
+    // tiles of <= 1024 points: one warp per tile when the frames are small enough for its bitmap bands (variant 4: always,
+    // variant 3: never - the label-table kernel for every P)
+    const bool warp_tiles = g_pv_variant == 4 || (g_pv_variant == 0 && max_frame_pixels > 0 && max_frame_pixels <= PVW_MAX_FRAME_PIXELS);
+    const int variant = (g_pv_variant == 3 || g_pv_variant == 4) ? 0 : g_pv_variant;
     if (variant != 2 && v4 && work && max_P <= (variant == 0 ? 16384 : 8192) && total_rows > 0 && total_rows <= 2147483647LL) {
         // persistent TMA path
         S2D_CHECK_ARG((((uintptr_t)work) & 15) == 0, "s2d_point_votes: work must be 16-byte aligned");

@@ -250,9 +250,9 @@ class Batch:
                  p(self.rsbits), p(self.rebits), p(self.winbits), p(self.rowinfo), p(self.vidinfo),
                  p(self.clusterinfo), st)
         if "D" in stages:
-            call("point_votes", 3 if self.use_tma else 1, "s2d_point_votes", d, nv, self.max_T, self.max_Nm, self.max_P,
+            call("point_votes", 3 if self.use_tma else 1, "s2d_point_votes_sized", d, nv, self.max_T, self.max_Nm, self.max_P,
                  self.vec4, self.total_rows, p(self.rowinfo), p(self.vidinfo),
-                 p(self.pvwork) if self.use_tma else None, p(self.pvtmaps), p(self.hits), p(self.uniq), st)
+                 p(self.pvwork) if self.use_tma else None, p(self.pvtmaps), self.max_npix, p(self.hits), p(self.uniq), st)
             call("select", 1, "s2d_select", d, nv, self.max_Nm, self.total_mw, p(self.hits), p(self.uniq),
                  p(self.gid_of), p(self.rowinfo), params.matching_threshold, params.one2x_iou,
                  params.one2x_frames, p(self.mbits), p(self.one2x), p(self.nmatch), p(self.vidinfo), st)
@@ -289,9 +289,9 @@ class Batch:
     def votes_all(self, stream=None):
         """K2 over every (query, frame) of every video, ignoring candidates/status (tests, bench)."""
         st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
-        _lib.call("s2d_point_votes", self.descs.data_ptr(), self.nv, self.max_T, self.max_Nm, self.max_P, self.vec4,
+        _lib.call("s2d_point_votes_sized", self.descs.data_ptr(), self.nv, self.max_T, self.max_Nm, self.max_P, self.vec4,
                   self.total_rows, None, None, self.pvwork.data_ptr() if self.use_tma else None,
-                  self.pvtmaps.data_ptr() if self.pvtmaps is not None else None,
+                  self.pvtmaps.data_ptr() if self.pvtmaps is not None else None, self.max_npix,
                   self.hits.data_ptr(), self.uniq.data_ptr(), st)
 
     # ------------------------------------------------------------------ results

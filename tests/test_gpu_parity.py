@@ -92,7 +92,7 @@ def test_point_votes_all_pairs_vs_oracle(golden_case):
         assert np.array_equal(h, hits[q]), (name, q)
 
 
-@pytest.fixture(params=[0, 1, 2, 3], ids=["product", "bitmap", "cta_per_tile", "table_any_P"])
+@pytest.fixture(params=[0, 1, 2, 3, 4], ids=["product", "bitmap", "cta_per_tile", "table_any_P", "warp_any_frame"])
 def pv_variant(request):
     """run a test once per point-votes kernel variant (include/s2d_b200.h: s2d_point_votes_variant)"""
     from s2d_b200 import _lib

@@ -1,8 +1,7 @@
 """Host model of the one-warp-per-tile votes kernel's integer arithmetic (s2d_b200/csrc/point_votes.cu,
 point_votes_warp_kernel: tiles of <= 1024 points): packed coordinates, bounding box from packed 16-bit min / max, the
 bitmap of the box in bands of PVW_BITS pixels (bit = dy * bw + dx - base in wrapping unsigned arithmetic, `e < lim` as the
-"inside the frame" test), groups of 256 consecutive points skipped when their range of bit indices misses the band (numeric
-min / max of the packed values: the bit index is monotone in them), claim of the first point per pixel, label address org + dy * W + dx, ragged last row of points
+"inside the frame" test), claim of the first point per pixel, label address org + dy * W + dx, ragged last row of points
 (n < P). The model follows the kernel statement by statement in uint32 arithmetic and is compared with the oracle's sparse
 votes (oracle/keymask_oracle.py::point_votes = cotracker_matching.py:453-503, 640-662)."""
 import numpy as np
@@ -47,41 +46,26 @@ def tile_votes_warp_model(tracks, label, n=None, bits_per_band=32768):
     assert bw >= 1 and bh >= 1 and x0 + bw <= W and y0 + bh <= H
     pk0, lim = ((y0 << 16) + x0) & U32, (bh << 16) & U32
     npx, org = bw * bh, y0 * W + x0
-    # numeric min / max + 1 of the packed points per group of 4 rows (256 consecutive points); invalid + 1 wraps to 0
-    ngroups = (kmax + 3) >> 2
-    rows = pk.reshape(16, 64)
-    gmin = [int(rows[4 * g:4 * g + 4].min()) for g in range(4)]
-    gmax1 = [int(((rows[4 * g:4 * g + 4] + 1) & U32).max()) for g in range(4)]
     bands = 0
     for base in range(0, npx, bits_per_band):
         bands += 1
         bits = np.zeros(bits_per_band // 32, np.uint32)
-        first = np.zeros(1024, bool)
-        for g in range(ngroups):                        # (1) claims, group by group; groups that miss the band are skipped
-            if gmax1[g] == 0:
-                continue
-            lo, hi = (gmin[g] - pk0) & U32, (gmax1[g] - 1 - pk0) & U32
-            lo_lin, hi_lin = (lo >> 16) * bw + (lo & 0xFFFF), (hi >> 16) * bw + (hi & 0xFFFF)
-            assert lo_lin <= hi_lin < npx
-            if hi_lin < base or (lo_lin >= base and lo_lin - base >= bits_per_band):
-                continue
+        for g in range(0, 32, 8):                       # the kernel's group order: rows g / 2 .. g / 2 + 3 of every lane
+            if g // 2 >= kmax:
+                break
             for lane in range(32):
-                for r in range(4):
-                    for c in range(2):
-                        i = 2 * ((4 * g + r) * 32 + lane) + c
-                        e = (int(pk[i]) - pk0) & U32
-                        lin = ((e >> 16) * bw + (e & 0xFFFF) - base) & U32
-                        if not (e < lim and lin < bits_per_band):
-                            continue
-                        assert (e & 0xFFFF) < bw
-                        m = np.uint32(1 << (lin & 31))
-                        if bits[lin >> 5] & m:
-                            continue
-                        bits[lin >> 5] |= m
-                        first[i] = True
-        for i in np.nonzero(first)[0]:                  # (2) labels of the first points, votes
-            e = (int(pk[i]) - pk0) & U32
-            hist[int(flat[org + (e >> 16) * W + (e & 0xFFFF)])] += 1
+                for k in range(g, g + 8):
+                    p = int(pk[2 * ((k // 2) * 32 + lane) + (k & 1)])
+                    e = (p - pk0) & U32
+                    lin = ((e >> 16) * bw + (e & 0xFFFF) - base) & U32
+                    if not (e < lim and lin < bits_per_band):
+                        continue
+                    assert (e & 0xFFFF) < bw
+                    m = np.uint32(1 << (lin & 31))
+                    if bits[lin >> 5] & m:
+                        continue
+                    bits[lin >> 5] |= m
+                    hist[int(flat[org + (e >> 16) * W + (e & 0xFFFF)])] += 1
     return hist, int(hist.sum()), bands
 
 

@@ -1,7 +1,7 @@
 """A/B of the votes kernel on sparse tiles (P <= 1024 tracked points per query) in ONE process on one GPU:
 python tools/r02_k2_small_ab.py > gpurun_out/r02_k2_small_ab.json
 Per workload (the C1 video, a 32-video slice of the C4 mixture, three 1 k-track points of the C5 sweep) and per kernel
-(s2d_point_votes_variant: 0 = product dispatch = one warp per tile, 3 = label-table kernel, 2 = one CTA per tile):
+(s2d_point_votes_variant: 4 = one warp per tile for every frame size, 3 = label-table kernel, 2 = one CTA per tile):
 K2 time, fraction of the measured HBM copy peak, frames/s, and the digest of the results (must not depend on the kernel)."""
 import json
 import os
@@ -31,7 +31,7 @@ def main():
         "c5_m50_t32": wl.c5_specs(50, 1024, 32),
         "c5_m100_t64": wl.c5_specs(100, 1024, 64),
     }
-    configs = [("table", 3), ("warp_per_tile", 0), ("cta_per_tile", 2)]
+    configs = [("table", 3), ("warp_per_tile", 4), ("cta_per_tile", 2)]
     out = {"peak_gbs": PEAK, "rows": []}
     runner = wl.DeviceRunner(dev, Params())
     runner.run_list([wl.VideoSpec(f"warm{i}", 7 + i, 16, 240, 426, 8, 1024) for i in range(2)])
