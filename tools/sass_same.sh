@@ -4,6 +4,7 @@
 # s2d_version() is unchanged, and the version is only kept when this check says SAME for the benchmarked kernel:
 #   tools/sass_same.sh 7d5f9d4 '_ZN3s2d22point_votes_tab_kernelILi128ELi32ELi6ELb0ELi2EEEvPK14s2d_video_descPK4int4iPiS7_S7_PKh'
 set -e
+trap 'rm -rf "$tmp"' EXIT
 commit=$1; fn=$2; root=$(cd "$(dirname "$0")/.." && pwd); tmp=$(mktemp -d)
 mkdir -p $tmp/inc
 for f in point_votes.cu common.cuh dbscan.cuh; do git -C $root show $commit:s2d_b200/csrc/$f > $tmp/$f; done
